@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- queries/sec of the dense-retrieval hot path at 1M x 1536, top-100 (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (exact oracle port /
+                                                             # hnswlib-equivalent HNSW), rank 0 only
+
+A step = one batch of B query vectors through cmw_search (exact mode: tensor-core / scan filter,
+fp64 rescoring, certificate) over the HBM-resident corpus.  `value` is device-resident throughput
+(CUDA events on the launching stream); `e2e` goes through the host-buffer C-ABI call
+(cmw_search_host: pinned staging, H2D, kernels, D2H, sync).  N > 1: one process per GPU
+(torchrun), the corpus replicated and the query batch sharded (no data-path collective), or
+`--shard rows` for the row-sharded corpus with an NCCL all-gather + merge kernel.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "queries/sec at 1Mx1536 top-100"
+UNIT = "queries/s"
+SEED = 20261018
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000, help="corpus rows per replica (or per shard)")
+    ap.add_argument("--dim", type=int, default=1536)
+    ap.add_argument("--batch", type=int, default=4096, help="query vectors per step per GPU")
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--mode", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--algo", default="auto")
+    ap.add_argument("--shard", default="queries", choices=["queries", "rows"])
+    ap.add_argument("--no-f32", action="store_true", help="bf16 tiles only (rows-sharded 200M config)")
+    ap.add_argument("--cpu-queries", type=int, default=16, help="queries in the bounded CPU sample")
+    ap.add_argument("--skip-b1", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md: sample nvidia-smi DURING the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows: list[list[str]] = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()  # the exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm
+# ------------------------------------------------------------------------------------------------
+def host_corpus(rows: int, dim: int) -> np.ndarray:
+    import synth
+
+    return synth.make_corpus(rows, dim, seed=SEED, ties=False)
+
+
+def cpu_exact_sample(corpus: np.ndarray, queries: np.ndarray, k: int, steps: int = 1):
+    """Times the oracle's C port (exact fp64 top-k, OpenMP over all host threads)."""
+    from oracle.cport import exact_topk_c, num_threads
+
+    exact_topk_c(corpus[:4096], queries[:1], k)  # page in / thread pool warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        exact_topk_c(corpus, queries, k)
+    dt = time.perf_counter() - t0
+    return queries.shape[0] * steps / dt, dt, num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The
+    reference delegates the arithmetic to chromadb/hnswlib (not installable here); the timed code is
+    the oracle's exact C port (all host threads), on a bounded sample of queries per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import synth
+
+    corpus = host_corpus(args.rows, args.dim)
+    nq = max(1, args.cpu_queries)
+    q, _ = synth.make_queries(corpus, nq, seed=7, tie_probe=False)
+    from oracle.cport import exact_topk_c, num_threads
+
+    for _ in range(max(1, min(args.warmup, 1))):
+        exact_topk_c(corpus, q[:2], args.k)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        exact_topk_c(corpus, q, args.k)
+    dt = time.perf_counter() - t0
+    qps = nq * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.rows}x{args.dim} fp32 corpus, top-{args.k} exact cosine, "
+                               f"{nq} queries per step (bounded sample of the {args.batch}-query batch)"},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": num_threads(), "kind": "port",
+                         "sample": f"{nq} queries x {args.rows} rows per step, exact fp64 brute force "
+                                   "(oracle/c/oracle_topk.c, OpenMP); the reference's own backend "
+                                   "(chromadb 1.3.0 / hnswlib) is not installable offline"},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def build_store(torch, args, device, rank, world):
+    """Synthetic FRIDA-shaped corpus (iid Gaussian rows, L2-normalised), generated on
+    the device block by block and appended through cmw_store_append_f32."""
+    from cmw_rag_b200 import DenseStore
+
+    row_shard = args.shard == "rows" and world > 1
+    id_offset = rank * args.rows if row_shard else 0
+    st = DenseStore(args.dim, args.rows, device=device.index, f32=not args.no_f32, bf16=True,
+                    id_offset=id_offset)
+    g = torch.Generator(device=device).manual_seed(SEED + (rank if row_shard else 0))
+    block = 125_000
+    first = None
+    for lo in range(0, args.rows, block):
+        m = min(block, args.rows - lo)
+        x = torch.randn((m, args.dim), generator=g, device=device, dtype=torch.float32)
+        x = torch.nn.functional.normalize(x, dim=1)
+        st.append(x)
+        if first is None:
+            first = x[: min(m, 65536)].clone()
+        del x
+    return st, first
+
+
+def make_queries(torch, first, batch, dim, device, seed):
+    """75 % planted needles normalise(C[j] + 0.75 g), 25 % random unit vectors."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    noise = torch.nn.functional.normalize(torch.randn((batch, dim), generator=g, device=device), dim=1)
+    j = torch.randint(0, first.shape[0], (batch,), generator=g, device=device)
+    q = first[j] + 0.75 * noise
+    rnd = torch.rand((batch,), generator=g, device=device) < 0.25
+    q[rnd] = noise[rnd]
+    needle = torch.where(rnd, torch.full_like(j, -1), j)
+    return torch.nn.functional.normalize(q, dim=1).contiguous(), needle
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from cmw_rag_b200 import _native as N
+    from cmw_rag_b200 import merge_topk
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    device = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    row_shard = args.shard == "rows" and world > 1
+
+    st, first = build_store(torch, args, device, rank, world)
+    q_seed = 7 if row_shard else 7 + rank  # row shards answer the SAME queries; replicas different ones
+    q, needle = make_queries(torch, first, args.batch, args.dim, device, q_seed)
+    if row_shard:  # every shard must answer the same queries; the needles live in rank 0's shard
+        dist.broadcast(q, 0)
+        dist.broadcast(needle, 0)
+    q_host = q.cpu().numpy()
+    k, B = args.k, args.batch
+
+    def step_device():
+        if not row_shard:
+            return st.search(q, k, mode=args.mode, algo=args.algo)
+        sc, ids, fl, s64 = st.search(q, k, mode=args.mode, algo=args.algo, return_scores64=True)
+        g_s = torch.empty((world,) + s64.shape, dtype=s64.dtype, device=device)
+        g_i = torch.empty((world,) + ids.shape, dtype=ids.dtype, device=device)
+        dist.all_gather_into_tensor(g_s, s64)
+        dist.all_gather_into_tensor(g_i, ids)
+        ms, mi, _ = merge_topk(g_s, g_i, k)
+        return ms, mi, fl
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- warm-up -------------------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        out = step_device()
+    st.search_host(q_host, k, mode=args.mode, algo=args.algo)
+    torch.cuda.synchronize(device)
+    sc0, ids0, fl0 = out
+    ids0_h = ids0.cpu().numpy()
+    needle_h = needle.cpu().numpy()
+    planted = needle_h >= 0
+    if not row_shard or rank == 0:
+        top1 = ids0_h[:, 0] - (st.id_offset if not row_shard else 0)
+        assert (top1[planted] == needle_h[planted]).all(), "planted needles are not top-1: wrong results"
+    uncertified = int(fl0.sum().item())
+
+    # ---- timed region: device-resident ------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    N.profile_enable(True)
+    launches0 = N.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = N.kernel_launches() - launches0
+    prof = N.profile_read()
+    N.profile_enable(False)
+
+    # ---- timed region: end to end through the host-buffer C ABI ------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st.search_host(q_host, k, mode=args.mode, algo=args.algo)
+    torch.cuda.synchronize(device)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- batch-1 leg (HBM-bound regime) -------------------------------------------------------
+    b1 = None
+    if not args.skip_b1 and not row_shard and rank == 0 and not args.no_f32:
+        q1 = q[:1].contiguous()
+        for _ in range(5):
+            st.search(q1, k, mode=args.mode)
+        torch.cuda.synchronize(device)
+        N.profile_enable(True)
+        iters = 50
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+        ev[0].record()
+        for i in range(iters):
+            st.search(q1, k, mode=args.mode)
+            ev[i + 1].record()
+        torch.cuda.synchronize(device)
+        lat = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(iters)])
+        prof1 = N.profile_read()
+        N.profile_enable(False)
+        elt = 4 if args.mode == "f32" else 2
+        bytes_scan = args.rows * (args.dim * elt + 4)
+        filt_ms = prof1["filter"][0] / iters
+        peaks = measured_peaks()
+        t_host0 = time.perf_counter()
+        for _ in range(20):
+            st.search_host(q_host[:1], k, mode=args.mode)
+        host_ms = (time.perf_counter() - t_host0) / 20 * 1e3
+        b1 = {
+            "qps": 1e3 / float(np.mean(lat)), "p50_ms": float(np.median(lat)), "p99_ms": float(np.percentile(lat, 99)),
+            "e2e_qps": 1e3 / host_ms, "e2e_ms": host_ms,
+            "roofline": {"bound": "hbm", "kernel": "scan_kernel (K1)", "achieved": bytes_scan / (filt_ms * 1e-3) / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": bytes_scan / (filt_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "peak_source": peaks["source"], "filter_ms": filt_ms,
+                         "whole_query_frac": bytes_scan / (float(np.mean(lat)) * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+        }
+    if world > 1:
+        dist.barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- report -------------------------------------------------------------------------------
+    peaks = measured_peaks()
+    units = B * args.steps * (1 if row_shard else world)
+    value = units / (dev_ms * 1e-3)
+    e2e = units / (e2e_ms * 1e-3)
+    total_rows = args.rows * (world if row_shard else 1)
+    filt_ms, filt_n = prof["filter"]
+    info = st.info()
+    used_gemm = info["gemm_ready"] and B > int(N.get_option("scan_max_batch")) and args.algo != "scan"
+    if used_gemm:
+        flops = 2.0 * B * args.rows * args.dim * args.steps
+        ach = flops / (filt_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_topk_kernel (K2)", "achieved": ach,
+                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
+                "frac_of_burst": ach / peaks["bf16_tflops"]}
+    else:
+        elt = 2 if args.mode == "bf16" else 4
+        passes = (B + 1) // 2
+        nbytes = float(passes) * args.rows * (args.dim * elt + 4) * args.steps
+        ach = nbytes / (filt_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "scan_kernel (K1)", "achieved": ach, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
+    roof["kernel_ms_per_step"] = filt_ms / args.steps
+    roof["kernel_launches_per_step"] = filt_n / args.steps
+    roof["share_of_step"] = filt_ms / dev_ms
+    phases = {name: {"ms_per_step": ms / args.steps, "launches_per_step": n / args.steps}
+              for name, (ms, n) in prof.items()}
+
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        import synth
+
+        # the same bits the GPU holds: read the first rows back is not enough for a full scan, so the
+        # CPU sample regenerates an equally shaped corpus on the host (seeded) -- same workload size.
+        corpus = host_corpus(args.rows, args.dim)
+        cq, _ = synth.make_queries(corpus, args.cpu_queries, seed=7, tie_probe=False)
+        qps, dt, threads = cpu_exact_sample(corpus, cq, k)
+        cpu = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_queries} queries x {args.rows} rows, exact fp64 brute force "
+                         f"(oracle/c/oracle_topk.c, OpenMP, {dt:.1f} s)"}
+        del corpus
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 filter + f64 rescoring" if (used_gemm and args.mode == "f32") else
+                 ("f32 filter + f64 rescoring" if args.mode == "f32" else "bf16"),
+        "data": "synthetic",
+        "config": {
+            "workload": f"{total_rows}x{args.dim} {'fp32+bf16' if not args.no_f32 else 'bf16'} corpus, "
+                        f"query batch {B} per GPU, top-{k} {'exact' if args.mode == 'f32' else 'bf16'} cosine",
+            "parallelism": ("single GPU" if world == 1 else
+                            (f"corpus row-sharded over {world} GPUs, NCCL all-gather + merge kernel" if row_shard
+                             else f"corpus replicated, query batch sharded over {world} GPUs (no collective)")),
+            "l2": "inputs larger than L2 (corpus tiles >= 3 GB per pass vs 126 MB), no flush",
+            "mode": args.mode, "algo": args.algo, "uncertified_queries": uncertified,
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * args.dim * 4,
+                "d2h_bytes_per_step": B * k * 12 + B * 4, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "phases": phases,
+        "cpu_baseline": cpu,
+        "batch1": b1,
+        "store": {"rows": info["rows"], "hbm_bytes": info["hbm_bytes"], "gemm_ready": info["gemm_ready"]},
+    }
+    print(json.dumps(line), flush=True)
+    st.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,401 @@
+// api.cu -- cmw_search / cmw_search_host: orchestration of one batched top-k search.
+//
+// Replaces ChromaStore.similarity_search_async -> collection.query(query_embeddings=[q], n_results=k)
+// (rag_engine/storage/vector_store.py:54-66 of the reference) for a whole batch of query vectors.
+//
+// Pipeline (all stream-ordered, no host synchronisation in cmw_search):
+//   prep queries (fp64 norms, scaled fp32 + bf16 copies)
+//   for each slab of rows (first slab dense, later slabs growing geometrically):
+//       filter kernel (K1 scan or K2 tcgen05 GEMM) admits rows with score >= thr into the pools
+//       compaction keeps the best K' per query and raises thr
+//   F32_EXACT: fp64 rescoring of the K' survivors from the fp32 tiles + final selection + certificate
+//   BF16:      emit the pool's best k
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace cmw {
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WsLayout {
+    size_t qn64, q_f32, q_bf16, pool_scores, pool_ids, pool_cnt, pool_thr, pool_ovf, exact, total;
+    int bpad;
+};
+
+static int pad_batch(int batch) {
+    if (batch <= 16) return 16;
+    if (batch <= 256) return (int)align_up((size_t)batch, 16);
+    return (int)align_up((size_t)batch, 256);
+}
+
+static WsLayout ws_layout(int dim, int batch, int kprime) {
+    WsLayout w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    w.bpad = pad_batch(batch);
+    w.qn64 = take((size_t)batch * sizeof(double));
+    w.q_f32 = take((size_t)batch * dim * sizeof(float));
+    w.q_bf16 = take((size_t)w.bpad * dim * sizeof(__nv_bfloat16));
+    w.pool_scores = take((size_t)batch * kPoolCap * sizeof(float));
+    w.pool_ids = take((size_t)batch * kPoolCap * sizeof(int32_t));
+    w.pool_cnt = take((size_t)batch * sizeof(int32_t));
+    w.pool_thr = take((size_t)batch * sizeof(float));
+    w.pool_ovf = take((size_t)batch * sizeof(int32_t));
+    w.exact = take((size_t)batch * kprime * sizeof(double));
+    w.total = off;
+    return w;
+}
+
+static bool use_gemm(const Store* s, int batch, int mode) {
+    const int algo = mode & 0xff00;
+    if (algo == CMW_ALGO_SCAN) return false;
+    if (!gemm_supported(s)) return false;
+    if (algo == CMW_ALGO_GEMM) return true;
+    return g_opt.gemm_enabled != 0 && batch > (int)g_opt.scan_max_batch;
+}
+
+static int pick_kprime(int k, int mode, bool gemm) {
+    int kp;
+    if (g_opt.kprime > 0) {
+        kp = (int)g_opt.kprime;
+    } else if ((mode & 0xff) == CMW_MODE_BF16) {
+        kp = k;
+    } else if (gemm) {
+        kp = (k + 64 > 2 * k) ? k + 64 : 2 * k;  // bf16 filter: room for the certificate
+    } else {
+        kp = k + 28;  // fp32 filter: the certificate bound is ~1e-6
+    }
+    if (kp < k) kp = k;
+    kp = (int)align_up((size_t)kp, 32);
+    if (kp > kMaxKPrime) kp = kMaxKPrime;
+    return kp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// optional per-phase timing (cmw_profile_enable / cmw_profile_read)
+// ---------------------------------------------------------------------------------------------
+struct PhaseRecord {
+    int phase;
+    cudaEvent_t e0, e1;
+    long long launches;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<PhaseRecord> g_prof_records;
+static std::vector<cudaEvent_t> g_prof_free;
+static double g_prof_ms[4] = {0, 0, 0, 0};
+static long long g_prof_counts[4] = {0, 0, 0, 0};
+
+static cudaEvent_t prof_event() {
+    if (!g_prof_free.empty()) {
+        cudaEvent_t e = g_prof_free.back();
+        g_prof_free.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct PhaseTimer {
+    bool on;
+    PhaseRecord rec;
+    cudaStream_t stream;
+    long long start;
+    PhaseTimer(int phase, cudaStream_t st) : on(g_prof_on), stream(st) {
+        if (!on) return;
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        rec.phase = phase;
+        rec.e0 = prof_event();
+        rec.e1 = prof_event();
+        start = g_kernel_launches.load();
+        cudaEventRecord(rec.e0, stream);
+    }
+    void stop() {
+        if (!on) return;
+        on = false;
+        cudaEventRecord(rec.e1, stream);
+        rec.launches = g_kernel_launches.load() - start;
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof_records.push_back(rec);
+    }
+    ~PhaseTimer() { stop(); }
+};
+
+static void prof_drain() {
+    for (auto& r : g_prof_records) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            g_prof_ms[r.phase] += ms;
+            g_prof_counts[r.phase] += r.launches;
+        }
+        g_prof_free.push_back(r.e0);
+        g_prof_free.push_back(r.e1);
+    }
+    g_prof_records.clear();
+}
+
+}  // namespace cmw
+
+using namespace cmw;
+
+extern "C" {
+
+int cmw_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    prof_drain();
+    for (int i = 0; i < 4; ++i) {
+        g_prof_ms[i] = 0;
+        g_prof_counts[i] = 0;
+    }
+    g_prof_on = on != 0;
+    return 0;
+}
+
+int cmw_profile_read(double* ms, int64_t* counts, int n) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    prof_drain();
+    for (int i = 0; i < n && i < 4; ++i) {
+        if (ms) ms[i] = g_prof_ms[i];
+        if (counts) counts[i] = g_prof_counts[i];
+        g_prof_ms[i] = 0;
+        g_prof_counts[i] = 0;
+    }
+    return 0;
+}
+
+size_t cmw_search_workspace_bytes(const cmw_store* h, int batch, int k, int mode) {
+    if (!h || batch <= 0 || k <= 0) return 0;
+    const Store* s = reinterpret_cast<const Store*>(h);
+    (void)mode;
+    (void)k;
+    // sized for the largest K' so that option changes between the query and the call stay safe
+    return ws_layout(s->dim, batch, kMaxKPrime).total;
+}
+
+int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int metric, int mode,
+               float* out_scores_dev, int64_t* out_ids_dev, double* out_scores64_dev,
+               int32_t* out_flags_dev, void* ws_dev, size_t ws_bytes, void* stream_v) {
+    CMW_REQUIRE(h != nullptr, "cmw_search: store is NULL");
+    Store* s = reinterpret_cast<Store*>(h);
+    if (batch == 0) return 0;
+    CMW_REQUIRE(batch > 0 && queries_dev && out_scores_dev && out_ids_dev, "cmw_search: bad arguments");
+    CMW_REQUIRE(k >= 1 && k <= kMaxKPrime, "cmw_search: k must be in [1, %d], got %d", kMaxKPrime, k);
+    CMW_REQUIRE(metric == CMW_METRIC_COSINE || metric == CMW_METRIC_IP, "cmw_search: unknown metric %d",
+                metric);
+    const int base_mode = mode & 0xff;
+    CMW_REQUIRE(base_mode == CMW_MODE_F32_EXACT || base_mode == CMW_MODE_BF16,
+                "cmw_search: unknown mode %d", base_mode);
+    CMW_REQUIRE((reinterpret_cast<uintptr_t>(queries_dev) & 15) == 0,
+                "cmw_search: queries_dev must be 16-byte aligned");
+    if (base_mode == CMW_MODE_F32_EXACT)
+        CMW_REQUIRE(s->f32 != nullptr, "cmw_search: CMW_MODE_F32_EXACT needs a CMW_STORE_F32 store");
+    if (base_mode == CMW_MODE_BF16)
+        CMW_REQUIRE(s->bf16 != nullptr, "cmw_search: CMW_MODE_BF16 needs a CMW_STORE_BF16 store");
+    CMW_CUDA_OK(cudaSetDevice(s->device));
+    cudaStream_t stream = (cudaStream_t)stream_v;
+
+    const bool gemm = use_gemm(s, batch, mode);
+    if ((mode & 0xff00) == CMW_ALGO_GEMM)
+        CMW_REQUIRE(gemm, "cmw_search: CMW_ALGO_GEMM requested but the tcgen05 path is unavailable "
+                          "(store without bf16 tiles or TMA descriptor)");
+    const int kprime = pick_kprime(k, mode, gemm);
+    const WsLayout w = ws_layout(s->dim, batch, kprime);
+    CMW_REQUIRE(ws_dev != nullptr && ws_bytes >= w.total,
+                "cmw_search: workspace too small (%zu bytes given, %zu needed)", ws_bytes, w.total);
+    CMW_REQUIRE((reinterpret_cast<uintptr_t>(ws_dev) & 255) == 0, "cmw_search: workspace must be 256-byte aligned");
+    uint8_t* ws = reinterpret_cast<uint8_t*>(ws_dev);
+    double* qn64 = reinterpret_cast<double*>(ws + w.qn64);
+    float* q_f32 = reinterpret_cast<float*>(ws + w.q_f32);
+    __nv_bfloat16* q_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + w.q_bf16);
+    Pool pool;
+    pool.scores = reinterpret_cast<float*>(ws + w.pool_scores);
+    pool.ids = reinterpret_cast<int32_t*>(ws + w.pool_ids);
+    pool.cnt = reinterpret_cast<int32_t*>(ws + w.pool_cnt);
+    pool.thr = reinterpret_cast<float*>(ws + w.pool_thr);
+    pool.ovf = reinterpret_cast<int32_t*>(ws + w.pool_ovf);
+    double* exact = reinterpret_cast<double*>(ws + w.exact);
+
+    int rc;
+    {
+        PhaseTimer t(3, stream);
+        if ((rc = launch_prep_queries(queries_dev, batch, w.bpad, s->dim, metric, qn64, q_f32,
+                                      gemm ? q_bf16 : nullptr, stream)))
+            return rc;
+        if ((rc = launch_pool_reset(pool, batch, stream))) return rc;
+    }
+
+    // which tiles the filter reads, and the per-row multiplier that goes with them
+    const bool filter_bf16 = gemm || base_mode == CMW_MODE_BF16;
+    const void* tiles = filter_bf16 ? (const void*)s->bf16 : (const void*)s->f32;
+    const float* row_mul;
+    if (filter_bf16) row_mul = (metric == CMW_METRIC_COSINE) ? s->live : s->norm;  // rows pre-normalised
+    else row_mul = (metric == CMW_METRIC_COSINE) ? s->inv_norm : s->live;          // raw rows
+
+    auto run_filter = [&](int64_t r0, int64_t r1, int dense) -> int {
+        PhaseTimer t(0, stream);
+        if (gemm) {
+            GemmArgs g;
+            g.store = s;
+            g.q_bf16 = q_bf16;
+            g.batch = batch;
+            g.bpad = w.bpad;
+            g.row_mul = row_mul;
+            g.row_begin = r0;
+            g.row_end = r1;
+            g.pool = pool;
+            g.dense = dense;
+            return launch_gemm(g, stream);
+        }
+        for (int b0 = 0; b0 < batch; b0 += 2) {
+            ScanArgs a;
+            a.rows = tiles;
+            a.elt_bytes = filter_bf16 ? 2 : 4;
+            a.dim = s->dim;
+            a.row_mul = row_mul;
+            a.row_begin = r0;
+            a.row_end = r1;
+            a.q = q_f32 + (size_t)b0 * s->dim;
+            a.nq = (batch - b0 >= 2) ? 2 : 1;
+            a.pool.scores = pool.scores + (size_t)b0 * kPoolCap;
+            a.pool.ids = pool.ids + (size_t)b0 * kPoolCap;
+            a.pool.cnt = pool.cnt + b0;
+            a.pool.thr = pool.thr + b0;
+            a.pool.ovf = pool.ovf + b0;
+            a.dense = dense;
+            a.sm_count = s->sm_count;
+            int r = launch_scan(a, stream);
+            if (r) return r;
+        }
+        return 0;
+    };
+
+    auto compact = [&]() -> int {
+        PhaseTimer t(1, stream);
+        return launch_pool_compact(pool, batch, kprime, stream);
+    };
+
+    const int64_t rows = s->rows;
+    double growth = (double)(kPoolCap - kprime) / (3.0 * kprime);
+    if (growth < 1.0) growth = 1.0;
+    if (growth > 8.0) growth = 8.0;
+    int64_t seen = 0;
+    if (rows > 0) {
+        const int64_t slab0 = rows < kDenseSlabRows ? rows : kDenseSlabRows;
+        if ((rc = launch_pool_set_count(pool, batch, (int)slab0, stream))) return rc;
+        if ((rc = run_filter(0, slab0, 1))) return rc;
+        if ((rc = compact())) return rc;
+        seen = slab0;
+        while (seen < rows) {
+            int64_t m, end;
+            if (mode & CMW_SLABS_SAFE) {
+                // a slab can add at most m rows to a pool holding at most kprime: never overflows
+                m = (int64_t)((kPoolCap - kprime) & ~255);
+                end = seen + m;
+                if (end > rows) end = rows;
+            } else {
+                m = (int64_t)((double)seen * growth);
+                m &= ~(int64_t)255;
+                if (m < kDenseSlabRows) m = kDenseSlabRows;
+                end = seen + m;
+                if (end > rows || rows - end < 4096) end = rows;
+            }
+            if ((rc = run_filter(seen, end, 0))) return rc;
+            if ((rc = compact())) return rc;
+            seen = end;
+        }
+    }
+
+    PhaseTimer tfin(2, stream);
+    if (base_mode == CMW_MODE_F32_EXACT) {
+        const double eps = gemm ? g_opt.bf16_eps : g_opt.f32_eps;
+        return launch_rescore_select(s, pool, batch, k, kprime, metric, queries_dev, qn64, eps, exact,
+                                     out_scores_dev, out_ids_dev, out_scores64_dev, out_flags_dev,
+                                     stream);
+    }
+    return launch_pool_emit(s, pool, batch, k, out_scores_dev, out_ids_dev, out_scores64_dev,
+                            out_flags_dev, stream);
+}
+
+int cmw_search_host(cmw_store* h, const float* queries_host, int batch, int k, int metric, int mode,
+                    float* out_scores_host, int64_t* out_ids_host, int32_t* out_flags_host) {
+    CMW_REQUIRE(h != nullptr, "cmw_search_host: store is NULL");
+    Store* s = reinterpret_cast<Store*>(h);
+    if (batch == 0) return 0;
+    CMW_REQUIRE(batch > 0 && queries_host && out_scores_host && out_ids_host,
+                "cmw_search_host: bad arguments");
+    CMW_REQUIRE(k >= 1 && k <= kMaxKPrime, "cmw_search_host: k must be in [1, %d], got %d", kMaxKPrime, k);
+    CMW_CUDA_OK(cudaSetDevice(s->device));
+    cudaStream_t stream;
+    int rc = get_stream(s, &stream);
+    if (rc) return rc;
+    const size_t q_bytes = align_up((size_t)batch * s->dim * sizeof(float), 256);
+    const size_t sc_bytes = align_up((size_t)batch * k * sizeof(float), 256);
+    const size_t id_bytes = align_up((size_t)batch * k * sizeof(int64_t), 256);
+    const size_t fl_bytes = align_up((size_t)batch * sizeof(int32_t), 256);
+    const size_t io_bytes = q_bytes + sc_bytes + id_bytes + fl_bytes;
+    if ((rc = ensure_pinned(s, io_bytes))) return rc;
+    if ((rc = ensure_dev_io(s, io_bytes))) return rc;
+    const size_t ws_bytes = cmw_search_workspace_bytes(h, batch, k, mode);
+    if ((rc = ensure_ws(s, ws_bytes))) return rc;
+    uint8_t* pin = reinterpret_cast<uint8_t*>(s->pinned);
+    uint8_t* dev = reinterpret_cast<uint8_t*>(s->dev_io);
+
+    auto run = [&](const float* q_src, int nb, int run_mode) -> int {
+        memcpy(pin, q_src, (size_t)nb * s->dim * sizeof(float));
+        CMW_CUDA_OK(cudaMemcpyAsync(dev, pin, (size_t)nb * s->dim * sizeof(float),
+                                    cudaMemcpyHostToDevice, stream));
+        int r = cmw_search(h, reinterpret_cast<const float*>(dev), nb, k, metric, run_mode,
+                           reinterpret_cast<float*>(dev + q_bytes),
+                           reinterpret_cast<int64_t*>(dev + q_bytes + sc_bytes), nullptr,
+                           reinterpret_cast<int32_t*>(dev + q_bytes + sc_bytes + id_bytes), s->ws,
+                           s->ws_bytes, stream);
+        if (r) return r;
+        // one D2H for scores + ids + flags (contiguous in dev_io)
+        CMW_CUDA_OK(cudaMemcpyAsync(pin + q_bytes, dev + q_bytes, sc_bytes + id_bytes + fl_bytes,
+                                    cudaMemcpyDeviceToHost, stream));
+        CMW_CUDA_OK(cudaStreamSynchronize(stream));
+        return 0;
+    };
+
+    if ((rc = run(queries_host, batch, mode))) return rc;
+    const float* sc = reinterpret_cast<const float*>(pin + q_bytes);
+    const int64_t* id = reinterpret_cast<const int64_t*>(pin + q_bytes + sc_bytes);
+    const int32_t* fl = reinterpret_cast<const int32_t*>(pin + q_bytes + sc_bytes + id_bytes);
+    memcpy(out_scores_host, sc, (size_t)batch * k * sizeof(float));
+    memcpy(out_ids_host, id, (size_t)batch * k * sizeof(int64_t));
+    std::vector<int> redo;
+    for (int b = 0; b < batch; ++b) {
+        if (out_flags_host) out_flags_host[b] = fl[b];
+        if (fl[b] & CMW_FLAG_UNCERTIFIED) redo.push_back(b);
+    }
+    // A query whose certificate failed (bf16 filter too coarse near the k-th score) or whose pool
+    // overflowed (adversarial row order) is repeated through the fp32 scan filter -- certificate
+    // bound three orders of magnitude tighter -- on the overflow-proof slab schedule.
+    const bool was_safe_scan = (mode & CMW_SLABS_SAFE) && !use_gemm(s, batch, mode);
+    if (!redo.empty() && (mode & 0xff) == CMW_MODE_F32_EXACT && !was_safe_scan) {
+        std::vector<float> q2((size_t)redo.size() * s->dim);
+        for (size_t i = 0; i < redo.size(); ++i)
+            memcpy(q2.data() + i * s->dim, queries_host + (size_t)redo[i] * s->dim,
+                   (size_t)s->dim * sizeof(float));
+        if ((rc = run(q2.data(), (int)redo.size(), CMW_MODE_F32_EXACT | CMW_ALGO_SCAN | CMW_SLABS_SAFE)))
+            return rc;
+        for (size_t i = 0; i < redo.size(); ++i) {
+            const int b = redo[i];
+            memcpy(out_scores_host + (size_t)b * k, sc + i * k, (size_t)k * sizeof(float));
+            memcpy(out_ids_host + (size_t)b * k, id + i * k, (size_t)k * sizeof(int64_t));
+            if (out_flags_host) out_flags_host[b] = fl[i];
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

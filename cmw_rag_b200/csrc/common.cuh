@@ -1,0 +1,245 @@
+// common.cuh -- shared declarations of libcmwdense.so (internal; the public surface is include/cmw_dense.h).
+//
+// Everything here is sm_100a-only device code plus the small amount of host glue the C ABI needs.
+// No torch types, no CPU fallback: a missing CUDA device makes every compute entry point fail.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/cmw_dense.h"
+
+namespace cmw {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_kernel_launches;
+
+#define CMW_CUDA_OK(expr)                                                                        \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            ::cmw::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                  \
+                             cudaGetErrorString(_e));                                            \
+            return -2;                                                                           \
+        }                                                                                        \
+    } while (0)
+
+#define CMW_REQUIRE(cond, ...)                                                                   \
+    do {                                                                                         \
+        if (!(cond)) {                                                                           \
+            ::cmw::set_error(__VA_ARGS__);                                                       \
+            return -1;                                                                           \
+        }                                                                                        \
+    } while (0)
+
+#define CMW_LAUNCHED() (::cmw::g_kernel_launches.fetch_add(1, std::memory_order_relaxed))
+
+// ---------------------------------------------------------------------------------------------
+// candidate pool: the state shared by the filter kernels (K1 scan, K2 GEMM), the compaction
+// kernel and the finalisation kernels.  One pool per query, resident in the caller's workspace.
+//   scores[b][CAP] approximate (filter) scores, ids[b][CAP] LOCAL row numbers, cnt[b] entries
+//   appended so far (may exceed CAP -> overflow), thr[b] admission threshold (score >= thr).
+// ---------------------------------------------------------------------------------------------
+constexpr int kPoolCap = 4096;      // entries per query
+constexpr int kDenseSlabRows = 2048;  // first slab: every row is written (no threshold yet)
+constexpr int kMaxKPrime = 1024;
+
+struct Pool {
+    float* scores;   // [B, kPoolCap]
+    int32_t* ids;    // [B, kPoolCap]
+    int32_t* cnt;    // [B]
+    float* thr;      // [B]
+    int32_t* ovf;    // [B]  1 = some candidate was dropped because the pool was full
+};
+
+// per-row multiplier selector (see store.cu): which array turns a raw dot into the filter score
+enum RowMul : int { ROWMUL_INV_NORM = 0, ROWMUL_NORM = 1, ROWMUL_LIVE = 2 };
+
+struct Store {
+    int device = 0;
+    int dim = 0;
+    uint32_t flags = 0;
+    int sm_count = 0;
+    int64_t capacity = 0;
+    int64_t rows = 0;
+    int64_t dead = 0;
+    int64_t id_offset = 0;
+    size_t hbm_bytes = 0;
+    float* f32 = nullptr;            // [capacity, dim] raw rows (CMW_STORE_F32)
+    __nv_bfloat16* bf16 = nullptr;   // [capacity, dim] L2-normalised rows (CMW_STORE_BF16)
+    float* inv_norm = nullptr;       // [cap4] 1/|c| (0 for a zero row, NaN when tombstoned)
+    float* norm = nullptr;           // [cap4] |c|   (NaN when tombstoned)
+    float* live = nullptr;           // [cap4] 1.0   (NaN when tombstoned)
+    double* norm64 = nullptr;        // [capacity] |c| in fp64
+    int32_t* kb_gid = nullptr;       // [capacity]
+    uint32_t* maxnorm_bits = nullptr;  // device scalar: max |c| as float bits
+    // host-API resources (cmw_search_host / *_host variants)
+    cudaStream_t stream = nullptr;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    void* dev_io = nullptr;
+    size_t dev_io_bytes = 0;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    // TMA descriptor of the bf16 tiles (K2), encoded at create time
+    alignas(64) CUtensorMap tmap_bf16;
+    bool tmap_ok = false;
+};
+
+// options (cmw_set_option)
+struct Options {
+    double bf16_eps = 5e-4;   // certificate bound on |bf16 filter score - exact score| (cosine units)
+    double f32_eps = 4e-6;    // same for the fp32 FMA filter
+    double kprime = 0;        // 0 = automatic
+    double scan_max_batch = 4;  // batches up to this use K1 (scan); larger use K2 (GEMM)
+    double gemm_enabled = 1;
+};
+extern Options g_opt;
+
+// ---------------------------------------------------------------------------------------------
+// launchers implemented in the other translation units (all stream-ordered, return 0 / <0)
+// ---------------------------------------------------------------------------------------------
+struct ScanArgs {
+    const void* rows;      // base pointer of the store's tiles (fp32 or bf16)
+    int elt_bytes;         // 4 or 2
+    int dim;
+    const float* row_mul;  // per-row multiplier (indexed by LOCAL row)
+    int64_t row_begin, row_end;
+    const float* q;        // [nq, dim] prepared fp32 queries
+    int nq;                // 1 or 2
+    Pool pool;             // already offset to the first of the nq queries
+    int dense;             // 1 = write every row at slot (row - row_begin)
+    int sm_count;
+};
+int launch_scan(const ScanArgs& a, cudaStream_t stream);
+
+struct GemmArgs {
+    const Store* store;
+    const __nv_bfloat16* q_bf16;  // [bpad, dim]
+    int batch;                    // real queries
+    int bpad;                     // padded to the N tile
+    const float* row_mul;
+    int64_t row_begin, row_end;
+    Pool pool;
+    int dense;
+};
+int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+bool gemm_supported(const Store* s);
+
+int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64,
+                        float* q_f32, __nv_bfloat16* q_bf16, cudaStream_t stream);
+int launch_pool_reset(Pool pool, int batch, cudaStream_t stream);
+int launch_pool_set_count(Pool pool, int batch, int count, cudaStream_t stream);
+int launch_pool_compact(Pool pool, int batch, int kprime, cudaStream_t stream);
+// exact fp64 rescoring of the pool's first min(cnt, kprime) entries + final (score desc, id asc)
+// selection with the exactness certificate
+int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprime, int metric,
+                          const float* q_raw, const double* qn64, double eps, double* exact_ws,
+                          float* out_scores, int64_t* out_ids, double* out_scores64,
+                          int32_t* out_flags, cudaStream_t stream);
+// bf16 mode: emit the pool's best k as they are
+int launch_pool_emit(const Store* s, Pool pool, int batch, int k, float* out_scores,
+                     int64_t* out_ids, double* out_scores64, int32_t* out_flags,
+                     cudaStream_t stream);
+
+// host-API resources (store.cu)
+int ensure_pinned(Store* s, size_t bytes);
+int ensure_dev_io(Store* s, size_t bytes);
+int ensure_ws(Store* s, size_t bytes);
+int get_stream(Store* s, cudaStream_t* out);
+
+inline int next_pow2_host(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t f32_orderable(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending uint <=> ascending float
+}
+__device__ __forceinline__ float f32_from_orderable(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ uint64_t f64_orderable(double d) {
+    uint64_t u = (uint64_t)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_from_orderable(uint64_t u) {
+    return __longlong_as_double((long long)((u >> 63) ? (u & 0x7fffffffffffffffull) : ~u));
+}
+// key whose ASCENDING order is (score descending, id ascending)
+__device__ __forceinline__ uint64_t desc_key(float score, uint32_t id) {
+    if (score == 0.f) score = 0.f;  // -0.0 and +0.0 are the same score
+    return ((uint64_t)(~f32_orderable(score)) << 32) | (uint64_t)id;
+}
+__device__ __forceinline__ float desc_key_score(uint64_t key) {
+    return f32_from_orderable(~(uint32_t)(key >> 32));
+}
+
+// In-place ascending bitonic sort of n (power of two) 64-bit keys in shared memory by the whole
+// CTA.  Ends with a __syncthreads().
+__device__ __forceinline__ void bitonic_sort_u64(uint64_t* keys, int n) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                uint64_t a = keys[lo], b = keys[hi];
+                if ((a > b) == up) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// (hi, lo) 128-bit keys, ascending lexicographic
+__device__ __forceinline__ void bitonic_sort_u128(uint64_t* hi_keys, uint64_t* lo_keys, int n) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                uint64_t ah = hi_keys[lo], bh = hi_keys[hi];
+                uint64_t al = lo_keys[lo], bl = lo_keys[hi];
+                bool gt = (ah > bh) || (ah == bh && al > bl);
+                if (gt == up) {
+                    hi_keys[lo] = bh;
+                    hi_keys[hi] = ah;
+                    lo_keys[lo] = bl;
+                    lo_keys[hi] = al;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+#endif  // __CUDACC__
+
+}  // namespace cmw

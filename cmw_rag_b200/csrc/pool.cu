@@ -1,0 +1,346 @@
+// pool.cu -- query preparation, candidate-pool maintenance, K3 (exact fp64 rescoring + final
+// deterministic selection with an exactness certificate) and K5 (cross-shard merge).
+//
+// Ordering contract everywhere: score descending, then id ascending (BASELINE.json north_star:
+// "ties broken by lower id"); results are best-first like collection.query() of
+// rag_engine/storage/vector_store.py:59-66.
+#include "common.cuh"
+
+namespace cmw {
+
+// ---------------------------------------------------------------------------------------------
+// query preparation: fp64 norm, scaled fp32 copy (K1), bf16 copy padded with zero rows (K2)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, int metric,
+                    double* __restrict__ qn64, float* __restrict__ q_f32,
+                    __nv_bfloat16* __restrict__ q_bf16) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= bpad) return;
+    const int nvec = dim >> 2;
+    if (b >= batch) {
+        if (q_bf16 != nullptr) {
+            uint2* out = reinterpret_cast<uint2*>(q_bf16 + (size_t)b * dim);
+            for (int c = lane; c < nvec; c += 32) out[c] = make_uint2(0u, 0u);
+        }
+        return;
+    }
+    const float4* in = reinterpret_cast<const float4*>(q + (size_t)b * dim);
+    double acc = 0.0;
+    for (int c = lane; c < nvec; c += 32) {
+        float4 v = __ldg(in + c);
+        acc += (double)v.x * (double)v.x;
+        acc += (double)v.y * (double)v.y;
+        acc += (double)v.z * (double)v.z;
+        acc += (double)v.w * (double)v.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const double nrm = sqrt(acc);
+    const double scale = (metric == CMW_METRIC_COSINE) ? (nrm > 0.0 ? 1.0 / nrm : 0.0) : 1.0;
+    if (lane == 0) qn64[b] = nrm;
+    float4* of = reinterpret_cast<float4*>(q_f32 + (size_t)b * dim);
+    for (int c = lane; c < nvec; c += 32) {
+        float4 v = __ldg(in + c);
+        float4 w = make_float4((float)((double)v.x * scale), (float)((double)v.y * scale),
+                               (float)((double)v.z * scale), (float)((double)v.w * scale));
+        of[c] = w;
+        if (q_bf16 != nullptr) {
+            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(q_bf16 + (size_t)b * dim);
+            ob[2 * c] = __floats2bfloat162_rn(w.x, w.y);
+            ob[2 * c + 1] = __floats2bfloat162_rn(w.z, w.w);
+        }
+    }
+}
+
+int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64,
+                        float* q_f32, __nv_bfloat16* q_bf16, cudaStream_t stream) {
+    const int wpb = 8;
+    prep_queries_kernel<<<(bpad + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, batch, bpad, dim, metric,
+                                                                        qn64, q_f32, q_bf16);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pool maintenance
+// ---------------------------------------------------------------------------------------------
+__global__ void pool_reset_kernel(Pool pool, int batch, int count) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    pool.cnt[b] = count;
+    if (count == 0) {
+        pool.thr[b] = -INFINITY;
+        pool.ovf[b] = 0;
+    }
+}
+
+int launch_pool_reset(Pool pool, int batch, cudaStream_t stream) {
+    pool_reset_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(pool, batch, 0);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_pool_set_count(Pool pool, int batch, int count, cudaStream_t stream) {
+    pool_reset_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(pool, batch, count);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// One CTA per query: sort the pool by (score desc, id asc), keep the best kprime, publish the
+// admission threshold for the next slab.
+__global__ void __launch_bounds__(512) pool_compact_kernel(Pool pool, int kprime) {
+    __shared__ uint64_t keys[kPoolCap];
+    const int b = blockIdx.x;
+    const int n_in = pool.cnt[b];
+    const int n = n_in < kPoolCap ? n_in : kPoolCap;
+    float* sc = pool.scores + (size_t)b * kPoolCap;
+    int32_t* id = pool.ids + (size_t)b * kPoolCap;
+    int m = next_pow2(n < 2 ? 2 : n);
+    for (int i = threadIdx.x; i < m; i += blockDim.x)
+        keys[i] = (i < n) ? desc_key(sc[i], (uint32_t)id[i]) : ~0ull;
+    bitonic_sort_u64(keys, m);
+    const int keep = n < kprime ? n : kprime;
+    for (int i = threadIdx.x; i < keep; i += blockDim.x) {
+        const uint64_t k = keys[i];
+        sc[i] = desc_key_score(k);
+        id[i] = (int32_t)(uint32_t)k;
+    }
+    if (threadIdx.x == 0) {
+        pool.cnt[b] = keep;
+        pool.thr[b] = (n >= kprime) ? desc_key_score(keys[kprime - 1]) : -INFINITY;
+        if (n_in > kPoolCap) pool.ovf[b] = 1;
+    }
+}
+
+int launch_pool_compact(Pool pool, int batch, int kprime, cudaStream_t stream) {
+    pool_compact_kernel<<<batch, 512, 0, stream>>>(pool, kprime);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3a: exact rescoring.  One warp per candidate: fp64 products accumulated in a fixed order
+// (lane-sequential over the row, then an xor butterfly), so bit-identical rows get bit-identical
+// scores and the result does not depend on which filter kernel produced the candidate.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rescore_kernel(const float* __restrict__ f32, const double* __restrict__ norm64,
+               const float* __restrict__ live, int dim, Pool pool, int kprime, int metric,
+               const float* __restrict__ q_raw, const double* __restrict__ qn64,
+               double* __restrict__ exact) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int n = pool.cnt[b] < kprime ? pool.cnt[b] : kprime;
+    if (j >= n) return;
+    const int32_t id = pool.ids[(size_t)b * kPoolCap + j];
+    const float4* row = reinterpret_cast<const float4*>(f32 + (size_t)id * dim);
+    const float4* qv = reinterpret_cast<const float4*>(q_raw + (size_t)b * dim);
+    const int nvec = dim >> 2;
+    double acc = 0.0;
+    for (int c = lane; c < nvec; c += 32) {
+        const float4 v = __ldg(row + c);
+        const float4 w = __ldg(qv + c);
+        acc += (double)v.x * (double)w.x;
+        acc += (double)v.y * (double)w.y;
+        acc += (double)v.z * (double)w.z;
+        acc += (double)v.w * (double)w.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        double s;
+        const float lv = live[id];
+        if (lv != lv) {
+            s = -INFINITY;  // tombstoned row that entered through the dense slab
+        } else if (metric == CMW_METRIC_COSINE) {
+            const double den = qn64[b] * norm64[id];
+            s = den > 0.0 ? acc / den : 0.0;
+        } else {
+            s = acc;
+        }
+        exact[(size_t)b * kprime + j] = s;
+    }
+}
+
+// K3b: per query, sort the rescored candidates by (exact desc, id asc), emit k, certify.
+__global__ void __launch_bounds__(256)
+select_kernel(Pool pool, int k, int kprime, int metric, const double* __restrict__ exact,
+              const double* __restrict__ qn64, const uint32_t* __restrict__ maxnorm_bits, double eps,
+              int64_t id_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+              double* __restrict__ out_scores64, int32_t* __restrict__ out_flags) {
+    extern __shared__ __align__(16) uint8_t sel_smem[];
+    const int b = blockIdx.x;
+    const int n = pool.cnt[b] < kprime ? pool.cnt[b] : kprime;
+    const int m = next_pow2(n < 2 ? 2 : n);
+    uint64_t* hi = reinterpret_cast<uint64_t*>(sel_smem);
+    uint64_t* lo = hi + m;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        if (i < n) {
+            hi[i] = ~f64_orderable(exact[(size_t)b * kprime + i]);
+            lo[i] = (uint64_t)(uint32_t)pool.ids[(size_t)b * kPoolCap + i];
+        } else {
+            hi[i] = ~0ull;
+            lo[i] = ~0ull;
+        }
+    }
+    bitonic_sort_u128(hi, lo, m);
+    const uint64_t neg_inf_key = ~f64_orderable(-INFINITY);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const bool ok = (j < n) && (hi[j] < neg_inf_key);
+        double s = -INFINITY;
+        int64_t id = -1;
+        if (ok) {
+            s = f64_from_orderable(~hi[j]);
+            id = (int64_t)lo[j] + id_offset;
+        }
+        out_scores[(size_t)b * k + j] = (float)s;
+        out_ids[(size_t)b * k + j] = id;
+        if (out_scores64 != nullptr) out_scores64[(size_t)b * k + j] = s;
+    }
+    if (threadIdx.x == 0 && out_flags != nullptr) {
+        int flag = 0;
+        if (pool.ovf[b]) flag = CMW_FLAG_UNCERTIFIED;
+        if (n >= kprime) {
+            // rows outside the pool have filter score <= t, hence exact score <= t + eps
+            const double t = (double)pool.thr[b];
+            double e = eps;
+            if (metric == CMW_METRIC_IP)
+                e *= qn64[b] * (double)__uint_as_float(*maxnorm_bits);
+            const int kk = (k <= n) ? k : n;
+            double kth = -INFINITY;
+            if (kk >= 1 && hi[kk - 1] < neg_inf_key) {
+                kth = f64_from_orderable(~hi[kk - 1]);
+            }
+            if (!(kth > t + e)) flag = CMW_FLAG_UNCERTIFIED;
+        }
+        out_flags[b] = flag;
+    }
+}
+
+int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprime, int metric,
+                          const float* q_raw, const double* qn64, double eps, double* exact_ws,
+                          float* out_scores, int64_t* out_ids, double* out_scores64,
+                          int32_t* out_flags, cudaStream_t stream) {
+    CMW_REQUIRE(s->f32 != nullptr, "CMW_MODE_F32_EXACT needs a store created with CMW_STORE_F32");
+    const int wpb = 8;
+    dim3 grid((kprime + wpb - 1) / wpb, batch);
+    rescore_kernel<<<grid, wpb * 32, 0, stream>>>(s->f32, s->norm64, s->live, s->dim, pool, kprime,
+                                                 metric, q_raw, qn64, exact_ws);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    const size_t smem = (size_t)next_pow2_host(kprime) * 16;
+    select_kernel<<<batch, 256, smem, stream>>>(pool, k, kprime, metric, exact_ws, qn64,
+                                               s->maxnorm_bits, eps, s->id_offset, out_scores,
+                                               out_ids, out_scores64, out_flags);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// bf16 mode: the pool is already sorted by the last compaction; emit its best k.
+__global__ void pool_emit_kernel(Pool pool, int k, int64_t id_offset, float* __restrict__ out_scores,
+                                 int64_t* __restrict__ out_ids, double* __restrict__ out_scores64,
+                                 int32_t* __restrict__ out_flags) {
+    const int b = blockIdx.x;
+    const int n = pool.cnt[b];
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        float s = -INFINITY;
+        int64_t id = -1;
+        if (j < n) {
+            const float v = pool.scores[(size_t)b * kPoolCap + j];
+            if (v > -INFINITY) {
+                s = v;
+                id = (int64_t)pool.ids[(size_t)b * kPoolCap + j] + id_offset;
+            }
+        }
+        out_scores[(size_t)b * k + j] = s;
+        out_ids[(size_t)b * k + j] = id;
+        if (out_scores64 != nullptr) out_scores64[(size_t)b * k + j] = (double)s;
+    }
+    if (threadIdx.x == 0 && out_flags != nullptr) out_flags[b] = pool.ovf[b] ? CMW_FLAG_UNCERTIFIED : 0;
+}
+
+int launch_pool_emit(const Store* s, Pool pool, int batch, int k, float* out_scores,
+                     int64_t* out_ids, double* out_scores64, int32_t* out_flags,
+                     cudaStream_t stream) {
+    pool_emit_kernel<<<batch, 128, 0, stream>>>(pool, k, s->id_offset, out_scores, out_ids,
+                                               out_scores64, out_flags);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: cross-shard merge after the all-gather: G lists of k_in per query -> k_out.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+merge_kernel(const double* __restrict__ scores, const int64_t* __restrict__ ids, int G, int B,
+             int k_in, int k_out, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+             double* __restrict__ out_scores64) {
+    extern __shared__ __align__(16) uint8_t mrg_smem[];
+    const int b = blockIdx.x;
+    const int n = G * k_in;
+    const int m = next_pow2(n < 2 ? 2 : n);
+    uint64_t* hi = reinterpret_cast<uint64_t*>(mrg_smem);
+    uint64_t* lo = hi + m;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        uint64_t h = ~0ull, l = ~0ull;
+        if (i < n) {
+            const int g = i / k_in, j = i - g * k_in;
+            const size_t src = ((size_t)g * B + b) * k_in + j;
+            const int64_t id = ids[src];
+            const double s = scores[src];
+            if (id >= 0 && s == s) {
+                h = ~f64_orderable(s);
+                l = (uint64_t)id;
+            }
+        }
+        hi[i] = h;
+        lo[i] = l;
+    }
+    bitonic_sort_u128(hi, lo, m);
+    for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
+        double s = -INFINITY;
+        int64_t id = -1;
+        if (j < n && !(hi[j] == ~0ull && lo[j] == ~0ull)) {
+            s = f64_from_orderable(~hi[j]);
+            id = (int64_t)lo[j];
+        }
+        out_scores[(size_t)b * k_out + j] = (float)s;
+        out_ids[(size_t)b * k_out + j] = id;
+        if (out_scores64 != nullptr) out_scores64[(size_t)b * k_out + j] = s;
+    }
+}
+
+}  // namespace cmw
+
+using namespace cmw;
+
+extern "C" int cmw_merge_topk(const double* scores_dev, const int64_t* ids_dev, int G, int B, int k_in,
+                              int k_out, float* out_scores_dev, int64_t* out_ids_dev,
+                              double* out_scores64_dev, void* stream) {
+    CMW_REQUIRE(scores_dev && ids_dev && out_scores_dev && out_ids_dev, "cmw_merge_topk: NULL argument");
+    CMW_REQUIRE(G >= 1 && B >= 0 && k_in >= 1 && k_out >= 1, "cmw_merge_topk: bad sizes");
+    if (B == 0) return 0;
+    const int n = G * k_in;
+    CMW_REQUIRE(n <= 8192, "cmw_merge_topk: G*k_in = %d exceeds 8192", n);
+    const size_t smem = (size_t)next_pow2_host(n) * 16;
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        CMW_CUDA_OK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+        smem_set = smem;
+    }
+    merge_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(scores_dev, ids_dev, G, B, k_in, k_out,
+                                                        out_scores_dev, out_ids_dev, out_scores64_dev);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,395 @@
+// store.cu -- the HBM-resident corpus store (K0 ingest, tombstones) and library-wide plumbing.
+//
+// Replaces the Chroma collection the reference creates at rag_engine/storage/vector_store.py:44-52
+// and writes through rag_engine/storage/vector_store.py:68-82 (collection.add) / :102-105 (delete).
+//
+// HBM layout (row-major, one allocation per array, sized for `capacity_rows` up front so device
+// pointers and the TMA descriptor never move):
+//   f32   [cap, D]  raw rows as appended                       (CMW_STORE_F32;  exact rescoring, K1)
+//   bf16  [cap, D]  rows divided by their fp64 norm, RN to bf16 (CMW_STORE_BF16; K1 bf16, K2)
+//   inv_norm/norm/live f32[cap]   per-row multipliers, NaN once tombstoned (a NaN score fails every
+//                                 `score >= thr` test, so dead rows are never admitted)
+//   norm64 f64[cap], kb_gid i32[cap]
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace cmw {
+
+static thread_local std::string t_last_error;
+std::atomic<long long> g_kernel_launches{0};
+Options g_opt;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0: ingest.  One warp per row: fp64 norm (fixed summation order), raw fp32 copy, normalised bf16.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ingest_kernel(const float* __restrict__ src, const int32_t* __restrict__ gid_src, int64_t n, int dim,
+              int64_t row0, float* __restrict__ f32, __nv_bfloat16* __restrict__ bf16,
+              float* __restrict__ inv_norm, float* __restrict__ norm, float* __restrict__ live,
+              double* __restrict__ norm64, int32_t* __restrict__ kb_gid,
+              uint32_t* __restrict__ maxnorm_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int nvec = dim >> 2;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const float4* in = reinterpret_cast<const float4*>(src + r * dim);
+        double acc = 0.0;
+        for (int c = lane; c < nvec; c += 32) {
+            float4 v = __ldg(in + c);
+            acc += (double)v.x * (double)v.x;
+            acc += (double)v.y * (double)v.y;
+            acc += (double)v.z * (double)v.z;
+            acc += (double)v.w * (double)v.w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const double nrm = sqrt(acc);
+        const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+        const int64_t dst = row0 + r;
+        if (f32 != nullptr) {
+            float4* out = reinterpret_cast<float4*>(f32 + dst * dim);
+            for (int c = lane; c < nvec; c += 32) out[c] = __ldg(in + c);
+        }
+        if (bf16 != nullptr) {
+            __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(bf16 + dst * dim);
+            for (int c = lane; c < nvec; c += 32) {
+                float4 v = __ldg(in + c);
+                out[2 * c] = __floats2bfloat162_rn((float)((double)v.x * inv), (float)((double)v.y * inv));
+                out[2 * c + 1] =
+                    __floats2bfloat162_rn((float)((double)v.z * inv), (float)((double)v.w * inv));
+            }
+        }
+        if (lane == 0) {
+            inv_norm[dst] = (float)inv;
+            norm[dst] = (float)nrm;
+            live[dst] = 1.0f;
+            norm64[dst] = nrm;
+            kb_gid[dst] = gid_src != nullptr ? gid_src[r] : -1;
+            atomicMax(maxnorm_bits, __float_as_uint((float)nrm) + 1u);  // +1 ulp: upper bound
+        }
+    }
+}
+
+__global__ void tombstone_kernel(const int64_t* __restrict__ rows, int64_t n, int64_t nrows,
+                                 float* inv_norm, float* norm, float* live,
+                                 unsigned long long* newly_dead) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t r = rows[i];
+    if (r < 0 || r >= nrows) return;
+    const float qnan = __int_as_float(0x7fc00000);
+    // atomic exchange on `live` so that duplicates in `rows` are counted once
+    float old = __uint_as_float(atomicExch(reinterpret_cast<unsigned int*>(live + r), 0x7fc00000u));
+    if (old == old) {
+        inv_norm[r] = qnan;
+        norm[r] = qnan;
+        atomicAdd(newly_dead, 1ull);
+    }
+}
+
+static int ensure_stream(Store* s) {
+    if (s->stream == nullptr) CMW_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    return 0;
+}
+
+int ensure_pinned(Store* s, size_t bytes) {
+    if (s->pinned_bytes >= bytes) return 0;
+    if (s->pinned) cudaFreeHost(s->pinned);
+    s->pinned = nullptr;
+    s->pinned_bytes = 0;
+    CMW_CUDA_OK(cudaMallocHost(&s->pinned, bytes));
+    s->pinned_bytes = bytes;
+    return 0;
+}
+
+int ensure_dev_io(Store* s, size_t bytes) {
+    if (s->dev_io_bytes >= bytes) return 0;
+    if (s->dev_io) cudaFree(s->dev_io);
+    s->dev_io = nullptr;
+    s->dev_io_bytes = 0;
+    CMW_CUDA_OK(cudaMalloc(&s->dev_io, bytes));
+    s->dev_io_bytes = bytes;
+    return 0;
+}
+
+int ensure_ws(Store* s, size_t bytes) {
+    if (s->ws_bytes >= bytes) return 0;
+    if (s->ws) cudaFree(s->ws);
+    s->ws = nullptr;
+    s->ws_bytes = 0;
+    CMW_CUDA_OK(cudaMalloc(&s->ws, bytes));
+    s->ws_bytes = bytes;
+    return 0;
+}
+
+int get_stream(Store* s, cudaStream_t* out) {
+    int rc = ensure_stream(s);
+    if (rc) return rc;
+    *out = s->stream;
+    return 0;
+}
+
+int encode_bf16_tmap(Store* s);  // gemm.cu
+
+}  // namespace cmw
+
+using namespace cmw;
+
+extern "C" {
+
+const char* cmw_last_error(void) { return t_last_error.c_str(); }
+int cmw_abi_version(void) { return CMW_ABI_VERSION; }
+int64_t cmw_kernel_launches(void) { return (int64_t)g_kernel_launches.load(); }
+
+int cmw_set_option(const char* name, double value) {
+    if (!name) return -1;
+    if (!strcmp(name, "bf16_eps")) g_opt.bf16_eps = value;
+    else if (!strcmp(name, "f32_eps")) g_opt.f32_eps = value;
+    else if (!strcmp(name, "kprime")) g_opt.kprime = value;
+    else if (!strcmp(name, "scan_max_batch")) g_opt.scan_max_batch = value;
+    else if (!strcmp(name, "gemm_enabled")) g_opt.gemm_enabled = value;
+    else {
+        set_error("unknown option '%s'", name);
+        return -1;
+    }
+    return 0;
+}
+
+double cmw_get_option(const char* name) {
+    if (!name) return 0.0;
+    if (!strcmp(name, "bf16_eps")) return g_opt.bf16_eps;
+    if (!strcmp(name, "f32_eps")) return g_opt.f32_eps;
+    if (!strcmp(name, "kprime")) return g_opt.kprime;
+    if (!strcmp(name, "scan_max_batch")) return g_opt.scan_max_batch;
+    if (!strcmp(name, "gemm_enabled")) return g_opt.gemm_enabled;
+    if (!strcmp(name, "pool_cap")) return (double)kPoolCap;
+    return 0.0;
+}
+
+int cmw_store_create(int device, int dim, int64_t capacity_rows, uint32_t flags, int64_t id_offset,
+                     cmw_store** out) {
+    CMW_REQUIRE(out != nullptr, "cmw_store_create: out is NULL");
+    *out = nullptr;
+    CMW_REQUIRE(dim >= 8 && dim % 8 == 0 && dim <= 8192,
+                "cmw_store_create: dim must be a multiple of 8 in [8, 8192], got %d", dim);
+    CMW_REQUIRE(capacity_rows > 0 && capacity_rows < (1ll << 31),
+                "cmw_store_create: capacity_rows must be in (0, 2^31), got %lld",
+                (long long)capacity_rows);
+    CMW_REQUIRE((flags & (CMW_STORE_F32 | CMW_STORE_BF16)) != 0,
+                "cmw_store_create: flags must include CMW_STORE_F32 and/or CMW_STORE_BF16");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        set_error("cmw_store_create: no CUDA device (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return -3;
+    }
+    CMW_REQUIRE(device >= 0 && device < ndev, "cmw_store_create: device %d out of range (0..%d)",
+                device, ndev - 1);
+    CMW_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CMW_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    CMW_REQUIRE(prop.major == 10, "cmw_store_create: device %d is sm_%d%d; this library is sm_100a only",
+                device, prop.major, prop.minor);
+    Store* s = new Store();
+    s->device = device;
+    s->dim = dim;
+    s->flags = flags;
+    s->sm_count = prop.multiProcessorCount;
+    s->capacity = capacity_rows;
+    s->id_offset = id_offset;
+    const int64_t cap4 = ((capacity_rows + 3) / 4) * 4 + 4;
+    auto alloc = [&](void** p, size_t bytes) -> int {
+        CMW_CUDA_OK(cudaMalloc(p, bytes));
+        s->hbm_bytes += bytes;
+        return 0;
+    };
+    int rc = 0;
+    const size_t elems = (size_t)capacity_rows * (size_t)dim;
+    if (!rc && (flags & CMW_STORE_F32)) rc = alloc((void**)&s->f32, elems * sizeof(float));
+    if (!rc && (flags & CMW_STORE_BF16)) rc = alloc((void**)&s->bf16, elems * sizeof(__nv_bfloat16));
+    if (!rc) rc = alloc((void**)&s->inv_norm, cap4 * sizeof(float));
+    if (!rc) rc = alloc((void**)&s->norm, cap4 * sizeof(float));
+    if (!rc) rc = alloc((void**)&s->live, cap4 * sizeof(float));
+    if (!rc) rc = alloc((void**)&s->norm64, capacity_rows * sizeof(double));
+    if (!rc) rc = alloc((void**)&s->kb_gid, capacity_rows * sizeof(int32_t));
+    if (!rc) rc = alloc((void**)&s->maxnorm_bits, 256);
+    if (!rc) rc = ensure_stream(s);
+    if (!rc) {
+        cudaError_t e2 = cudaMemsetAsync(s->maxnorm_bits, 0, 256, s->stream);
+        if (e2 == cudaSuccess) e2 = cudaMemsetAsync(s->inv_norm, 0xff, cap4 * sizeof(float), s->stream);
+        if (e2 == cudaSuccess) e2 = cudaMemsetAsync(s->norm, 0xff, cap4 * sizeof(float), s->stream);
+        if (e2 == cudaSuccess) e2 = cudaMemsetAsync(s->live, 0xff, cap4 * sizeof(float), s->stream);
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s->stream);
+        if (e2 != cudaSuccess) {
+            set_error("cmw_store_create: init failed: %s", cudaGetErrorString(e2));
+            rc = -2;
+        }
+    }
+    if (!rc && s->bf16 != nullptr) {
+        // a failed encode only disables K2 (the store stays usable through K1); reported by info
+        s->tmap_ok = (encode_bf16_tmap(s) == 0);
+    }
+    if (rc) {
+        cmw_store_destroy(reinterpret_cast<cmw_store*>(s));
+        return rc;
+    }
+    *out = reinterpret_cast<cmw_store*>(s);
+    return 0;
+}
+
+int cmw_store_destroy(cmw_store* h) {
+    if (!h) return 0;
+    Store* s = reinterpret_cast<Store*>(h);
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->f32);
+    cudaFree(s->bf16);
+    cudaFree(s->inv_norm);
+    cudaFree(s->norm);
+    cudaFree(s->live);
+    cudaFree(s->norm64);
+    cudaFree(s->kb_gid);
+    cudaFree(s->maxnorm_bits);
+    cudaFree(s->dev_io);
+    cudaFree(s->ws);
+    if (s->pinned) cudaFreeHost(s->pinned);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return 0;
+}
+
+int cmw_store_get_info(const cmw_store* h, cmw_store_info* out) {
+    CMW_REQUIRE(h && out, "cmw_store_get_info: NULL argument");
+    const Store* s = reinterpret_cast<const Store*>(h);
+    out->device = s->device;
+    out->dim = s->dim;
+    out->flags = s->flags | (s->tmap_ok ? 0x100u : 0u);
+    out->sm_count = s->sm_count;
+    out->capacity_rows = s->capacity;
+    out->rows = s->rows;
+    out->live_rows = s->rows - s->dead;
+    out->id_offset = s->id_offset;
+    out->hbm_bytes = (int64_t)s->hbm_bytes;
+    return 0;
+}
+
+int cmw_store_append_f32(cmw_store* h, const float* rows_dev, const int32_t* kb_gid_dev, int64_t n,
+                         void* stream) {
+    CMW_REQUIRE(h != nullptr, "cmw_store_append_f32: store is NULL");
+    Store* s = reinterpret_cast<Store*>(h);
+    if (n == 0) return 0;
+    CMW_REQUIRE(n > 0 && rows_dev != nullptr, "cmw_store_append_f32: bad arguments");
+    CMW_REQUIRE(s->rows + n <= s->capacity,
+                "cmw_store_append_f32: %lld rows + %lld exceed the capacity %lld", (long long)s->rows,
+                (long long)n, (long long)s->capacity);
+    CMW_REQUIRE((reinterpret_cast<uintptr_t>(rows_dev) & 15) == 0,
+                "cmw_store_append_f32: rows_dev must be 16-byte aligned");
+    CMW_CUDA_OK(cudaSetDevice(s->device));
+    const int warps_per_block = 8;
+    int64_t blocks = (n + warps_per_block - 1) / warps_per_block;
+    const int64_t max_blocks = (int64_t)s->sm_count * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    ingest_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(
+        rows_dev, kb_gid_dev, n, s->dim, s->rows, s->f32, s->bf16, s->inv_norm, s->norm, s->live,
+        s->norm64, s->kb_gid, s->maxnorm_bits);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    s->rows += n;
+    return 0;
+}
+
+int cmw_store_append_host_f32(cmw_store* h, const float* rows_host, const int32_t* kb_gid_host,
+                              int64_t n) {
+    CMW_REQUIRE(h != nullptr, "cmw_store_append_host_f32: store is NULL");
+    Store* s = reinterpret_cast<Store*>(h);
+    if (n == 0) return 0;
+    CMW_REQUIRE(n > 0 && rows_host != nullptr, "cmw_store_append_host_f32: bad arguments");
+    CMW_REQUIRE(s->rows + n <= s->capacity,
+                "cmw_store_append_host_f32: %lld rows + %lld exceed the capacity %lld",
+                (long long)s->rows, (long long)n, (long long)s->capacity);
+    CMW_CUDA_OK(cudaSetDevice(s->device));
+    int rc = ensure_stream(s);
+    if (rc) return rc;
+    const size_t row_bytes = (size_t)s->dim * sizeof(float);
+    int64_t chunk = (int64_t)((64u << 20) / row_bytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    const size_t gid_off = ((size_t)chunk * row_bytes + 255) & ~(size_t)255;
+    const size_t need = gid_off + (size_t)chunk * sizeof(int32_t);
+    if ((rc = ensure_pinned(s, need))) return rc;
+    if ((rc = ensure_dev_io(s, need))) return rc;
+    for (int64_t lo = 0; lo < n; lo += chunk) {
+        const int64_t m = (n - lo < chunk) ? (n - lo) : chunk;
+        memcpy(s->pinned, rows_host + lo * s->dim, (size_t)m * row_bytes);
+        if (kb_gid_host) memcpy((char*)s->pinned + gid_off, kb_gid_host + lo, (size_t)m * sizeof(int32_t));
+        CMW_CUDA_OK(cudaMemcpyAsync(s->dev_io, s->pinned, (size_t)m * row_bytes, cudaMemcpyHostToDevice,
+                                    s->stream));
+        if (kb_gid_host)
+            CMW_CUDA_OK(cudaMemcpyAsync((char*)s->dev_io + gid_off, (char*)s->pinned + gid_off,
+                                        (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+        rc = cmw_store_append_f32(h, (const float*)s->dev_io,
+                                  kb_gid_host ? (const int32_t*)((char*)s->dev_io + gid_off) : nullptr,
+                                  m, s->stream);
+        if (rc) return rc;
+        CMW_CUDA_OK(cudaStreamSynchronize(s->stream));
+    }
+    return 0;
+}
+
+int cmw_store_tombstone(cmw_store* h, const int64_t* rows_dev, int64_t n, void* stream) {
+    CMW_REQUIRE(h != nullptr, "cmw_store_tombstone: store is NULL");
+    Store* s = reinterpret_cast<Store*>(h);
+    if (n == 0) return 0;
+    CMW_REQUIRE(n > 0 && rows_dev != nullptr, "cmw_store_tombstone: bad arguments");
+    CMW_CUDA_OK(cudaSetDevice(s->device));
+    // the live-row count is host state: count newly dead rows through a device counter
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(s->maxnorm_bits + 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    CMW_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    tombstone_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows_dev, n, s->rows, s->inv_norm,
+                                                                 s->norm, s->live, counter);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    unsigned long long host_count = 0;
+    CMW_CUDA_OK(cudaMemcpyAsync(&host_count, counter, sizeof(host_count), cudaMemcpyDeviceToHost, st));
+    CMW_CUDA_OK(cudaStreamSynchronize(st));
+    s->dead += (int64_t)host_count;
+    return 0;
+}
+
+int cmw_store_tombstone_host(cmw_store* h, const int64_t* rows_host, int64_t n) {
+    CMW_REQUIRE(h != nullptr, "cmw_store_tombstone_host: store is NULL");
+    Store* s = reinterpret_cast<Store*>(h);
+    if (n == 0) return 0;
+    CMW_REQUIRE(n > 0 && rows_host != nullptr, "cmw_store_tombstone_host: bad arguments");
+    CMW_CUDA_OK(cudaSetDevice(s->device));
+    int rc = ensure_stream(s);
+    if (rc) return rc;
+    const size_t bytes = (size_t)n * sizeof(int64_t);
+    if ((rc = ensure_pinned(s, bytes))) return rc;
+    if ((rc = ensure_dev_io(s, bytes))) return rc;
+    memcpy(s->pinned, rows_host, bytes);
+    CMW_CUDA_OK(cudaMemcpyAsync(s->dev_io, s->pinned, bytes, cudaMemcpyHostToDevice, s->stream));
+    return cmw_store_tombstone(h, (const int64_t*)s->dev_io, n, s->stream);
+}
+
+const int32_t* cmw_store_kb_gid_dev(const cmw_store* h) {
+    return h ? reinterpret_cast<const Store*>(h)->kb_gid : nullptr;
+}
+
+}  // extern "C"

@@ -1,0 +1,280 @@
+"""DenseStore -- the Python handle on one HBM-resident corpus shard (``cmw_store`` in the C ABI).
+
+PyTorch is only the hand-off: tensors own query / output / workspace memory, and their
+``data_ptr()`` plus the current CUDA stream are what crosses into ``libcmwdense.so``.  Every
+compute method ends in a kernel of that library; nothing here computes a score or a top-k in
+Python, numpy or torch.
+
+Replaces, on the reference side, the Chroma collection behind
+``rag_engine/storage/vector_store.py:44-66`` (create + query) for whole batches of queries.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native as N
+
+
+@dataclass
+class MultiVectorResult:
+    """Outputs of K4 for Q long queries (arrays padded to P = pre-rerank cap or S*k).
+
+    Mirrors the intermediate values of ``RAGRetriever.retrieve_async``
+    (rag_engine/retrieval/retriever.py:185-242,307): ``cand_*`` is the deduplicated candidate
+    list in first-seen order, ``grp_*`` the kbId groups in first-appearance order and
+    ``grp_order`` their stable score-descending order.
+    """
+
+    cand_ids: "object"
+    cand_scores: "object"
+    cand_best: "object"
+    cand_n: "object"
+    cand_grp: "object"
+    grp_gid: "object"
+    grp_max: "object"
+    grp_cnt: "object"
+    grp_first: "object"
+    grp_order: "object"
+    grp_n: "object"
+
+    def cpu(self) -> "MultiVectorResult":
+        return MultiVectorResult(**{k: v.cpu() for k, v in self.__dict__.items()})
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+class DenseStore:
+    """One corpus shard on one B200.
+
+    ``dim``: embedding width (FRIDA: 1536 -- rag_engine/config/models.yaml:8-11 of the reference).
+    ``capacity``: rows reserved in HBM up front (pointers never move, TMA descriptors stay valid).
+    ``id_offset``: added to row numbers in results (row shards of a multi-GPU corpus).
+    """
+
+    def __init__(self, dim: int, capacity: int, device: int = 0, f32: bool = True, bf16: bool = True,
+                 id_offset: int = 0):
+        lib = N.lib()
+        flags = (N.STORE_F32 if f32 else 0) | (N.STORE_BF16 if bf16 else 0)
+        handle = ctypes.c_void_p()
+        N.check(lib.cmw_store_create(int(device), int(dim), int(capacity), flags, int(id_offset),
+                                     ctypes.byref(handle)), "cmw_store_create")
+        self._h = handle
+        self.dim = int(dim)
+        self.device = int(device)
+        self.capacity = int(capacity)
+        self.id_offset = int(id_offset)
+        self._ws = None
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            N.lib().cmw_store_destroy(self._h)
+            self._h = None
+            self._ws = None
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        st = N.StoreInfo()
+        N.check(N.lib().cmw_store_get_info(self._h, ctypes.byref(st)), "cmw_store_get_info")
+        d = {name: int(getattr(st, name)) for name, _ in N.StoreInfo._fields_}
+        d["gemm_ready"] = bool(d["flags"] & 0x100)
+        return d
+
+    @property
+    def rows(self) -> int:
+        return self.info()["rows"]
+
+    @property
+    def live_rows(self) -> int:
+        return self.info()["live_rows"]
+
+    # -- ingest (K0) ---------------------------------------------------------------------------
+    def append(self, rows, kb_gid=None) -> None:
+        """Append fp32 rows [n, dim] (numpy array -> staged H2D; CUDA tensor -> direct)."""
+        torch = _torch()
+        lib = N.lib()
+        if isinstance(rows, torch.Tensor) and rows.is_cuda:
+            rows = rows.contiguous().to(torch.float32)
+            assert rows.dim() == 2 and rows.shape[1] == self.dim
+            gid_ptr = None
+            if kb_gid is not None:
+                kb_gid = torch.as_tensor(kb_gid, dtype=torch.int32, device=rows.device).contiguous()
+                assert kb_gid.numel() == rows.shape[0]
+                gid_ptr = kb_gid.data_ptr()
+            stream = torch.cuda.current_stream(rows.device).cuda_stream
+            N.check(lib.cmw_store_append_f32(self._h, rows.data_ptr(), gid_ptr, rows.shape[0], stream),
+                    "cmw_store_append_f32")
+            # the kernel reads `rows` asynchronously; keep the caller's tensor alive until it ran
+            torch.cuda.current_stream(rows.device).synchronize()
+            return
+        arr = np.ascontiguousarray(rows.cpu().numpy() if isinstance(rows, torch.Tensor) else rows,
+                                   dtype=np.float32)
+        assert arr.ndim == 2 and arr.shape[1] == self.dim, f"expected [n, {self.dim}], got {arr.shape}"
+        gid_ptr = None
+        if kb_gid is not None:
+            gid = np.ascontiguousarray(kb_gid, dtype=np.int32)
+            assert gid.shape[0] == arr.shape[0]
+            gid_ptr = gid.ctypes.data
+        N.check(lib.cmw_store_append_host_f32(self._h, arr.ctypes.data, gid_ptr, arr.shape[0]),
+                "cmw_store_append_host_f32")
+
+    def tombstone(self, rows) -> None:
+        """Mark LOCAL row numbers dead (never returned again)."""
+        arr = np.ascontiguousarray(rows, dtype=np.int64)
+        if arr.size:
+            N.check(N.lib().cmw_store_tombstone_host(self._h, arr.ctypes.data, arr.size),
+                    "cmw_store_tombstone_host")
+
+    # -- search -----------------------------------------------------------------------------------
+    @staticmethod
+    def _mode(mode, algo) -> int:
+        return N.MODES[mode] | N.ALGOS[algo]
+
+    def _workspace(self, batch: int, k: int, mode: int):
+        torch = _torch()
+        need = int(N.lib().cmw_search_workspace_bytes(self._h, batch, k, mode))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
+        return self._ws
+
+    def search(self, queries, k: int, metric="cosine", mode="f32", algo=None, return_scores64=False):
+        """Batched top-k on the device.  ``queries``: CUDA fp32 tensor [B, dim].
+
+        Returns (scores f32[B,k], ids i64[B,k], flags i32[B]) as CUDA tensors, stream-ordered on
+        the current stream (plus scores64 f64[B,k] when asked: needed for an exact shard merge).
+        """
+        torch = _torch()
+        assert queries.is_cuda and queries.dtype == torch.float32 and queries.dim() == 2
+        assert queries.shape[1] == self.dim
+        q = queries.contiguous()
+        b = q.shape[0]
+        dev = q.device
+        m = self._mode(mode, algo)
+        scores = torch.empty((b, k), dtype=torch.float32, device=dev)
+        ids = torch.empty((b, k), dtype=torch.int64, device=dev)
+        flags = torch.zeros((b,), dtype=torch.int32, device=dev)
+        s64 = torch.empty((b, k), dtype=torch.float64, device=dev) if return_scores64 else None
+        if b == 0:
+            return (scores, ids, flags, s64) if return_scores64 else (scores, ids, flags)
+        ws = self._workspace(b, k, m)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        N.check(
+            N.lib().cmw_search(self._h, q.data_ptr(), b, k, N.METRICS[metric], m, scores.data_ptr(),
+                               ids.data_ptr(), s64.data_ptr() if s64 is not None else None,
+                               flags.data_ptr(), ws.data_ptr(), ws.numel(), stream),
+            "cmw_search",
+        )
+        return (scores, ids, flags, s64) if return_scores64 else (scores, ids, flags)
+
+    def search_host(self, queries, k: int, metric="cosine", mode="f32", algo=None):
+        """End-to-end form with HOST buffers (numpy in, numpy out): pinned staging, H2D, kernels,
+        D2H, synchronised.  This is the call that stands in for one HTTP round trip to Chroma."""
+        q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
+        assert q.shape[1] == self.dim
+        b = q.shape[0]
+        scores = np.empty((b, k), np.float32)
+        ids = np.empty((b, k), np.int64)
+        flags = np.zeros((b,), np.int32)
+        if b:
+            N.check(
+                N.lib().cmw_search_host(self._h, q.ctypes.data, b, k, N.METRICS[metric],
+                                        self._mode(mode, algo), scores.ctypes.data, ids.ctypes.data,
+                                        flags.ctypes.data),
+                "cmw_search_host",
+            )
+        return scores, ids, flags
+
+    # -- multi-vector reduction (K4) -----------------------------------------------------------------
+    def multivector(self, ids, scores, prl: int = 0, limit: int = 0, kb_gid=None, kb_id_offset=None):
+        """ids i64[Q,S,k] / scores f32[Q,S,k] (CUDA) -> MultiVectorResult (CUDA tensors).
+
+        ``kb_gid`` defaults to this store's own table; pass a full-corpus table (and its id offset)
+        when the ids come from a cross-shard merge."""
+        torch = _torch()
+        assert ids.is_cuda and ids.dtype == torch.int64 and ids.dim() == 3
+        assert scores.shape == ids.shape and scores.dtype == torch.float32
+        ids = ids.contiguous()
+        scores = scores.contiguous()
+        qn, s, k = ids.shape
+        n = s * k
+        p = prl if 0 < prl < n else n
+        dev = ids.device
+        if kb_gid is None:
+            kb_ptr = N.lib().cmw_store_kb_gid_dev(self._h)
+            kb_rows = self.info()["rows"]
+            kb_off = self.id_offset
+        else:
+            assert kb_gid.is_cuda and kb_gid.dtype == torch.int32
+            kb_gid = kb_gid.contiguous()
+            kb_ptr, kb_rows = kb_gid.data_ptr(), kb_gid.numel()
+            kb_off = int(kb_id_offset or 0)
+        out = MultiVectorResult(
+            cand_ids=torch.empty((qn, p), dtype=torch.int64, device=dev),
+            cand_scores=torch.empty((qn, p), dtype=torch.float32, device=dev),
+            cand_best=torch.empty((qn, p), dtype=torch.float32, device=dev),
+            cand_n=torch.zeros((qn,), dtype=torch.int32, device=dev),
+            cand_grp=torch.empty((qn, p), dtype=torch.int32, device=dev),
+            grp_gid=torch.empty((qn, p), dtype=torch.int32, device=dev),
+            grp_max=torch.empty((qn, p), dtype=torch.float32, device=dev),
+            grp_cnt=torch.empty((qn, p), dtype=torch.int32, device=dev),
+            grp_first=torch.empty((qn, p), dtype=torch.int32, device=dev),
+            grp_order=torch.empty((qn, p), dtype=torch.int32, device=dev),
+            grp_n=torch.zeros((qn,), dtype=torch.int32, device=dev),
+        )
+        if qn == 0:
+            return out
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        N.check(
+            N.lib().cmw_multivector(
+                kb_ptr, kb_rows, kb_off, ids.data_ptr(), scores.data_ptr(), qn, s, k, int(prl), int(limit),
+                out.cand_ids.data_ptr(), out.cand_scores.data_ptr(), out.cand_best.data_ptr(),
+                out.cand_n.data_ptr(), out.cand_grp.data_ptr(), out.grp_gid.data_ptr(),
+                out.grp_max.data_ptr(), out.grp_cnt.data_ptr(), out.grp_first.data_ptr(),
+                out.grp_order.data_ptr(), out.grp_n.data_ptr(), stream),
+            "cmw_multivector",
+        )
+        return out
+
+    def search_multivector(self, segment_queries, k: int, prl: int = 0, limit: int = 0, metric="cosine",
+                           mode="f32", algo=None):
+        """[Q, S, dim] segment embeddings -> per-segment top-k (one batched launch instead of the
+        reference's S awaits, retriever.py:179-182) -> union / dedup / cap / kbId groups."""
+        torch = _torch()
+        qn, s, d = segment_queries.shape
+        flat = segment_queries.reshape(qn * s, d)
+        scores, ids, flags = self.search(flat, k, metric=metric, mode=mode, algo=algo)
+        res = self.multivector(ids.view(qn, s, k), scores.view(qn, s, k), prl=prl, limit=limit)
+        return res, scores.view(qn, s, k), ids.view(qn, s, k), flags.view(qn, s)
+
+
+def merge_topk(scores64, ids, k_out: int):
+    """K5: scores f64[G,B,k_in], ids i64[G,B,k_in] (CUDA) -> (scores f32[B,k_out], ids, scores64)."""
+    torch = _torch()
+    assert scores64.is_cuda and scores64.dtype == torch.float64 and ids.dtype == torch.int64
+    scores64 = scores64.contiguous()
+    ids = ids.contiguous()
+    g, b, k_in = ids.shape
+    dev = ids.device
+    out_s = torch.empty((b, k_out), dtype=torch.float32, device=dev)
+    out_i = torch.empty((b, k_out), dtype=torch.int64, device=dev)
+    out_s64 = torch.empty((b, k_out), dtype=torch.float64, device=dev)
+    if b:
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        N.check(
+            N.lib().cmw_merge_topk(scores64.data_ptr(), ids.data_ptr(), g, b, k_in, k_out,
+                                   out_s.data_ptr(), out_i.data_ptr(), out_s64.data_ptr(), stream),
+            "cmw_merge_topk",
+        )
+    return out_s, out_i, out_s64

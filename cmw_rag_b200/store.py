@@ -1,0 +1,362 @@
+"""B200Store -- drop-in for the reference's ``ChromaStore`` on the dense-retrieval hot path.
+
+Mirrors ``rag_engine/storage/vector_store.py`` of the reference method for method (same names,
+keyword arguments, return shapes and "fewer than k when the collection is small" behaviour):
+
+* ``similarity_search_async(query_embedding, k=5)``   (vector_store.py:54-66)
+* ``add_async(texts, metadatas, ids=None, embeddings=None)``  (:68-82)
+* ``get_any_doc_meta_async(where)`` (:84-91), ``get_by_kb_id_async(kb_id)`` (:93-100)
+* ``delete_where_async(where)`` (:102-105), ``get_collection()`` (:44-52)
+
+so it can be handed to ``RAGRetriever(vector_store=...)`` (retrieval/retriever.py:34-46) or to
+``top_k_search_async`` (retrieval/vector_search.py:8-10) unchanged.  The vectors live in HBM inside
+``libcmwdense.so``; this class only keeps the host sidecar (documents, metadata, id maps, the
+kbId -> dense group table) and coalesces concurrent ``similarity_search_async`` awaits -- the S
+per-segment searches the reference gathers at retriever.py:179-182 -- into one batched launch.
+
+Additions over the reference surface: ``search`` (batched, returns ids + scores), ``query``
+(Chroma-shaped dict with ``ids`` / ``distances`` = 1 - cosine), ``search_multivector``.
+"""
+from __future__ import annotations
+
+import asyncio
+import threading
+import uuid
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+
+from .engine import DenseStore
+from .kbid import group_key
+
+
+@dataclass
+class RetrievedDoc:
+    """Same shape as rag_engine/storage/vector_store.py:13-16."""
+
+    page_content: str
+    metadata: dict[str, Any]
+
+
+def _match(meta: dict[str, Any], where: dict[str, Any] | None) -> bool:
+    """Chroma ``where`` subset: equality (what the reference uses: vector_store.py:87,96,105)
+    plus $eq/$ne/$in/$nin and $and/$or."""
+    if not where:
+        return True
+    for key, cond in where.items():
+        if key == "$and":
+            if not all(_match(meta, w) for w in cond):
+                return False
+        elif key == "$or":
+            if not any(_match(meta, w) for w in cond):
+                return False
+        elif isinstance(cond, dict):
+            val = meta.get(key)
+            for op, ref in cond.items():
+                if op == "$eq" and not (key in meta and val == ref):
+                    return False
+                if op == "$ne" and (key in meta and val == ref):
+                    return False
+                if op == "$in" and not (key in meta and val in ref):
+                    return False
+                if op == "$nin" and (key in meta and val in ref):
+                    return False
+        else:
+            if key not in meta or meta[key] != cond:
+                return False
+    return True
+
+
+class B200Store:
+    def __init__(
+        self,
+        collection_name: str = "default",
+        host: str | None = None,  # accepted for signature compatibility; unused (no server)
+        port: int | None = None,
+        *,
+        dim: int | None = None,
+        capacity: int = 1 << 20,
+        device: int = 0,
+        metric: str = "cosine",  # vector_store.py:48-51 pins {"hnsw:space": "cosine"}
+        mode: str = "f32",
+        keep_f32: bool = True,
+        keep_bf16: bool = True,
+        id_offset: int = 0,
+    ):
+        self.collection_name = collection_name
+        self.host = host
+        self.port = port
+        self.metric = metric
+        self.mode = mode
+        self._dim = dim
+        self._capacity = int(capacity)
+        self._device = int(device)
+        self._keep = (keep_f32, keep_bf16)
+        self._id_offset = int(id_offset)
+        self._dense: DenseStore | None = None
+        self._lock = threading.RLock()
+        # host sidecar, indexed by LOCAL row number
+        self._ids: list[str] = []
+        self._docs: list[str | None] = []
+        self._metas: list[dict[str, Any] | None] = []
+        self._alive: list[bool] = []
+        self._row_of: dict[str, int] = {}
+        self._gid_of_key: dict[str, int] = {}
+        self._key_of_gid: list[str] = []
+        # micro-batching of concurrent awaits
+        self._pending: list[tuple[np.ndarray, int, asyncio.Future]] = []
+        self._flush_scheduled = False
+        self.stats = {"searches": 0, "launch_batches": 0, "max_batch": 0}
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def _ensure(self, dim: int) -> DenseStore:
+        if self._dense is None:
+            self._dim = int(dim)
+            # the kernels want rows of 16-byte multiples; zero padding changes neither dots nor norms
+            # (the reference's own store test uses 3-d vectors: tests/test_storage_vector_store.py:10-24)
+            self._pdim = (self._dim + 7) // 8 * 8
+            self._dense = DenseStore(self._pdim, self._capacity, device=self._device, f32=self._keep[0],
+                                     bf16=self._keep[1], id_offset=self._id_offset)
+        elif dim != self._dim:
+            raise ValueError(f"embedding dimension {dim} does not match the collection's {self._dim}")
+        return self._dense
+
+    def _pad(self, x: np.ndarray) -> np.ndarray:
+        if x.shape[1] == self._pdim:
+            return x
+        out = np.zeros((x.shape[0], self._pdim), np.float32)
+        out[:, : x.shape[1]] = x
+        return out
+
+    @property
+    def dense(self) -> DenseStore | None:
+        return self._dense
+
+    def count(self) -> int:
+        return sum(self._alive)
+
+    def gid_for(self, raw_kb_id) -> int:
+        """Dense group number of a kbId (retriever.py:236-239 grouping key), -1 for a falsy kbId."""
+        key = group_key(raw_kb_id)
+        if key is None:
+            return -1
+        gid = self._gid_of_key.get(key)
+        if gid is None:
+            gid = len(self._key_of_gid)
+            self._gid_of_key[key] = gid
+            self._key_of_gid.append(key)
+        return gid
+
+    def key_of_gid(self, gid: int) -> str:
+        return self._key_of_gid[gid]
+
+    # -- ingest / mutation (sync cores + the reference's async names) ------------------------------
+    def add(self, texts, metadatas, ids=None, embeddings=None) -> None:
+        if embeddings is None:
+            raise ValueError("B200Store.add needs embeddings (the reference's indexer always passes "
+                             "them: rag_engine/core/indexer.py:495-507); there is no embedding function")
+        n = len(texts)
+        emb = np.ascontiguousarray(embeddings, dtype=np.float32)
+        if emb.ndim != 2 or emb.shape[0] != n:
+            raise ValueError(f"embeddings must be [{n}, dim], got {emb.shape}")
+        metadatas = list(metadatas) if metadatas is not None else [None] * n
+        if len(metadatas) != n:
+            raise ValueError("texts and metadatas differ in length")
+        ids = [str(i) for i in ids] if ids is not None else [uuid.uuid4().hex for _ in range(n)]
+        if len(ids) != n or len(set(ids)) != n:
+            raise ValueError("ids must be unique and match texts in length")
+        with self._lock:
+            keep = [i for i in range(n) if ids[i] not in self._row_of]  # Chroma add() ignores known ids
+            if not keep:
+                return
+            dense = self._ensure(emb.shape[1])
+            gids = np.array([self.gid_for((metadatas[i] or {}).get("kbId", "")) for i in keep], np.int32)
+            base = len(self._ids)
+            dense.append(self._pad(emb[keep]), gids)
+            for j, i in enumerate(keep):
+                self._row_of[ids[i]] = base + j
+                self._ids.append(ids[i])
+                self._docs.append(texts[i])
+                self._metas.append(dict(metadatas[i]) if metadatas[i] is not None else None)
+                self._alive.append(True)
+
+    def _rows_where(self, where, limit: int | None = None) -> list[int]:
+        out = []
+        for r, (alive, meta) in enumerate(zip(self._alive, self._metas)):
+            if alive and _match(meta or {}, where):
+                out.append(r)
+                if limit is not None and len(out) >= limit:
+                    break
+        return out
+
+    def delete(self, where=None, ids=None) -> int:
+        with self._lock:
+            rows = set()
+            if ids is not None:
+                rows.update(self._row_of[i] for i in ids if i in self._row_of)
+                if where:
+                    rows = {r for r in rows if _match(self._metas[r] or {}, where)}
+            elif where:
+                rows.update(self._rows_where(where))
+            rows = sorted(r for r in rows if self._alive[r])
+            if rows and self._dense is not None:
+                self._dense.tombstone(rows)
+            for r in rows:
+                self._alive[r] = False
+                self._row_of.pop(self._ids[r], None)
+                self._docs[r] = None
+                self._metas[r] = None
+            return len(rows)
+
+    def get(self, where=None, ids=None, include=("metadatas", "documents"), limit=None) -> dict:
+        with self._lock:
+            if ids is not None:
+                rows = [self._row_of[i] for i in ids if i in self._row_of]
+                rows = [r for r in rows if _match(self._metas[r] or {}, where)]
+                if limit is not None:
+                    rows = rows[:limit]
+            else:
+                rows = self._rows_where(where, limit)
+            out: dict[str, Any] = {"ids": [self._ids[r] for r in rows]}
+            out["metadatas"] = [self._metas[r] for r in rows] if "metadatas" in include else None
+            out["documents"] = [self._docs[r] for r in rows] if "documents" in include else None
+            return out
+
+    async def add_async(self, texts, metadatas, ids=None, embeddings=None) -> None:
+        await asyncio.to_thread(self.add, texts, metadatas, ids, embeddings)
+
+    async def get_any_doc_meta_async(self, where: dict[str, Any]) -> dict[str, Any] | None:
+        metas = self.get(where=where, include=["metadatas"], limit=1).get("metadatas") or []
+        return metas[0] if metas else None
+
+    async def get_by_kb_id_async(self, kb_id: str) -> dict[str, Any] | None:
+        metas = self.get(where={"kbId": kb_id}, include=["metadatas"], limit=1).get("metadatas") or []
+        return metas[0] if metas else None
+
+    async def delete_where_async(self, where: dict[str, Any]) -> None:
+        await asyncio.to_thread(self.delete, where)
+
+    async def get_collection(self):
+        return _Collection(self)
+
+    # -- search ---------------------------------------------------------------------------------
+    def search(self, queries, k: int, mode: str | None = None, algo: str | None = None):
+        """Batched search from HOST vectors: (scores f32[B,k'], ids i64[B,k'], flags) numpy, where
+        slots beyond the number of live rows hold id -1 / score -inf."""
+        q = np.ascontiguousarray(np.atleast_2d(np.asarray(queries, dtype=np.float32)))
+        with self._lock:
+            if self._dense is None or q.shape[0] == 0:
+                b = q.shape[0]
+                return (np.full((b, k), -np.inf, np.float32), np.full((b, k), -1, np.int64),
+                        np.zeros((b,), np.int32))
+            if q.shape[1] != self._dim:
+                raise ValueError(f"query dimension {q.shape[1]} does not match the collection's {self._dim}")
+            return self._dense.search_host(self._pad(q), k, metric=self.metric, mode=mode or self.mode,
+                                           algo=algo)
+
+    def _docs_for(self, ids_row: np.ndarray) -> list[RetrievedDoc]:
+        out = []
+        for gid in ids_row.tolist():
+            if gid < 0:
+                continue
+            r = gid - self._id_offset
+            if 0 <= r < len(self._ids) and self._alive[r]:
+                out.append(RetrievedDoc(page_content=self._docs[r], metadata=dict(self._metas[r] or {})))
+        return out
+
+    def query(self, query_embeddings, n_results: int = 10, include=("documents", "metadatas", "distances")):
+        """Chroma-shaped result dict: every value is a list (one per query) of lists."""
+        scores, ids, _ = self.search(query_embeddings, n_results)
+        res: dict[str, Any] = {"ids": [], "documents": None, "metadatas": None, "distances": None}
+        docs, metas, dists = [], [], []
+        for b in range(ids.shape[0]):
+            rows = [int(g) - self._id_offset for g in ids[b] if g >= 0]
+            rows = [r for r in rows if 0 <= r < len(self._ids) and self._alive[r]]
+            res["ids"].append([self._ids[r] for r in rows])
+            docs.append([self._docs[r] for r in rows])
+            metas.append([dict(self._metas[r] or {}) for r in rows])
+            dists.append([float(1.0 - s) for s, g in zip(scores[b], ids[b]) if g >= 0][: len(rows)])
+        if "documents" in include:
+            res["documents"] = docs
+        if "metadatas" in include:
+            res["metadatas"] = metas
+        if "distances" in include:
+            res["distances"] = dists
+        return res
+
+    def similarity_search(self, query_embedding, k: int = 5) -> list[RetrievedDoc]:
+        _, ids, _ = self.search([query_embedding], k)
+        return self._docs_for(ids[0])
+
+    async def similarity_search_async(self, query_embedding: list[float], k: int = 5) -> list[RetrievedDoc]:
+        """Same contract as ChromaStore.similarity_search_async (vector_store.py:54-66).  Awaits
+        issued in the same event-loop tick (asyncio.gather over segments, retriever.py:179-182)
+        share one batched kernel launch."""
+        loop = asyncio.get_running_loop()
+        fut: asyncio.Future = loop.create_future()
+        self._pending.append((np.asarray(query_embedding, dtype=np.float32), int(k), fut))
+        if not self._flush_scheduled:
+            self._flush_scheduled = True
+            loop.call_soon(lambda: asyncio.ensure_future(self._flush()))
+        return await fut
+
+    async def _flush(self) -> None:
+        batch, self._pending = self._pending, []
+        self._flush_scheduled = False
+        if not batch:
+            return
+        try:
+            kmax = max(k for _, k, _ in batch)
+            q = np.stack([v for v, _, _ in batch])
+            self.stats["searches"] += len(batch)
+            self.stats["launch_batches"] += 1
+            self.stats["max_batch"] = max(self.stats["max_batch"], len(batch))
+            _, ids, _ = await asyncio.to_thread(self.search, q, kmax)
+            for i, (_, k, fut) in enumerate(batch):
+                if not fut.done():
+                    fut.set_result(self._docs_for(ids[i, :k]))
+        except Exception as exc:  # propagate like a chromadb error would (retrieve_context.py:435-449)
+            for _, _, fut in batch:
+                if not fut.done():
+                    fut.set_exception(exc)
+
+    def search_multivector(self, segment_embeddings, k: int, prl: int = 0, limit: int = 0):
+        """[Q, S, dim] host array -> (MultiVectorResult on CPU, ids [Q,S,k], scores [Q,S,k])."""
+        import torch
+
+        seg = np.ascontiguousarray(segment_embeddings, dtype=np.float32)
+        with self._lock:
+            if self._dense is None:
+                raise RuntimeError("empty collection")
+            dev = torch.device(f"cuda:{self._device}")
+            t = torch.from_numpy(seg).to(dev)
+            res, scores, ids, _ = self._dense.search_multivector(t, k, prl=prl, limit=limit,
+                                                                 metric=self.metric, mode=self.mode)
+            torch.cuda.synchronize(dev)
+            return res.cpu(), ids.cpu().numpy(), scores.cpu().numpy()
+
+
+class _Collection:
+    """The slice of chromadb's AsyncCollection API the reference touches."""
+
+    def __init__(self, store: B200Store):
+        self._s = store
+        self.name = store.collection_name
+        self.metadata = {"hnsw:space": store.metric}
+
+    async def query(self, query_embeddings, n_results: int = 10, include=("documents", "metadatas", "distances"),
+                    **_ignored):
+        return await asyncio.to_thread(self._s.query, query_embeddings, n_results, include)
+
+    async def add(self, ids=None, documents=None, metadatas=None, embeddings=None):
+        await self._s.add_async(documents, metadatas, ids=ids, embeddings=embeddings)
+
+    async def get(self, where=None, ids=None, include=("metadatas", "documents"), limit=None, **_ignored):
+        return self._s.get(where=where, ids=ids, include=include, limit=limit)
+
+    async def delete(self, where=None, ids=None):
+        await asyncio.to_thread(self._s.delete, where, ids)
+
+    async def count(self) -> int:
+        return self._s.count()

@@ -1,0 +1,147 @@
+/* cmw_dense.h -- C ABI of libcmwdense.so: the B200-native dense-retrieval hot path of cmw-rag.
+ *
+ * The reference (arterm-sedov/cmw-rag) is pure Python and has NO native boundary for this
+ * path: scoring + top-k run inside an external ChromaDB server reached over HTTP.  Each entry
+ * point below names the reference interface it stands in for (paths relative to the reference
+ * checkout).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C types only; every *_dev pointer is a CUDA device pointer on the store's device,
+ *     every *_host pointer is ordinary host memory; `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream).  Device-pointer entry points are stream-ordered and do not
+ *     synchronise; outputs are valid when the stream reaches that point.
+ *   - return value: 0 = ok, negative = error; the message is in cmw_last_error() (thread-local).
+ *   - row ids are int64 = row number in append order + the store's id offset (row shards).
+ *   - unused output slots (k larger than the number of live rows): id = -1, score = -inf.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef CMW_DENSE_H_
+#define CMW_DENSE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMW_ABI_VERSION 2
+
+/* metric -- rag_engine/storage/vector_store.py:48-51 fixes the collection to cosine
+ * ({"hnsw:space": "cosine"}); inner product is the north star's second metric. */
+#define CMW_METRIC_COSINE 0
+#define CMW_METRIC_IP 1
+
+/* search mode */
+#define CMW_MODE_F32_EXACT 0 /* ids identical to the exact fp64 oracle (ties -> lower id); fp64-accumulated scores */
+#define CMW_MODE_BF16 1      /* bf16 operands, fp32 accumulation; approximate (reported as recall@k) */
+/* optional algorithm override, OR-ed into `mode` (default: chosen from the batch size) */
+#define CMW_ALGO_AUTO (0 << 8)
+#define CMW_ALGO_SCAN (1 << 8) /* K1: TMA-staged streaming dot product (batch 1-4 per pass, HBM-bound) */
+#define CMW_ALGO_GEMM (2 << 8) /* K2: tcgen05/TMEM GEMM with fused top-k epilogue */
+/* slab schedule override, OR-ed into `mode`: fixed slabs small enough that the candidate pool can
+ * never overflow, whatever the row order (slower; cmw_search_host falls back to it by itself) */
+#define CMW_SLABS_SAFE (1 << 16)
+
+/* store flags */
+#define CMW_STORE_F32 1u  /* keep row-major fp32 tiles (needed by CMW_MODE_F32_EXACT) */
+#define CMW_STORE_BF16 2u /* keep row-major bf16 tiles of the L2-normalised rows */
+
+/* per-query flags written by cmw_search (out_flags) */
+#define CMW_FLAG_UNCERTIFIED 1 /* F32_EXACT only: the exactness certificate could not be established */
+
+typedef struct cmw_store cmw_store;
+
+typedef struct cmw_store_info {
+    int32_t device;
+    int32_t dim;
+    uint32_t flags;
+    int32_t sm_count;
+    int64_t capacity_rows;
+    int64_t rows;      /* appended so far (including tombstoned) */
+    int64_t live_rows; /* rows - tombstoned */
+    int64_t id_offset;
+    int64_t hbm_bytes; /* device memory held by the store */
+} cmw_store_info;
+
+const char* cmw_last_error(void);
+int cmw_abi_version(void);
+
+/* ---- corpus store: replaces the Chroma collection of
+ *      rag_engine/storage/vector_store.py:44-52 (get_or_create_collection) ---- */
+int cmw_store_create(int device, int dim, int64_t capacity_rows, uint32_t flags, int64_t id_offset,
+                     cmw_store** out);
+int cmw_store_destroy(cmw_store* s);
+int cmw_store_get_info(const cmw_store* s, cmw_store_info* out);
+
+/* K0 ingest -- replaces collection.add(embeddings=...) of vector_store.py:68-82.
+ * rows: fp32 [n, dim] row-major.  kb_gid: int32 [n] dense group number of the row's normalised
+ * kbId (rag_engine/utils/metadata_utils.py:20-32), negative = falsy kbId; may be NULL (= -1).
+ * Builds fp32 tiles, bf16 tiles of the normalised rows, norm / inv_norm. */
+int cmw_store_append_f32(cmw_store* s, const float* rows_dev, const int32_t* kb_gid_dev, int64_t n,
+                         void* stream);
+int cmw_store_append_host_f32(cmw_store* s, const float* rows_host, const int32_t* kb_gid_host,
+                              int64_t n);
+/* replaces collection.delete(where=...) of vector_store.py:102-105 once the host has resolved the
+ * filter to row numbers (LOCAL rows, i.e. without id_offset).  Tombstoned rows are never returned. */
+int cmw_store_tombstone(cmw_store* s, const int64_t* rows_dev, int64_t n, void* stream);
+int cmw_store_tombstone_host(cmw_store* s, const int64_t* rows_host, int64_t n);
+/* device pointer to kb_gid[rows] (for cmw_multivector) */
+const int32_t* cmw_store_kb_gid_dev(const cmw_store* s);
+
+/* ---- search: replaces collection.query(query_embeddings, n_results) of
+ *      vector_store.py:54-66 for a whole batch of query vectors ---- */
+size_t cmw_search_workspace_bytes(const cmw_store* s, int batch, int k, int mode);
+/* queries: fp32 [batch, dim].  out_scores f32 [batch,k], out_ids i64 [batch,k];
+ * out_scores64 f64 [batch,k] (may be NULL; the scores the ranking used, needed for an exact
+ * cross-shard merge); out_flags i32 [batch] (may be NULL).  ws: >= cmw_search_workspace_bytes. */
+int cmw_search(cmw_store* s, const float* queries_dev, int batch, int k, int metric, int mode,
+               float* out_scores_dev, int64_t* out_ids_dev, double* out_scores64_dev,
+               int32_t* out_flags_dev, void* ws_dev, size_t ws_bytes, void* stream);
+/* End-to-end form with HOST buffers (what a ctypes / HTTP-replacing caller uses): pinned staging,
+ * H2D of the queries, search, D2H of the results, synchronises before returning. */
+int cmw_search_host(cmw_store* s, const float* queries_host, int batch, int k, int metric, int mode,
+                    float* out_scores_host, int64_t* out_ids_host, int32_t* out_flags_host);
+
+/* ---- multi-vector reduction: replaces the Python loops of
+ *      rag_engine/retrieval/retriever.py:185-194 (ordered union, first-seen dedup),
+ *      :208-210 (pre-rerank cap), :229-242 (truncate + group by normalised kbId, max score),
+ *      :307 (stable sort by score descending) for Q long queries at once.
+ * ids i64 [Q,S,k] / scores f32 [Q,S,k]: per-segment top-k (LOCAL or global ids; negative = pad).
+ * kb_gid: int32 table indexed by (id - id_offset).  P = (0 < prl < S*k) ? prl : S*k.
+ * limit: group only the first `limit` candidates (0 = all)  [retriever.py:229-231].
+ * Outputs (any may be NULL): cand_ids i64[Q,P], cand_scores f32[Q,P] (first-seen occurrence),
+ * cand_best f32[Q,P] (max over occurrences), cand_n i32[Q], cand_grp i32[Q,P] (group index in
+ * first-appearance order or -1), grp_gid i32[Q,P], grp_max f32[Q,P], grp_cnt i32[Q,P],
+ * grp_first i32[Q,P], grp_order i32[Q,P] (group indices, stable score-desc), grp_n i32[Q]. */
+int cmw_multivector(const int32_t* kb_gid_dev, int64_t kb_rows, int64_t id_offset,
+                    const int64_t* ids_dev, const float* scores_dev, int Q, int S, int k, int prl,
+                    int limit, int64_t* cand_ids, float* cand_scores, float* cand_best,
+                    int32_t* cand_n, int32_t* cand_grp, int32_t* grp_gid, float* grp_max,
+                    int32_t* grp_cnt, int32_t* grp_first, int32_t* grp_order, int32_t* grp_n,
+                    void* stream);
+
+/* ---- cross-shard merge (after the NCCL all-gather of per-GPU candidates):
+ * scores f64 [G,B,k_in], ids i64 [G,B,k_in] -> top k_out by (score desc, id asc). */
+int cmw_merge_topk(const double* scores_dev, const int64_t* ids_dev, int G, int B, int k_in,
+                   int k_out, float* out_scores_dev, int64_t* out_ids_dev,
+                   double* out_scores64_dev, void* stream);
+
+/* ---- instrumentation ---- */
+/* number of kernels this library has launched since load (all stores, all streams) */
+int64_t cmw_kernel_launches(void);
+ /* Per-phase device timing for roofline reports: while enabled, cmw_search brackets its phases with
+ * CUDA events on the caller's stream.  cmw_profile_read synchronises those events and returns the
+ * accumulated milliseconds since the last enable/read: ms[0] = filter kernels (K1 scan / K2 GEMM),
+ * ms[1] = pool compaction, ms[2] = finalisation (K3 rescoring + select, or emit), ms[3] = query
+ * preparation; counts[i] = kernels launched in that phase.  n = array length (<= 4). */
+int cmw_profile_enable(int on);
+int cmw_profile_read(double* ms, int64_t* counts, int n);
+/* tunables: "bf16_eps" (certificate bound for the bf16 filter), "scan_max_batch", ... */
+int cmw_set_option(const char* name, double value);
+double cmw_get_option(const char* name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMW_DENSE_H_ */

@@ -1,0 +1,372 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200): the CUDA path, called through the C ABI, against
+the CPU oracle on the same seeded inputs.  Bars (BASELINE.json north_star): fp32-exact mode -- top-k
+ids bit-identical to the fp64 oracle (ties -> lower id), scores within 1e-5; bf16 mode -- scores
+within 2e-3, reported as recall@k.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import exact_topk, merge_topk as oracle_merge
+from oracle.cport import exact_topk_c
+from oracle.multivector import group_key, multivector_reduce
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = 1e-5
+BF16_TOL = 2e-3
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def cfg1(torch_cuda):
+    """Config 1 of BASELINE.json: 10k x 1536, 64 queries, top-20 cosine."""
+    from cmw_rag_b200 import DenseStore
+
+    c = synth.make_corpus(10000)
+    q, needle = synth.make_queries(c, 64)
+    kb, _ = synth.make_kbids(10000)
+    keys: dict[str, int] = {}
+    gid = np.full(10000, -1, np.int32)
+    for i, raw in enumerate(kb):
+        k = group_key(raw)
+        if k is not None:
+            gid[i] = keys.setdefault(k, len(keys))
+    st = DenseStore(1536, 10000)
+    st.append(c, gid)
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, 20)
+    yield dict(store=st, c=c, q=q, needle=needle, gid=gid, ref_ids=ref_ids, ref_sc=ref_sc)
+    st.close()
+
+
+def _check_exact(ids, scores, ref_ids, ref_sc):
+    assert (ids == ref_ids).all(), f"{(ids != ref_ids).sum()} ids differ"
+    fin = np.isfinite(ref_sc)
+    assert np.abs(scores[fin] - ref_sc[fin]).max() <= F32_TOL
+    assert (np.isneginf(scores) == np.isneginf(ref_sc)).all()
+
+
+def test_config1_exact_scan_host_api(cfg1):
+    sc, ids, flags = cfg1["store"].search_host(cfg1["q"], 20, mode="f32", algo="scan")
+    _check_exact(ids, sc, cfg1["ref_ids"], cfg1["ref_sc"])
+    assert (flags == 0).all()
+    planted = cfg1["needle"] >= 0
+    assert (ids[planted, 0] == cfg1["needle"][planted]).all()
+    assert ids[1, :3].tolist() == [17, 5000, 9999]  # duplicated rows: lower id first
+
+
+def test_config1_exact_auto_device_api(cfg1, torch_cuda):
+    torch = torch_cuda
+    q = torch.from_numpy(cfg1["q"]).cuda()
+    sc, ids, flags = cfg1["store"].search(q, 20, mode="f32")
+    torch.cuda.synchronize()
+    _check_exact(ids.cpu().numpy(), sc.cpu().numpy(), cfg1["ref_ids"], cfg1["ref_sc"])
+    assert int(flags.sum()) == 0
+
+
+@pytest.mark.parametrize("algo", ["scan", "auto"])
+def test_config1_bf16_recall(cfg1, algo):
+    sc, ids, _ = cfg1["store"].search_host(cfg1["q"], 20, mode="bf16", algo=algo)
+    ref = cfg1["ref_ids"]
+    recall = np.mean([len(set(ids[b]) & set(ref[b])) / 20 for b in range(ref.shape[0])])
+    assert recall >= 0.97, recall
+    # scores of the rows that were returned agree with the exact scores of those rows
+    c, q = cfg1["c"], cfg1["q"]
+    ex = np.einsum("bkd,bd->bk", c[ids].astype(np.float64), q.astype(np.float64))
+    assert np.abs(sc - ex).max() <= BF16_TOL
+    assert (ids[np.arange(64), 0] == ref[:, 0]).all()
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3, 5])
+def test_ragged_batches(cfg1, batch):
+    sc, ids, _ = cfg1["store"].search_host(cfg1["q"][:batch], 20, mode="f32")
+    _check_exact(ids, sc, cfg1["ref_ids"][:batch], cfg1["ref_sc"][:batch])
+
+
+def test_inner_product(cfg1):
+    c = cfg1["c"].copy()
+    rng = np.random.default_rng(3)
+    c *= rng.uniform(0.5, 2.0, size=(c.shape[0], 1)).astype(np.float32)  # un-normalised rows
+    from cmw_rag_b200 import DenseStore
+
+    st = DenseStore(1536, c.shape[0])
+    st.append(c)
+    q = cfg1["q"][:8] * 3.0
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, 10, metric="ip")
+    for algo in ("scan", "auto"):
+        sc, ids, fl = st.search_host(q, 10, metric="ip", mode="f32", algo=algo)
+        assert (ids == ref_ids).all()
+        assert np.abs(sc - ref_sc).max() <= 2e-5 * 6.0  # scores are up to |q||c| = 6
+    ref_ids_c, ref_sc_c, _ = exact_topk_c(c, q, 10, metric="cosine")
+    sc, ids, fl = st.search_host(q, 10, metric="cosine", mode="f32")
+    _check_exact(ids, sc, ref_ids_c, ref_sc_c)
+    st.close()
+
+
+def test_edge_cases_small_dims(torch_cuda):
+    from cmw_rag_b200 import DenseStore
+
+    rng = np.random.default_rng(0)
+    c = rng.standard_normal((37, 16)).astype(np.float32)
+    q = rng.standard_normal((3, 16)).astype(np.float32)
+    c[5] = 0
+    q[2] = 0
+    st = DenseStore(16, 64)
+    # empty store: nothing to return
+    sc, ids, _ = st.search_host(q, 5)
+    assert (ids == -1).all() and np.isneginf(sc).all()
+    st.append(c)
+    # k > N -> padded with (-1, -inf), like Chroma returning fewer results
+    ref_ids, ref_sc, _ = exact_topk(c, q, 50)
+    sc, ids, _ = st.search_host(q, 50)
+    _check_exact(ids, sc, ref_ids, ref_sc)
+    assert ids[2, :37].tolist() == list(range(37))  # zero query: all scores 0 -> id order
+    # tombstones are never returned
+    live = np.ones(37, bool)
+    dead = [int(ref_ids[0, 0]), int(ref_ids[0, 1]), 36]
+    live[dead] = False
+    st.tombstone(dead + [dead[0]])
+    assert st.live_rows == 34
+    ref_ids2, ref_sc2, _ = exact_topk(c, q, 37, live=live)
+    sc, ids, _ = st.search_host(q, 37)
+    _check_exact(ids, sc, ref_ids2, ref_sc2)
+    sc, ids, _ = st.search_host(q, 37, mode="bf16")
+    assert set(ids[0].tolist()) - {-1} == set(np.flatnonzero(live).tolist())
+    # append after tombstoning; id offset
+    st.close()
+    st = DenseStore(16, 64, id_offset=1000)
+    st.append(c[:20])
+    st.append(c[20:])
+    ref_ids, ref_sc, _ = exact_topk(c, q, 7, id_offset=1000)
+    sc, ids, _ = st.search_host(q, 7)
+    _check_exact(ids, sc, ref_ids, ref_sc)
+    st.close()
+
+
+@pytest.mark.parametrize("n,d", [(50007, 1024), (30000, 768), (20011, 200)])
+def test_multi_slab_other_dims(torch_cuda, n, d):
+    """Several slabs (dense + growing sparse ones), row counts that are not tile multiples, the
+    register-resident (1024), the fp32-only specialisation (768) and the generic (200) paths."""
+    from cmw_rag_b200 import DenseStore
+
+    c = synth.make_corpus(n, d, seed=123)
+    q, _ = synth.make_queries(c, 6, seed=5)
+    st = DenseStore(d, n + 5)
+    st.append(c)
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, 100)
+    sc, ids, fl = st.search_host(q, 100, mode="f32")
+    _check_exact(ids, sc, ref_ids, ref_sc)
+    assert (fl == 0).all()
+    sc, ids, fl = st.search_host(q[:3], 100, mode="bf16")
+    recall = np.mean([len(set(ids[b]) & set(ref_ids[b])) / 100 for b in range(3)])
+    assert recall >= 0.9
+    st.close()
+
+
+def test_adversarial_ascending_order(torch_cuda):
+    """Rows sorted by ascending score: every slab floods the pool; the overflow must be flagged or
+    the answer exact -- never silently wrong."""
+    from cmw_rag_b200 import DenseStore
+
+    d, n = 64, 60000
+    rng = np.random.default_rng(1)
+    q = rng.standard_normal((1, d)).astype(np.float32)
+    c = rng.standard_normal((n, d)).astype(np.float32)
+    order = np.argsort((c @ q[0]) / np.linalg.norm(c, axis=1))
+    c = np.ascontiguousarray(c[order])
+    st = DenseStore(d, n)
+    st.append(c)
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, 10)
+    sc, ids, fl = st.search_host(q, 10)  # host API: falls back to the overflow-proof schedule
+    assert fl[0] == 0
+    _check_exact(ids, sc, ref_ids, ref_sc)
+    import torch
+
+    _, _, fl_dev = st.search(torch.from_numpy(q).cuda(), 10)  # device API: reports, never hides
+    sc2, ids2, fl2 = st.search(torch.from_numpy(q).cuda(), 10, algo="scan_safe")
+    torch.cuda.synchronize()
+    assert int(fl_dev[0]) == 1 and int(fl2[0]) == 0
+    _check_exact(ids2.cpu().numpy(), sc2.cpu().numpy(), ref_ids, ref_sc)
+    st.close()
+
+
+def test_merge_topk_matches_oracle(cfg1, torch_cuda):
+    torch = torch_cuda
+    from cmw_rag_b200 import DenseStore, merge_topk
+
+    c, q = cfg1["c"], cfg1["q"][:9]
+    shards = []
+    bounds = [0, 2500, 2507, 7000, 10000]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        st = DenseStore(1536, hi - lo, id_offset=lo)
+        st.append(c[lo:hi])
+        shards.append(st)
+    qd = torch.from_numpy(q).cuda()
+    parts = [st.search(qd, 20, return_scores64=True) for st in shards]
+    s64 = torch.stack([p[3] for p in parts])
+    ids = torch.stack([p[1] for p in parts])
+    ms, mi, _ = merge_topk(s64, ids, 20)
+    torch.cuda.synchronize()
+    assert (mi.cpu().numpy() == cfg1["ref_ids"][:9]).all()
+    assert np.abs(ms.cpu().numpy() - cfg1["ref_sc"][:9]).max() <= F32_TOL
+    oi, osc = oracle_merge(ids.cpu().numpy(), s64.cpu().numpy(), 20)
+    assert (oi == mi.cpu().numpy()).all()
+    for st in shards:
+        st.close()
+
+
+def _gid_table(kb):
+    keys: dict[str, int] = {}
+    gid = np.full(len(kb), -1, np.int32)
+    for i, raw in enumerate(kb):
+        k = group_key(raw)
+        if k is not None:
+            gid[i] = keys.setdefault(k, len(keys))
+    return gid
+
+
+def _mv_compare(res, ref):
+    for name, want in ref.items():
+        got = getattr(res, name).numpy()
+        if want.dtype.kind == "f":
+            assert np.array_equal(got, want), name
+        else:
+            assert (got == want).all(), name
+
+
+def test_multivector_kernel_matches_oracle_and_golden(golden_dir, torch_cuda):
+    torch = torch_cuda
+    from cmw_rag_b200 import DenseStore
+
+    with open(os.path.join(golden_dir, "multivector_golden.json")) as f:
+        g = json.load(f)
+    gid = _gid_table(g["kb"])
+    st = DenseStore(8, len(gid))
+    st.append(np.ones((len(gid), 8), np.float32), gid)
+    for case in g["cases"]:
+        ids = np.array([[s["ids"] for s in case["segments"]]], np.int64)
+        sc = np.array([[s["scores"] for s in case["segments"]]], np.float32)
+        for prl, limit in ((case["params"]["prl"], 0), (0, 0), (case["params"]["prl"], case["params"]["top_k_rerank"]), (7, 3)):
+            ref = multivector_reduce(ids, sc, gid, prl=prl, limit=limit)
+            res = st.multivector(torch.from_numpy(ids).cuda(), torch.from_numpy(sc).cuda(), prl=prl, limit=limit).cpu()
+            _mv_compare(res, ref)
+        if case["rerank_input_stable_ids"] is not None:
+            res = st.multivector(torch.from_numpy(ids).cuda(), torch.from_numpy(sc).cuda(),
+                                 prl=case["params"]["prl"]).cpu()
+            n = int(res.cand_n[0])
+            assert [f"{i:012d}" for i in res.cand_ids[0, :n].tolist()] == case["rerank_input_stable_ids"]
+    # random ragged case: padding ids, duplicates across and inside segments, many queries
+    rng = np.random.default_rng(9)
+    ids = rng.integers(0, 300, size=(33, 8, 50)).astype(np.int64)
+    ids[rng.random(ids.shape) < 0.1] = -1
+    sc = rng.standard_normal(ids.shape).astype(np.float32)
+    sc[rng.random(ids.shape) < 0.2] = 0.5  # score ties between groups
+    for prl, limit in ((60, 0), (0, 0), (400, 10), (1, 0)):
+        ref = multivector_reduce(ids, sc, gid, prl=prl, limit=limit)
+        res = st.multivector(torch.from_numpy(ids).cuda(), torch.from_numpy(sc).cuda(), prl=prl, limit=limit).cpu()
+        _mv_compare(res, ref)
+    st.close()
+
+
+def test_search_multivector_end_to_end(cfg1, torch_cuda):
+    """Config 3 in miniature: long queries x segments -> per-segment top-k -> union -> kbId groups,
+    against the oracle chain exact_topk -> multivector_reduce."""
+    torch = torch_cuda
+    c, gid = cfg1["c"], cfg1["gid"]
+    qs, _ = synth.make_queries(c, 6 * 4, seed=21)
+    seg = qs.reshape(6, 4, 1536)
+    res, sc, ids, flags = cfg1["store"].search_multivector(torch.from_numpy(seg).cuda(), 20, prl=60)
+    torch.cuda.synchronize()
+    ref_ids, ref_sc, _ = exact_topk_c(c, qs, 20)
+    assert (ids.cpu().numpy().reshape(24, 20) == ref_ids).all()
+    ref = multivector_reduce(ids.cpu().numpy(), sc.cpu().numpy(), gid, prl=60)
+    _mv_compare(res.cpu(), ref)
+
+
+def test_b200store_reference_store_kat(torch_cuda):
+    """The reference's only numeric nearest-neighbour assertion
+    (rag_engine/tests/test_storage_vector_store.py:10-24), against B200Store."""
+    import asyncio
+
+    from cmw_rag_b200 import B200Store
+
+    async def run():
+        store = B200Store(collection_name="test_collection", capacity=16)
+        await store.add_async(texts=["a", "b"], metadatas=[{"kbId": "doc1"}, {"kbId": "doc2"}],
+                              ids=["1", "2"], embeddings=[[0.1, 0.0, 0.0], [0.0, 0.1, 0.0]])
+        results = await store.similarity_search_async(query_embedding=[0.1, 0.0, 0.0], k=1)
+        assert len(results) == 1
+        assert results[0].metadata["kbId"] == "doc1"
+        # test_storage_vector_store.py:27-48: get / delete by where
+        await store.add_async(texts=["c"], metadatas=[{"doc_stable_id": "d3", "kbId": "doc3"}], ids=["3"],
+                              embeddings=[[0.0, 0.0, 0.1]])
+        meta = await store.get_any_doc_meta_async({"doc_stable_id": "d3"})
+        assert meta and meta["doc_stable_id"] == "d3"
+        assert (await store.get_by_kb_id_async("doc2"))["kbId"] == "doc2"
+        await store.delete_where_async({"doc_stable_id": "d3"})
+        assert await store.get_any_doc_meta_async({"doc_stable_id": "d3"}) is None
+        res = await store.similarity_search_async(query_embedding=[0.0, 0.0, 0.1], k=5)
+        assert [r.metadata["kbId"] for r in res] == ["doc1", "doc2"]  # both score 0: lower id first
+        # concurrent awaits coalesce into one launch (retriever.py:179-182 fan-out)
+        before = store.stats["launch_batches"]
+        outs = await asyncio.gather(*[store.similarity_search_async([0.1, 0.0, 0.0], k=2) for _ in range(4)])
+        assert store.stats["launch_batches"] == before + 1 and store.stats["max_batch"] >= 4
+        assert all(o[0].metadata["kbId"] == "doc1" for o in outs)
+        col = await store.get_collection()
+        raw = await col.query(query_embeddings=[[0.1, 0.0, 0.0]], n_results=2)
+        assert raw["ids"] == [["1", "2"]] and abs(raw["distances"][0][0]) < 1e-6
+
+    asyncio.run(run())
+
+
+@pytest.mark.timeout(900)
+def test_full_size_1m_properties(torch_cuda):
+    """BASELINE.json config 2 size (1M x 1536, top-100): size-independent properties -- planted
+    needles come back first, duplicated rows in id order, scores non-increasing, and a C-oracle
+    cross-check on a few queries."""
+    torch = torch_cuda
+    from cmw_rag_b200 import DenseStore
+
+    n, d, k = 1_000_000, 1536, 100
+    g = torch.Generator(device="cuda").manual_seed(synth.CORPUS_SEED)
+    st = DenseStore(d, n)
+    block = 125_000
+    host = np.empty((n, d), np.float32)
+    for lo in range(0, n, block):
+        x = torch.randn((block, d), generator=g, device="cuda", dtype=torch.float32)
+        x = torch.nn.functional.normalize(x, dim=1)
+        if lo == 0:
+            keep17 = x[17].clone()
+        if lo <= n // 2 < lo + block:
+            x[n // 2 - lo] = keep17
+        if lo + block == n:
+            x[block - 1] = keep17
+        st.append(x)
+        host[lo:lo + block] = x.cpu().numpy()
+    q, needle = synth.make_queries(host, 16)
+    sc, ids, fl = st.search_host(q, k, mode="f32")
+    planted = needle >= 0
+    assert (ids[planted, 0] == needle[planted]).all()
+    assert ids[1, :3].tolist() == [17, n // 2, n - 1]
+    assert (np.diff(sc, axis=1) <= 0).all()
+    assert (fl == 0).all()
+    ref_ids, ref_sc, _ = exact_topk_c(host, q[:6], k)
+    _check_exact(ids[:6], sc[:6], ref_ids, ref_sc)
+    sc1, ids1, _ = st.search_host(q[:1], k, mode="f32", algo="scan")
+    assert (ids1 == ids[:1]).all()
+    scb, idsb, _ = st.search_host(q[:6], k, mode="bf16")
+    recall = np.mean([len(set(idsb[b]) & set(ref_ids[b])) / k for b in range(6)])
+    assert recall >= 0.9
+    st.close()
