@@ -1,10 +1,341 @@
-// gemm.cu -- K2 placeholder (replaced by the tcgen05 kernel).
+// gemm.cu -- K2: tcgen05 / TMEM tensor-core filter with the top-k admission fused into the epilogue.
+//
+// Stands in for collection.query() (rag_engine/storage/vector_store.py:59-63 of the reference) for
+// batches of query vectors: the S per-segment searches RAGRetriever gathers at
+// rag_engine/retrieval/retriever.py:179-182, or thousands of independent queries.
+//
+// Shape: scores[row, query] = sum_d corpus_bf16[row, d] * query_bf16[query, d]
+//   A operand = corpus tile, 128 rows (the MMA M dimension -> the 128 TMEM lanes)
+//   B operand = query group, NT <= 256 queries (the MMA N dimension -> TMEM columns)
+//   both K-major bf16 in shared memory, 128-byte swizzle, written by TMA (cp.async.bulk.tensor.2d);
+//   fp32 accumulators in TMEM, two stages of 256 columns so the epilogue of item i overlaps the
+//   MMAs of item i+1.
+// Warp roles (192 threads, one persistent CTA per SM):
+//   warp 0   TMA producer (one elected lane): ring of [A 16 KB | B NT*128 B] stages, mbarrier tx
+//   warp 1   TMEM allocator + MMA issuer (one lane): tcgen05.mma.cta_group::1.kind::f16, K = 16,
+//            tcgen05.commit releases shared-memory stages and publishes finished accumulators
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns), multiply by the per-row multiplier
+//            (NaN for tombstoned rows), compare with the per-query admission threshold and append the
+//            rare survivors to the query's candidate pool (one global atomic each).  In the first
+//            ("dense") slab every score is written to its own slot instead.
+// The B x N score matrix is never written to memory.
+//
+// Work items: (row tile, query group), row-tile-major so that the CTAs running concurrently read the
+// same corpus rows for different query groups (one HBM read, L2 hits for the rest).
+// Algorithmic work per item: 2 * 128 * NT * D flop; HBM bytes per row tile: 128 * D * 2.
 #include "common.cuh"
+#include "ptx.cuh"
+
 namespace cmw {
-int encode_bf16_tmap(Store*) { return -1; }
-bool gemm_supported(const Store*) { return false; }
-int launch_gemm(const GemmArgs&, cudaStream_t) {
-    set_error("K2 (tcgen05 GEMM) is not built in");
-    return -1;
+
+constexpr int kGemmThreads = 192;
+constexpr int kTileM = 128;          // corpus rows per item
+constexpr int kBlockK = 64;          // bf16 elements per k-block = one 128-byte swizzle atom
+constexpr int kUmmaK = 16;
+constexpr int kMaxNT = 256;
+constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;      // TMEM columns per accumulator stage
+
+struct GemmParams {
+    int dim;
+    int num_kb;           // ceil(dim / 64)
+    int nt;               // queries per group (multiple of 16, <= 256)
+    int n_groups;
+    int batch;            // real queries
+    int64_t row_begin, row_end;
+    int n_tiles;
+    int nstages;
+    int stage_bytes;
+    int dense;
+    uint32_t idesc;
+    const float* row_mul;
+    float* pool_scores;
+    int32_t* pool_ids;
+    int32_t* pool_cnt;
+    const float* pool_thr;
+};
+
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    // K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), LBO unused,
+    // descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
 }
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // 128-byte-swizzled operand tiles must start on 1024-byte boundaries of the shared window
+    uint8_t* stages = smem + ((1024u - (ptx::smem_u32(smem) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)p.nstages * p.stage_bytes);
+    uint64_t* full = bars;                       // [kMaxStages]
+    uint64_t* empty = bars + kMaxStages;         // [kMaxStages]
+    uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int n_items = p.n_tiles * p.n_groups;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < p.nstages; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tmem_full[s], 1);
+            ptx::mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_base_smem, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint64_t pol_a = (p.n_groups > 1) ? ptx::l2_policy_evict_last() : ptx::l2_policy_evict_first();
+            const uint64_t pol_b = ptx::l2_policy_evict_last();
+            const uint32_t tx_bytes = (uint32_t)(kABytes + p.nt * kBlockK * 2);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int tile = item / p.n_groups;
+                const int group = item - tile * p.n_groups;
+                const int row0 = (int)(p.row_begin + (int64_t)tile * kTileM);
+                const int q0 = group * p.nt;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    ptx::mbar_wait(&empty[stage], phase ^ 1u);
+                    uint8_t* sa = stages + (size_t)stage * p.stage_bytes;
+                    uint8_t* sb = sa + kABytes;
+                    ptx::mbar_arrive_expect_tx(&full[stage], tx_bytes);
+                    ptx::tma_load_2d(sa, &tmap_a, kb * kBlockK, row0, &full[stage], pol_a);
+                    ptx::tma_load_2d(sb, &tmap_b, kb * kBlockK, q0, &full[stage], pol_b);
+                    if (++stage == p.nstages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(stages + (size_t)stage * p.stage_bytes);
+                    const uint32_t sb = sa + kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        const uint64_t da = make_sw128_desc(sa + k * kUmmaK * 2);
+                        const uint64_t db = make_sw128_desc(sb + k * kUmmaK * 2);
+                        ptx::umma_bf16(d_tmem, da, db, p.idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty[stage]);  // frees the stage once these MMAs have read it
+                    if (++stage == p.nstages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                ptx::umma_commit(&tmem_full[acc]);  // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter + 32) belong to this warp
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int tile = item / p.n_groups;
+            const int group = item - tile * p.n_groups;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            const int64_t row = p.row_begin + (int64_t)tile * kTileM + quarter * 32 + lane;
+            const bool row_ok = row < p.row_end;
+            const float mul = row_ok ? __ldg(p.row_mul + row) : __int_as_float(0x7fc00000);
+            const int q0 = group * p.nt;
+            int ncols = p.batch - q0;  // real (unpadded) queries in this group
+            if (ncols > p.nt) ncols = p.nt;
+
+            ptx::mbar_wait(&tmem_full[acc], acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccStride);
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                uint32_t v[32];
+                if (p.nt - c0 >= 32) {
+                    ptx::tmem_ld_32x32(taddr + (uint32_t)c0, v);
+                } else {
+                    uint32_t w[16];
+                    ptx::tmem_ld_32x16(taddr + (uint32_t)c0, w);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        v[j] = w[j];
+                        v[16 + j] = 0u;
+                    }
+                }
+                ptx::tmem_ld_wait();
+                const int cend = (ncols - c0 < 32) ? (ncols - c0) : 32;
+                if (p.dense) {
+                    const size_t slot = (size_t)(row - p.row_begin);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < cend && row_ok) {
+                            const float s = __uint_as_float(v[j]) * mul;
+                            const size_t pos = (size_t)(q0 + c0 + j) * kPoolCap + slot;
+                            p.pool_scores[pos] = (s == s) ? s : -INFINITY;
+                            p.pool_ids[pos] = (int32_t)row;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j4 = 0; j4 < 32; j4 += 4) {
+                        if (j4 < cend) {
+                            // thresholds are constant during the launch: broadcast, L1-resident loads
+                            const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.pool_thr + q0 + c0 + j4));
+                            const float th[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int j = j4 + u;
+                                const float s = __uint_as_float(v[j]) * mul;
+                                if (j < cend && s >= th[u]) {
+                                    const int q = q0 + c0 + j;
+                                    const int pos = atomicAdd(p.pool_cnt + q, 1);
+                                    if (pos < kPoolCap) {
+                                        p.pool_scores[(size_t)q * kPoolCap + pos] = s;
+                                        p.pool_ids[(size_t)q * kPoolCap + pos] = (int32_t)row;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // all tcgen05.ld of this accumulator stage have completed (wait::ld above)
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, dim] tensor, box = 64 elements (128 bytes) x box_rows, 128-byte swizzle
+static int encode_2d(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    CMW_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                    estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CMW_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+int encode_bf16_tmap(Store* s) {
+    if (s->bf16 == nullptr) return -1;
+    return encode_2d(&s->tmap_bf16, s->bf16, s->capacity, s->dim, kTileM);
+}
+
+bool gemm_supported(const Store* s) { return s->bf16 != nullptr && s->tmap_ok; }
+
+int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+    const Store* s = a.store;
+    CMW_REQUIRE(gemm_supported(s), "launch_gemm: store has no bf16 tiles / TMA descriptor");
+    if (a.row_end <= a.row_begin) return 0;
+    GemmParams p;
+    p.dim = s->dim;
+    p.num_kb = (s->dim + kBlockK - 1) / kBlockK;
+    p.nt = a.bpad < kMaxNT ? a.bpad : kMaxNT;
+    CMW_REQUIRE(p.nt % 16 == 0 && a.bpad % p.nt == 0, "launch_gemm: bad query padding %d", a.bpad);
+    p.n_groups = a.bpad / p.nt;
+    p.batch = a.batch;
+    p.row_begin = a.row_begin;
+    p.row_end = a.row_end;
+    p.n_tiles = (int)((a.row_end - a.row_begin + kTileM - 1) / kTileM);
+    p.stage_bytes = kABytes + p.nt * kBlockK * 2;
+    const size_t tail = (2 * kMaxStages + 4) * sizeof(uint64_t) + 64;
+    int nst = (int)((220 * 1024 - tail - 1024) / (size_t)p.stage_bytes);
+    if (nst > kMaxStages) nst = kMaxStages;
+    p.nstages = nst;
+    p.dense = a.dense;
+    // instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    p.row_mul = a.row_mul;
+    p.pool_scores = a.pool.scores;
+    p.pool_ids = a.pool.ids;
+    p.pool_cnt = a.pool.cnt;
+    p.pool_thr = a.pool.thr;
+    if (a.dense)
+        CMW_REQUIRE(a.row_end - a.row_begin <= kPoolCap, "launch_gemm: dense slab larger than the pool");
+    CUtensorMap tmap_b;
+    int rc = encode_2d(&tmap_b, a.q_bf16, a.bpad, s->dim, p.nt);
+    if (rc) return rc;
+    const size_t smem = (size_t)nst * p.stage_bytes + tail + 1024;  // + slack for 1024-byte alignment
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        CMW_CUDA_OK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+        smem_set = smem;
+    }
+    const int n_items = p.n_tiles * p.n_groups;
+    const int grid = n_items < s->sm_count ? n_items : s->sm_count;
+    gemm_topk_kernel<<<grid, kGemmThreads, smem, stream>>>(s->tmap_bf16, tmap_b, p);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace cmw

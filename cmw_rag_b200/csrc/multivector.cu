@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(kMvThreads) multivector_kernel(const MvParams 
         flag[first_pos] = 1;
         best_at[first_pos] = best;
     }
+    __syncthreads();
     // ---- C: candidate index = rank of the first occurrence in position order -------------------
     // (flag becomes the exclusive scan; remember which positions were heads through best_at/ids)
     for (int i = threadIdx.x; i < n2; i += blockDim.x) g_flag[i] = flag[i];  // keep a copy of the flags

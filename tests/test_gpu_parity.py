@@ -370,3 +370,40 @@ def test_full_size_1m_properties(torch_cuda):
     recall = np.mean([len(set(idsb[b]) & set(ref_ids[b])) / k for b in range(6)])
     assert recall >= 0.9
     st.close()
+
+
+@pytest.mark.parametrize("batch", [1, 7, 16, 33, 300])
+def test_gemm_filter_exact(cfg1, batch):
+    """K2 (tcgen05 GEMM filter) forced for every batch size: one partial group, exactly one group,
+    several groups (300 -> 2 groups of 256 with padding)."""
+    c = cfg1["c"]
+    q, _ = synth.make_queries(c, batch, seed=31, tie_probe=False)
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, 20)
+    sc, ids, fl = cfg1["store"].search_host(q, 20, mode="f32", algo="gemm")
+    _check_exact(ids, sc, ref_ids, ref_sc)
+    assert (fl == 0).all()
+    sc, ids, fl = cfg1["store"].search_host(q, 20, mode="bf16", algo="gemm")
+    recall = np.mean([len(set(ids[b]) & set(ref_ids[b])) / 20 for b in range(batch)])
+    assert recall >= 0.97
+    ex = np.einsum("bkd,bd->bk", c[ids].astype(np.float64), q.astype(np.float64))
+    assert np.abs(sc - ex).max() <= BF16_TOL
+
+
+def test_gemm_device_certificate_and_fallback(cfg1, torch_cuda):
+    """With an absurdly small certificate bound nothing changes; with K' = k the certificate must
+    fail for some queries on the device API and the host API must repair them through the scan."""
+    from cmw_rag_b200 import _native as N
+
+    torch = torch_cuda
+    q = cfg1["q"]
+    old = N.get_option("kprime")
+    try:
+        N.set_option("kprime", 20)
+        sc, ids, fl = cfg1["store"].search(torch.from_numpy(q).cuda(), 20, mode="f32", algo="gemm")
+        torch.cuda.synchronize()
+        assert int(fl.sum()) > 0  # K' == k leaves no room: flagged, not silently accepted
+        sc, ids, fl = cfg1["store"].search_host(q, 20, mode="f32", algo="gemm")
+    finally:
+        N.set_option("kprime", old)
+    _check_exact(ids, sc, cfg1["ref_ids"], cfg1["ref_sc"])
+    assert (fl == 0).all()
