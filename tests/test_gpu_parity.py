@@ -390,20 +390,20 @@ def test_gemm_filter_exact(cfg1, batch):
 
 
 def test_gemm_device_certificate_and_fallback(cfg1, torch_cuda):
-    """With an absurdly small certificate bound nothing changes; with K' = k the certificate must
-    fail for some queries on the device API and the host API must repair them through the scan."""
+    """An absurdly large certificate bound makes every certificate fail: the device API must flag the
+    queries (never silently accept), the host API must repair them through the fp32 scan filter."""
     from cmw_rag_b200 import _native as N
 
     torch = torch_cuda
     q = cfg1["q"]
-    old = N.get_option("kprime")
+    old = N.get_option("bf16_eps")
     try:
-        N.set_option("kprime", 20)
+        N.set_option("bf16_eps", 0.5)
         sc, ids, fl = cfg1["store"].search(torch.from_numpy(q).cuda(), 20, mode="f32", algo="gemm")
         torch.cuda.synchronize()
-        assert int(fl.sum()) > 0  # K' == k leaves no room: flagged, not silently accepted
+        assert int(fl.sum()) == q.shape[0]
         sc, ids, fl = cfg1["store"].search_host(q, 20, mode="f32", algo="gemm")
     finally:
-        N.set_option("kprime", old)
+        N.set_option("bf16_eps", old)
     _check_exact(ids, sc, cfg1["ref_ids"], cfg1["ref_sc"])
     assert (fl == 0).all()
