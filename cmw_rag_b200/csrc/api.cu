@@ -278,9 +278,9 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
         return 0;
     };
 
-    auto compact = [&]() -> int {
+    auto compact = [&](bool last) -> int {
         PhaseTimer t(1, stream);
-        return launch_pool_compact(pool, batch, kprime, stream);
+        return launch_pool_compact(pool, batch, kprime, last ? 1 : 0, stream);
     };
 
     const int64_t rows = s->rows;
@@ -292,7 +292,7 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
         const int64_t slab0 = rows < kDenseSlabRows ? rows : kDenseSlabRows;
         if ((rc = launch_pool_set_count(pool, batch, (int)slab0, stream))) return rc;
         if ((rc = run_filter(0, slab0, 1))) return rc;
-        if ((rc = compact())) return rc;
+        if ((rc = compact(slab0 == rows))) return rc;
         seen = slab0;
         while (seen < rows) {
             int64_t m, end;
@@ -309,7 +309,7 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
                 if (end > rows || rows - end < 4096) end = rows;
             }
             if ((rc = run_filter(seen, end, 0))) return rc;
-            if ((rc = compact())) return rc;
+            if ((rc = compact(end == rows))) return rc;
             seen = end;
         }
     }

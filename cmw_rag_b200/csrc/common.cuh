@@ -139,7 +139,7 @@ int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric
                         float* q_f32, __nv_bfloat16* q_bf16, cudaStream_t stream);
 int launch_pool_reset(Pool pool, int batch, cudaStream_t stream);
 int launch_pool_set_count(Pool pool, int batch, int count, cudaStream_t stream);
-int launch_pool_compact(Pool pool, int batch, int kprime, cudaStream_t stream);
+int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_t stream);
 // exact fp64 rescoring of the pool's first min(cnt, kprime) entries + final (score desc, id asc)
 // selection with the exactness certificate
 int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprime, int metric,

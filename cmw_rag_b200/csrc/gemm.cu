@@ -37,6 +37,7 @@ constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KB
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;      // TMEM columns per accumulator stage
+constexpr int kStageCap = 512;       // staged survivors per epilogue warp (8 bytes each)
 
 struct GemmParams {
     int dim;
@@ -64,6 +65,24 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
            (2ull << 61);
 }
 
+// Append the survivors a warp staged in shared memory to their queries' pools: every lane takes one
+// entry, so 32 global atomics are in flight per round trip instead of one per admitted column.
+__device__ __forceinline__ void flush_staged(const uint2* stg, int wcount, int lane, int64_t row_warp0,
+                                             const GemmParams& p) {
+    __syncwarp();
+    for (int e = lane; e < wcount; e += 32) {
+        const uint2 en = stg[e];
+        const int q = (int)(en.y >> 5);
+        const int64_t row = row_warp0 + (int)(en.y & 31u);
+        const int pos = atomicAdd(p.pool_cnt + q, 1);
+        if (pos < kPoolCap) {
+            p.pool_scores[(size_t)q * kPoolCap + pos] = __uint_as_float(en.x);
+            p.pool_ids[(size_t)q * kPoolCap + pos] = (int32_t)row;
+        }
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
@@ -79,6 +98,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint2* stage_buf = reinterpret_cast<uint2*>(tmem_empty + 4);  // [4 warps][kStageCap] survivors
 
     const int n_items = p.n_tiles * p.n_groups;
 
@@ -166,13 +186,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter + 32) belong to this warp
+        uint2* stg = stage_buf + (size_t)(warp - 2) * kStageCap;
+        const uint32_t lanemask_lt = (1u << lane) - 1u;
+        int wcount = 0;  // survivors staged by this warp (warp-uniform)
         int it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int tile = item / p.n_groups;
             const int group = item - tile * p.n_groups;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-            const int64_t row = p.row_begin + (int64_t)tile * kTileM + quarter * 32 + lane;
+            const int64_t row_warp0 = p.row_begin + (int64_t)tile * kTileM + quarter * 32;
+            const int64_t row = row_warp0 + lane;
             const bool row_ok = row < p.row_end;
             const float mul = row_ok ? __ldg(p.row_mul + row) : __int_as_float(0x7fc00000);
             const int q0 = group * p.nt;
@@ -215,27 +239,45 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             // thresholds are constant during the launch: broadcast, L1-resident loads
                             const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.pool_thr + q0 + c0 + j4));
                             const float th[4] = {t4.x, t4.y, t4.z, t4.w};
+                            float sc[4];
+                            bool pass[4];
+                            bool any = false;
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const int j = j4 + u;
-                                const float s = __uint_as_float(v[j]) * mul;
-                                if (j < cend && s >= th[u]) {
-                                    const int q = q0 + c0 + j;
-                                    const int pos = atomicAdd(p.pool_cnt + q, 1);
-                                    if (pos < kPoolCap) {
-                                        p.pool_scores[(size_t)q * kPoolCap + pos] = s;
-                                        p.pool_ids[(size_t)q * kPoolCap + pos] = (int32_t)row;
+                                sc[u] = __uint_as_float(v[j4 + u]) * mul;
+                                pass[u] = (j4 + u < cend) && (sc[u] >= th[u]);
+                                any |= pass[u];
+                            }
+                            if (__any_sync(0xffffffffu, any)) {
+                                // rare: stage the survivors of these 4 columns in the warp's buffer
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const uint32_t m = __ballot_sync(0xffffffffu, pass[u]);
+                                    if (pass[u]) {
+                                        const int e = wcount + __popc(m & lanemask_lt);
+                                        stg[e] = make_uint2(__float_as_uint(sc[u]),
+                                                            ((uint32_t)(q0 + c0 + j4 + u) << 5) | (uint32_t)lane);
                                     }
+                                    wcount += __popc(m);
+                                }
+                                if (wcount > kStageCap - 128) {
+                                    flush_staged(stg, wcount, lane, row_warp0, p);
+                                    wcount = 0;
                                 }
                             }
                         }
                     }
                 }
             }
-            // all tcgen05.ld of this accumulator stage have completed (wait::ld above)
+            // all tcgen05.ld of this accumulator stage have completed (wait::ld above): hand the
+            // accumulator back to the MMA warp before the (global-atomic) flush of the survivors
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+            if (wcount > 0) {
+                flush_staged(stg, wcount, lane, row_warp0, p);
+                wcount = 0;
+            }
         }
     }
 
@@ -306,7 +348,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.row_end = a.row_end;
     p.n_tiles = (int)((a.row_end - a.row_begin + kTileM - 1) / kTileM);
     p.stage_bytes = kABytes + p.nt * kBlockK * 2;
-    const size_t tail = (2 * kMaxStages + 4) * sizeof(uint64_t) + 64;
+    const size_t tail = (2 * kMaxStages + 4) * sizeof(uint64_t) + 64 + 4 * kStageCap * sizeof(uint2);
     int nst = (int)((220 * 1024 - tail - 1024) / (size_t)p.stage_bytes);
     if (nst > kMaxStages) nst = kMaxStages;
     p.nstages = nst;

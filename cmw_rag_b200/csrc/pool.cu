@@ -91,34 +91,146 @@ int launch_pool_set_count(Pool pool, int batch, int count, cudaStream_t stream) 
     return 0;
 }
 
-// One CTA per query: sort the pool by (score desc, id asc), keep the best kprime, publish the
-// admission threshold for the next slab.
-__global__ void __launch_bounds__(512) pool_compact_kernel(Pool pool, int kprime) {
-    __shared__ uint64_t keys[kPoolCap];
+// One CTA per query.  Intermediate slabs only need the best kprime entries and the admission
+// threshold, not their order: an MSB-first radix select (4 passes of 8 bits over the order-preserving
+// score keys, shared-memory histograms) finds the kprime-th best score T, entries with score >= T are
+// compacted to the front (all ties at T are kept, so the `score >= thr` admission rule and the pool
+// stay consistent) and thr is raised to T.  The last call (final = 1) also sorts the survivors by
+// (score desc, id asc) and truncates to kprime -- the order K3 / the bf16 emit rely on.
+constexpr int kCompactThreads = 256;
+constexpr int kCompactPer = kPoolCap / kCompactThreads;  // 16 entries per thread, in registers
+
+__global__ void __launch_bounds__(kCompactThreads) pool_compact_kernel(Pool pool, int kprime, int final) {
+    extern __shared__ __align__(16) uint8_t cmp_smem[];
+    __shared__ int hist[256];
+    __shared__ int warp_sums[32];
+    __shared__ int sel_digit, sel_below;
     const int b = blockIdx.x;
+    const int t = threadIdx.x;
     const int n_in = pool.cnt[b];
     const int n = n_in < kPoolCap ? n_in : kPoolCap;
     float* sc = pool.scores + (size_t)b * kPoolCap;
     int32_t* id = pool.ids + (size_t)b * kPoolCap;
-    int m = next_pow2(n < 2 ? 2 : n);
-    for (int i = threadIdx.x; i < m; i += blockDim.x)
-        keys[i] = (i < n) ? desc_key(sc[i], (uint32_t)id[i]) : ~0ull;
-    bitonic_sort_u64(keys, m);
-    const int keep = n < kprime ? n : kprime;
-    for (int i = threadIdx.x; i < keep; i += blockDim.x) {
-        const uint64_t k = keys[i];
-        sc[i] = desc_key_score(k);
-        id[i] = (int32_t)(uint32_t)k;
+
+    // ascending key = better score
+    uint32_t key[kCompactPer];
+    int32_t rid[kCompactPer];
+#pragma unroll
+    for (int j = 0; j < kCompactPer; ++j) {
+        const int i = t + j * kCompactThreads;
+        key[j] = 0xffffffffu;
+        rid[j] = -1;
+        if (i < n) {
+            key[j] = (uint32_t)(desc_key(sc[i], 0u) >> 32);
+            rid[j] = id[i];
+        }
     }
-    if (threadIdx.x == 0) {
-        pool.cnt[b] = keep;
-        pool.thr[b] = (n >= kprime) ? desc_key_score(keys[kprime - 1]) : -INFINITY;
-        if (n_in > kPoolCap) pool.ovf[b] = 1;
+    uint32_t T = 0xffffffffu;  // keep everything
+    const bool select = n > kprime;
+    if (select) {
+        uint32_t prefix = 0, mask = 0;
+        int remaining = kprime;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            hist[t] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < kCompactPer; ++j) {
+                if (rid[j] >= 0 && (key[j] & mask) == prefix) atomicAdd(&hist[(key[j] >> shift) & 255u], 1);
+            }
+            __syncthreads();
+            // inclusive scan of the 256 bins (one per thread)
+            const int h = hist[t];
+            int v = h;
+            const int lane = t & 31, w = t >> 5;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += u;
+            }
+            if (lane == 31) warp_sums[w] = v;
+            __syncthreads();
+            int base = 0;
+            for (int ww = 0; ww < w; ++ww) base += warp_sums[ww];
+            const int cum = base + v;
+            if (cum >= remaining && cum - h < remaining) {
+                sel_digit = t;
+                sel_below = cum - h;
+            }
+            __syncthreads();
+            prefix |= (uint32_t)sel_digit << shift;
+            mask |= 0xffu << shift;
+            remaining -= sel_below;
+            __syncthreads();
+        }
+        T = prefix;
+    } else {
+        __syncthreads();
+    }
+    // stream compaction of the kept entries (every entry was read into registers above)
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < kCompactPer; ++j) mine += (rid[j] >= 0 && key[j] <= T) ? 1 : 0;
+    {
+        const int lane = t & 31, w = t >> 5;
+        int v = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        if (lane == 31) warp_sums[w] = v;
+        __syncthreads();
+        int base = 0;
+        for (int ww = 0; ww < w; ++ww) base += warp_sums[ww];
+        int total = 0;
+        for (int ww = 0; ww < kCompactThreads / 32; ++ww) total += warp_sums[ww];
+        int pos = base + v - mine;
+        if (!final) {
+#pragma unroll
+            for (int j = 0; j < kCompactPer; ++j) {
+                if (rid[j] >= 0 && key[j] <= T) {
+                    sc[pos] = f32_from_orderable(~key[j]);
+                    id[pos] = rid[j];
+                    ++pos;
+                }
+            }
+            if (t == 0) {
+                pool.cnt[b] = total;
+                if (select) pool.thr[b] = f32_from_orderable(~T);
+                if (n_in > kPoolCap) pool.ovf[b] = 1;
+            }
+            return;
+        }
+        // final: sort the survivors by (score desc, id asc), keep kprime
+        uint64_t* keys = reinterpret_cast<uint64_t*>(cmp_smem);
+        const int m = next_pow2(total < 2 ? 2 : total);
+        for (int i = total + t; i < m; i += kCompactThreads) keys[i] = ~0ull;
+#pragma unroll
+        for (int j = 0; j < kCompactPer; ++j) {
+            if (rid[j] >= 0 && key[j] <= T) {
+                keys[pos] = ((uint64_t)key[j] << 32) | (uint64_t)(uint32_t)rid[j];
+                ++pos;
+            }
+        }
+        bitonic_sort_u64(keys, m);
+        const int keep = total < kprime ? total : kprime;
+        for (int i = t; i < keep; i += kCompactThreads) {
+            const uint64_t k = keys[i];
+            sc[i] = desc_key_score(k);
+            id[i] = (int32_t)(uint32_t)k;
+        }
+        if (t == 0) {
+            pool.cnt[b] = keep;
+            if (total >= kprime) pool.thr[b] = desc_key_score(keys[kprime - 1]);
+            if (n_in > kPoolCap) pool.ovf[b] = 1;
+        }
     }
 }
 
-int launch_pool_compact(Pool pool, int batch, int kprime, cudaStream_t stream) {
-    pool_compact_kernel<<<batch, 512, 0, stream>>>(pool, kprime);
+int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_t stream) {
+    const size_t smem = final ? (size_t)kPoolCap * sizeof(uint64_t) : 0;
+    pool_compact_kernel<<<batch, kCompactThreads, smem, stream>>>(pool, kprime, final);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
@@ -133,12 +245,24 @@ __global__ void __launch_bounds__(256)
 rescore_kernel(const float* __restrict__ f32, const double* __restrict__ norm64,
                const float* __restrict__ live, int dim, Pool pool, int kprime, int metric,
                const float* __restrict__ q_raw, const double* __restrict__ qn64,
-               double* __restrict__ exact) {
+               const uint32_t* __restrict__ maxnorm_bits, int k, double eps, double* __restrict__ exact) {
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int n = pool.cnt[b] < kprime ? pool.cnt[b] : kprime;
     if (j >= n) return;
+    // The pool is sorted by filter score.  With a_k its k-th filter score, every row whose filter score
+    // is below a_k - 2*eps has an exact score below a_k - eps <= (k-th exact score): it cannot be in the
+    // exact top-k, so it is not rescored (its slot gets -inf and sorts last).
+    if (n > k) {
+        double e = eps;
+        if (metric == CMW_METRIC_IP) e *= qn64[b] * (double)__uint_as_float(*maxnorm_bits);
+        const double cut = (double)pool.scores[(size_t)b * kPoolCap + (k - 1)] - 2.0 * e;
+        if ((double)pool.scores[(size_t)b * kPoolCap + j] < cut) {
+            if (lane == 0) exact[(size_t)b * kprime + j] = -INFINITY;
+            return;
+        }
+    }
     const int32_t id = pool.ids[(size_t)b * kPoolCap + j];
     const float4* row = reinterpret_cast<const float4*>(f32 + (size_t)id * dim);
     const float4* qv = reinterpret_cast<const float4*>(q_raw + (size_t)b * dim);
@@ -232,7 +356,7 @@ int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprim
     const int wpb = 8;
     dim3 grid((kprime + wpb - 1) / wpb, batch);
     rescore_kernel<<<grid, wpb * 32, 0, stream>>>(s->f32, s->norm64, s->live, s->dim, pool, kprime,
-                                                 metric, q_raw, qn64, exact_ws);
+                                                 metric, q_raw, qn64, s->maxnorm_bits, k, eps, exact_ws);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     const size_t smem = (size_t)next_pow2_host(kprime) * 16;
