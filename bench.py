@@ -247,11 +247,11 @@ def run_ours(args):
         if not row_shard:
             return st.search(q, k, mode=args.mode, algo=args.algo)
         sc, ids, fl, s64 = st.search(q, k, mode=args.mode, algo=args.algo, return_scores64=True)
-        g_s = torch.empty((world,) + s64.shape, dtype=s64.dtype, device=device)
-        g_i = torch.empty((world,) + ids.shape, dtype=ids.dtype, device=device)
+        g_s = torch.empty((world * B, k), dtype=s64.dtype, device=device)
+        g_i = torch.empty((world * B, k), dtype=ids.dtype, device=device)
         dist.all_gather_into_tensor(g_s, s64)
         dist.all_gather_into_tensor(g_i, ids)
-        ms, mi, _ = merge_topk(g_s, g_i, k)
+        ms, mi, _ = merge_topk(g_s.view(world, B, k), g_i.view(world, B, k), k)
         return ms, mi, fl
 
     def barrier():

@@ -12,7 +12,7 @@
 //   :307      articles.sort(key=score, reverse=True)  -- stable
 //
 // One CTA per long query; everything is integer/compare work in shared memory (bitonic sorts +
-// block scans), bit-exact against oracle/multivector.py by construction.
+// block scans), checked bit for bit against the CPU restatement in the parity tests.
 #include "common.cuh"
 
 namespace cmw {

@@ -1,7 +1,7 @@
 """kbId normalisation on the host -- the grouping key of the multi-vector reduction.
 
 Mirrors ``extract_numeric_kbid`` (rag_engine/utils/metadata_utils.py:20-32 of the reference: the
-leading run of ASCII digits of ``str(kb_id)``, else None) and the key the retriever builds from
+leading run of decimal digits of ``str(kb_id)``, else None) and the key the retriever builds from
 it (rag_engine/retrieval/retriever.py:236-239: falsy kbId -> chunk skipped; otherwise the numeric
 prefix, falling back to ``str(kbId)``).  Strings stay on the host; the device sees a dense int32
 group number per row (``kb_gid``), assigned at ingest.
@@ -14,7 +14,7 @@ def extract_numeric_kbid(kb_id) -> str | None:
         return None
     s = str(kb_id)
     n = 0
-    while n < len(s) and s[n] in "0123456789":
+    while n < len(s) and s[n].isdecimal():  # regex \d of the reference = Unicode decimal digits
         n += 1
     return s[:n] if n else None
 

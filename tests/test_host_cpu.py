@@ -1,0 +1,266 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol the header declares,
+the compute entry points fail loudly without a device, and the host logic of the Python layer
+(kbId keys, where-filters, sidecar bookkeeping, await coalescing, shard plumbing) behaves like the
+reference's store.  Where a search result is needed the oracle is injected as the backend -- test
+infrastructure only; the product classes have no CPU path of their own."""
+from __future__ import annotations
+
+import asyncio
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import exact_topk, merge_topk as oracle_merge
+from oracle.multivector import extract_numeric_kbid as oracle_kbid, group_key as oracle_group_key
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session")
+def native():
+    from cmw_rag_b200 import build
+
+    build.build()
+    from cmw_rag_b200 import _native
+
+    return _native
+
+
+def test_library_exports_every_declared_symbol(native):
+    with open(os.path.join(ROOT, "include", "cmw_dense.h")) as f:
+        header = f.read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(cmw_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(native.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/cmw_dense.h but not exported"
+    assert declared == set(native.SIGNATURES), declared ^ set(native.SIGNATURES)
+    assert native.lib().cmw_abi_version() == int(re.search(r"CMW_ABI_VERSION (\d+)", header).group(1))
+
+
+def test_no_cpu_fallback(native):
+    """Without a CUDA device the store cannot be created and says why."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    from cmw_rag_b200 import DenseStore
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        DenseStore(1536, 16)
+    assert native.kernel_launches() == 0
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under cmw_rag_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "cmw_rag_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+                assert "liboracle" not in src and "oracle_topk" not in src and "oracle." not in src, fn
+
+
+def test_kbid_keys_match_reference_behaviour():
+    from cmw_rag_b200 import extract_numeric_kbid, group_key
+
+    for v in ["4578-toc", "abc", 12, None, "", "12ab34", "007", "-5", " 12", 0, "٣٤"]:
+        assert extract_numeric_kbid(v) == oracle_kbid(v), v
+        assert group_key(v) == oracle_group_key(v), v
+
+
+def test_where_filter():
+    from cmw_rag_b200.store import _match
+
+    meta = {"kbId": "12", "n": 3, "flag": True}
+    assert _match(meta, None) and _match(meta, {})
+    assert _match(meta, {"kbId": "12"}) and not _match(meta, {"kbId": 12})
+    assert not _match(meta, {"missing": 1})
+    assert _match(meta, {"n": {"$eq": 3}}) and not _match(meta, {"n": {"$ne": 3}})
+    assert _match(meta, {"n": {"$in": [1, 3]}}) and _match(meta, {"n": {"$nin": [1, 2]}})
+    assert _match(meta, {"$and": [{"kbId": "12"}, {"n": 3}]})
+    assert _match(meta, {"$or": [{"kbId": "x"}, {"flag": True}]})
+    assert not _match(meta, {"$and": [{"kbId": "12"}, {"n": 4}]})
+
+
+class FakeDense:
+    """Stands in for DenseStore in host-logic tests: answers with the oracle."""
+
+    def __init__(self, dim, capacity, device=0, f32=True, bf16=True, id_offset=0):
+        self.dim, self.id_offset = dim, id_offset
+        self.rows_ = np.zeros((0, dim), np.float32)
+        self.live = np.zeros((0,), bool)
+        self.gid = np.zeros((0,), np.int32)
+        self.calls = []
+
+    def append(self, rows, kb_gid=None):
+        rows = np.asarray(rows, np.float32)
+        self.rows_ = np.concatenate([self.rows_, rows])
+        self.live = np.concatenate([self.live, np.ones(len(rows), bool)])
+        self.gid = np.concatenate([self.gid, np.asarray(kb_gid, np.int32) if kb_gid is not None
+                                   else np.full(len(rows), -1, np.int32)])
+
+    def tombstone(self, rows):
+        self.live[np.asarray(rows, np.int64)] = False
+
+    def search_host(self, q, k, metric="cosine", mode="f32", algo=None):
+        self.calls.append(q.shape[0])
+        ids, sc, _ = exact_topk(self.rows_, q, k, metric=metric, live=self.live, id_offset=self.id_offset)
+        return sc, ids, np.zeros(q.shape[0], np.int32)
+
+
+@pytest.fixture()
+def fake_store(monkeypatch):
+    import cmw_rag_b200.store as store_mod
+
+    monkeypatch.setattr(store_mod, "DenseStore", FakeDense)
+    return store_mod.B200Store(collection_name="t", capacity=1024)
+
+
+def test_store_mirrors_reference_store_tests(fake_store):
+    """rag_engine/tests/test_storage_vector_store.py:10-70 of the reference, against B200Store."""
+    store = fake_store
+
+    async def run():
+        await store.add_async(texts=["a", "b"], metadatas=[{"kbId": "doc1"}, {"kbId": "doc2"}],
+                              ids=["1", "2"], embeddings=[[0.1, 0.0, 0.0], [0.0, 0.1, 0.0]])
+        results = await store.similarity_search_async(query_embedding=[0.1, 0.0, 0.0], k=1)
+        assert len(results) == 1 and results[0].metadata["kbId"] == "doc1"
+        assert results[0].page_content == "a"
+        await store.add_async(texts=["t"], metadatas=[{"doc_stable_id": "D", "kbId": "k9", "file_mtime_epoch": 5}],
+                              ids=["x"], embeddings=[[0.0, 0.0, 1.0]])
+        meta = await store.get_any_doc_meta_async({"doc_stable_id": "D"})
+        assert meta["file_mtime_epoch"] == 5
+        assert (await store.get_by_kb_id_async("k9"))["doc_stable_id"] == "D"
+        assert await store.get_by_kb_id_async("nope") is None
+        await store.delete_where_async({"doc_stable_id": "D"})
+        assert await store.get_any_doc_meta_async({"doc_stable_id": "D"}) is None
+        assert store.count() == 2
+        # a deleted row is never returned, and k larger than the collection returns fewer results
+        res = await store.similarity_search_async(query_embedding=[0.0, 0.0, 1.0], k=5)
+        assert len(res) == 2
+        # adding a known id again is ignored (Chroma add semantics), new ids are appended
+        await store.add_async(texts=["dup", "new"], metadatas=[{"kbId": "zz"}, {"kbId": "doc3-toc"}],
+                              ids=["1", "3"], embeddings=[[1.0, 0, 0], [0, 0, 1.0]])
+        assert store.count() == 3
+        got = await store.similarity_search_async(query_embedding=[0.0, 0.0, 1.0], k=1)
+        assert got[0].metadata["kbId"] == "doc3-toc"
+        col = await store.get_collection()
+        raw = await col.query(query_embeddings=[[0.1, 0.0, 0.0]], n_results=2, include=["documents", "metadatas"])
+        assert raw["ids"] == [["1", "2"]] and raw["documents"] == [["a", "b"]] and raw["distances"] is None
+        assert await col.count() == 3
+        with pytest.raises(ValueError):
+            await store.add_async(texts=["q"], metadatas=[{}], ids=["9"], embeddings=[[1.0, 2.0]])  # wrong dim
+
+    asyncio.run(run())
+    assert store.gid_for("doc3") == store.gid_for("doc3-toc") or store.gid_for("doc3-toc") >= 0
+    assert store.gid_for("") == -1 and store.gid_for(None) == -1
+    assert store.gid_for("4578-toc") == store.gid_for("4578")
+
+
+def test_seam_and_await_coalescing(fake_store):
+    """rag_engine/tests/test_retrieval_vector_search.py:11-20 (kwargs passed literally) and the
+    fan-out of retriever.py:179-182: S concurrent awaits become ONE batched search."""
+    from cmw_rag_b200 import top_k_search_async
+
+    store = fake_store
+    rng = np.random.default_rng(0)
+    emb = rng.standard_normal((50, 8)).astype(np.float32)
+    store.add([f"t{i}" for i in range(50)], [{"stable_id": f"{i:04d}", "kbId": str(100 + i // 5)} for i in range(50)],
+              ids=[f"{i:04d}" for i in range(50)], embeddings=emb)
+    qs = rng.standard_normal((4, 8)).astype(np.float32)
+
+    async def run():
+        outs = await asyncio.gather(*[top_k_search_async(store, q.tolist(), k=3 + i) for i, q in enumerate(qs)])
+        return outs
+
+    outs = asyncio.run(run())
+    assert store.dense.calls == [4]  # one launch for the four awaits
+    ids, _, _ = exact_topk(emb, qs, 6)
+    for i, docs in enumerate(outs):
+        assert [d.metadata["stable_id"] for d in docs] == [f"{r:04d}" for r in ids[i, : 3 + i]]
+    assert store.stats["max_batch"] == 4 and store.stats["launch_batches"] == 1
+
+    class Recorder:
+        def __init__(self):
+            self.kw = None
+
+        async def similarity_search_async(self, **kw):
+            self.kw = kw
+            return ["x"]
+
+    rec = Recorder()
+    assert asyncio.run(top_k_search_async(rec, [0.1, 0.2], 3)) == ["x"]
+    assert rec.kw == {"query_embedding": [0.1, 0.2], "k": 3}
+
+
+def test_shard_bounds():
+    from cmw_rag_b200.sharded import shard_bounds
+
+    assert shard_bounds(10, 1) == [(0, 10)]
+    assert shard_bounds(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert shard_bounds(3, 8)[3:] == [(3, 3)] * 5
+    b = shard_bounds(200_000_000, 8)
+    assert b[0] == (0, 25_000_000) and b[-1] == (175_000_000, 200_000_000)
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import synth
+from oracle import exact_topk, merge_topk
+from cmw_rag_b200.sharded import ShardedSearcher, shard_bounds
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n, d, k = 1003, 32, 10
+c = synth.make_corpus(n, d, seed=1)
+q, _ = synth.make_queries(c, 7, seed=2)
+lo, hi = shard_bounds(n, world)[rank]
+def local_search(qt, k, **kw):
+    ids, sc, sc64 = exact_topk(c[lo:hi], qt.numpy(), k, id_offset=lo)
+    return torch.from_numpy(sc64), torch.from_numpy(ids), torch.zeros(qt.shape[0], dtype=torch.int32)
+def merge(s64, ids, k):
+    mi, ms = merge_topk(ids.numpy(), s64.numpy(), k)
+    return torch.from_numpy(ms), torch.from_numpy(mi), None
+s = ShardedSearcher(local_search=local_search, merge=merge)
+ms, mi, fl = s.search(torch.from_numpy(q), k)
+gi, gs, _ = exact_topk(c, q, k)
+assert (mi.numpy() == gi).all(), (rank, mi, gi)
+assert np.abs(ms.numpy() - gs).max() == 0.0
+# a world larger than the corpus: empty shards contribute only padding
+tiny = c[:1]
+lo2, hi2 = shard_bounds(1, world)[rank]
+def ls2(qt, k, **kw):
+    ids, sc, sc64 = exact_topk(tiny[lo2:hi2], qt.numpy(), k, id_offset=lo2) if hi2 > lo2 else (
+        np.full((qt.shape[0], k), -1, np.int64), None, np.full((qt.shape[0], k), -np.inf))
+    return torch.from_numpy(sc64), torch.from_numpy(ids), None
+ms, mi, _ = ShardedSearcher(local_search=ls2, merge=merge).search(torch.from_numpy(q), 3)
+assert (mi.numpy()[:, 0] == 0).all() and (mi.numpy()[:, 1:] == -1).all()
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_sharded_search_world_size_2_gloo(tmp_path):
+    """The N > 1 path under gloo on CPU: shard bounds, id offsets, all-gather layout, merge."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    res = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+        capture_output=True, text=True, timeout=300, env=env)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert res.stdout.count("ok") == 2
