@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--shard", default="queries", choices=["queries", "rows"])
     ap.add_argument("--no-f32", action="store_true", help="bf16 tiles only (rows-sharded 200M config)")
     ap.add_argument("--cpu-queries", type=int, default=16, help="queries in the bounded CPU sample")
+    ap.add_argument("--hnsw-rows", type=int, default=50_000, help="rows in the CPU HNSW index (bounded sample)")
+    ap.add_argument("--hnsw-queries", type=int, default=512)
+    ap.add_argument("--skip-cpu-exact", action="store_true")
     ap.add_argument("--skip-b1", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     return ap.parse_args()
@@ -142,6 +145,35 @@ def cpu_exact_sample(corpus: np.ndarray, queries: np.ndarray, k: int, steps: int
     return queries.shape[0] * steps / dt, dt, num_threads()
 
 
+def cpu_hnsw_sample(corpus: np.ndarray, queries: np.ndarray, k: int, index_rows: int, steps: int = 1):
+    """The "Chroma HNSW" baseline (BASELINE.json north_star): an hnswlib-equivalent index with
+    Chroma's defaults (M=16, ef_construction=100, ef_search=100) over the first `index_rows` rows,
+    all host threads, one query per thread.  Returns (qps, recall@k vs exact on the same rows,
+    build seconds, threads)."""
+    from oracle.cport import exact_topk_c
+    from oracle.hnsw import HnswIndex, num_threads
+
+    sub = corpus[:index_rows]
+    ix = HnswIndex(sub.shape[1], sub.shape[0])
+    t0 = time.perf_counter()
+    ix.add(sub)
+    build_s = time.perf_counter() - t0
+    ix.search(queries[:8], k)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ids, _ = ix.search(queries, k)
+    dt = time.perf_counter() - t0
+    nref = min(64, queries.shape[0])
+    ref, _, _ = exact_topk_c(sub, queries[:nref], k)
+    recall = float(np.mean([len(set(ids[b]) & set(ref[b])) / k for b in range(nref)]))
+    ix.close()
+    return queries.shape[0] * steps / dt, recall, build_s, num_threads()
+
+
+HNSW_LABEL = ("hnswlib-equivalent HNSW re-implementation (oracle/hnsw/hnsw_baseline.cpp), chromadb 1.3.0 "
+              "defaults assumed (M=16, ef_construction=100, ef_search=100), not verifiable offline")
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  The
     reference delegates the arithmetic to chromadb/hnswlib (not installable here); the timed code is
@@ -150,29 +182,39 @@ def run_reference(args):
     if rank != 0:
         return
     import synth
+    from oracle.hnsw import HnswIndex, num_threads
 
-    corpus = host_corpus(args.rows, args.dim)
-    nq = max(1, args.cpu_queries)
+    index_rows = min(args.rows, args.hnsw_rows)
+    corpus = host_corpus(index_rows, args.dim)
+    nq = max(16, args.hnsw_queries)
     q, _ = synth.make_queries(corpus, nq, seed=7, tie_probe=False)
-    from oracle.cport import exact_topk_c, num_threads
-
-    for _ in range(max(1, min(args.warmup, 1))):
-        exact_topk_c(corpus, q[:2], args.k)
+    ix = HnswIndex(args.dim, index_rows)
+    t0 = time.perf_counter()
+    ix.add(corpus)
+    build_s = time.perf_counter() - t0
+    for _ in range(max(1, args.warmup)):
+        ix.search(q[:16], args.k)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        exact_topk_c(corpus, q, args.k)
+        ids, _ = ix.search(q, args.k)
     dt = time.perf_counter() - t0
     qps = nq * args.steps / dt
+    from oracle.cport import exact_topk_c
+
+    nref = min(64, nq)
+    ref, _, _ = exact_topk_c(corpus, q[:nref], args.k)
+    recall = float(np.mean([len(set(ids[b]) & set(ref[b])) / args.k for b in range(nref)]))
+    sample = (f"{nq} queries per step against an HNSW index over {index_rows} rows "
+              f"({'the full corpus' if index_rows == args.rows else 'a subsample of the ' + str(args.rows) + '-row corpus; HNSW cost grows ~log N, so this flatters the CPU'}), "
+              f"index build {build_s:.1f} s (not timed), recall@{args.k} {recall:.3f} vs exact; {HNSW_LABEL}")
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.rows}x{args.dim} fp32 corpus, top-{args.k} exact cosine, "
-                               f"{nq} queries per step (bounded sample of the {args.batch}-query batch)"},
-        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": num_threads(), "kind": "port",
-                         "sample": f"{nq} queries x {args.rows} rows per step, exact fp64 brute force "
-                                   "(oracle/c/oracle_topk.c, OpenMP); the reference's own backend "
-                                   "(chromadb 1.3.0 / hnswlib) is not installable offline"},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.rows}x{args.dim} fp32 corpus, top-{args.k} cosine, "
+                               f"query batch {args.batch} per GPU (CPU arm: {nq}-query sample per step)"},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": num_threads(), "kind": "port", "sample": sample,
+                         "recall_at_k": recall, "index_rows": index_rows, "build_s": build_s},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -382,14 +424,21 @@ def run_ours(args):
     if world == 1 and not args.skip_cpu:
         import synth
 
-        # the same bits the GPU holds: read the first rows back is not enough for a full scan, so the
-        # CPU sample regenerates an equally shaped corpus on the host (seeded) -- same workload size.
-        corpus = host_corpus(args.rows, args.dim)
-        cq, _ = synth.make_queries(corpus, args.cpu_queries, seed=7, tie_probe=False)
-        qps, dt, threads = cpu_exact_sample(corpus, cq, k)
+        # an equally shaped, equally seeded corpus on the host (same workload, bounded sample)
+        index_rows = min(args.rows, args.hnsw_rows)
+        corpus = host_corpus(args.rows if not args.skip_cpu_exact else index_rows, args.dim)
+        cq, _ = synth.make_queries(corpus[:index_rows], max(16, args.hnsw_queries), seed=7, tie_probe=False)
+        qps, recall, build_s, threads = cpu_hnsw_sample(corpus, cq, k, index_rows)
         cpu = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_queries} queries x {args.rows} rows, exact fp64 brute force "
-                         f"(oracle/c/oracle_topk.c, OpenMP, {dt:.1f} s)"}
+               "sample": f"{cq.shape[0]} queries against an HNSW index over a {index_rows}-row subsample "
+                         f"(build {build_s:.1f} s, not timed; HNSW cost grows ~log N, so the subsample flatters "
+                         f"the CPU), recall@{k} {recall:.3f} vs exact; {HNSW_LABEL}",
+               "recall_at_k": recall, "index_rows": index_rows, "build_s": build_s}
+        if not args.skip_cpu_exact:
+            xq, dt, xthreads = cpu_exact_sample(corpus, cq[: args.cpu_queries], k)
+            cpu["exact_port"] = {"value": xq, "unit": UNIT, "cores": xthreads,
+                                 "sample": f"{args.cpu_queries} queries x {args.rows} rows, exact fp64 brute force "
+                                           f"(oracle/c/oracle_topk.c, OpenMP, {dt:.1f} s)"}
         del corpus
 
     line = {

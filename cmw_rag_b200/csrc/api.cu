@@ -46,9 +46,9 @@ static WsLayout ws_layout(int dim, int batch, int kprime) {
     w.q_bf16 = take((size_t)w.bpad * dim * sizeof(__nv_bfloat16));
     w.pool_scores = take((size_t)batch * kPoolCap * sizeof(float));
     w.pool_ids = take((size_t)batch * kPoolCap * sizeof(int32_t));
-    w.pool_cnt = take((size_t)batch * sizeof(int32_t));
-    w.pool_thr = take((size_t)batch * sizeof(float));
-    w.pool_ovf = take((size_t)batch * sizeof(int32_t));
+    w.pool_cnt = take((size_t)w.bpad * sizeof(int32_t));
+    w.pool_thr = take((size_t)w.bpad * sizeof(float));
+    w.pool_ovf = take((size_t)w.bpad * sizeof(int32_t));
     w.exact = take((size_t)batch * kprime * sizeof(double));
     w.total = off;
     return w;
@@ -230,7 +230,7 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
         if ((rc = launch_prep_queries(queries_dev, batch, w.bpad, s->dim, metric, qn64, q_f32,
                                       gemm ? q_bf16 : nullptr, stream)))
             return rc;
-        if ((rc = launch_pool_reset(pool, batch, stream))) return rc;
+        if ((rc = launch_pool_reset(pool, batch, w.bpad, stream))) return rc;
     }
 
     // which tiles the filter reads, and the per-row multiplier that goes with them

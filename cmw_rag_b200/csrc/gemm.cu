@@ -70,14 +70,20 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 __device__ __forceinline__ void flush_staged(const uint2* stg, int wcount, int lane, int64_t row_warp0,
                                              const GemmParams& p) {
     __syncwarp();
-    for (int e = lane; e < wcount; e += 32) {
-        const uint2 en = stg[e];
-        const int q = (int)(en.y >> 5);
-        const int64_t row = row_warp0 + (int)(en.y & 31u);
-        const int pos = atomicAdd(p.pool_cnt + q, 1);
-        if (pos < kPoolCap) {
-            p.pool_scores[(size_t)q * kPoolCap + pos] = __uint_as_float(en.x);
-            p.pool_ids[(size_t)q * kPoolCap + pos] = (int32_t)row;
+    for (int e = lane; e < wcount; e += 64) {
+        const bool two = (e + 32 < wcount);
+        const uint2 en0 = stg[e];
+        const uint2 en1 = two ? stg[e + 32] : make_uint2(0u, 0u);
+        const int qa = (int)(en0.y >> 5), qb = (int)(en1.y >> 5);
+        const int pos0 = atomicAdd(p.pool_cnt + qa, 1);
+        const int pos1 = two ? atomicAdd(p.pool_cnt + qb, 1) : kPoolCap;
+        if (pos0 < kPoolCap) {
+            p.pool_scores[(size_t)qa * kPoolCap + pos0] = __uint_as_float(en0.x);
+            p.pool_ids[(size_t)qa * kPoolCap + pos0] = (int32_t)(row_warp0 + (int)(en0.y & 31u));
+        }
+        if (pos1 < kPoolCap) {
+            p.pool_scores[(size_t)qb * kPoolCap + pos1] = __uint_as_float(en1.x);
+            p.pool_ids[(size_t)qb * kPoolCap + pos1] = (int32_t)(row_warp0 + (int)(en1.y & 31u));
         }
     }
     __syncwarp();
@@ -208,7 +214,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccStride);
             for (int c0 = 0; c0 < ncols; c0 += 32) {
                 uint32_t v[32];
-                if (p.nt - c0 >= 32) {
+                const bool wide = (p.nt - c0 >= 32);
+                if (wide) {
                     ptx::tmem_ld_32x32(taddr + (uint32_t)c0, v);
                 } else {
                     uint32_t w[16];
@@ -219,9 +226,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         v[16 + j] = 0u;
                     }
                 }
+                // Admission thresholds of these 32 queries: constant during the launch, so these are
+                // broadcast, L1-resident loads -- issued as one batch while the TMEM load is in flight.
+                // Padded queries (>= batch) carry thr = +inf, so no column mask is needed below.
+                float4 t4[8];
+                if (!p.dense) {
+                    const float4* tp = reinterpret_cast<const float4*>(p.pool_thr + q0 + c0);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        t4[g] = (wide || g < 4) ? __ldg(tp + g) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+                }
                 ptx::tmem_ld_wait();
-                const int cend = (ncols - c0 < 32) ? (ncols - c0) : 32;
                 if (p.dense) {
+                    const int cend = (ncols - c0 < 32) ? (ncols - c0) : 32;
                     const size_t slot = (size_t)(row - p.row_begin);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -234,36 +251,32 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 } else {
 #pragma unroll
-                    for (int j4 = 0; j4 < 32; j4 += 4) {
-                        if (j4 < cend) {
-                            // thresholds are constant during the launch: broadcast, L1-resident loads
-                            const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.pool_thr + q0 + c0 + j4));
-                            const float th[4] = {t4.x, t4.y, t4.z, t4.w};
-                            float sc[4];
-                            bool pass[4];
-                            bool any = false;
+                    for (int g = 0; g < 8; ++g) {
+                        const float th[4] = {t4[g].x, t4[g].y, t4[g].z, t4[g].w};
+                        float sc[4];
+                        bool pass[4];
+                        bool any = false;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            sc[u] = __uint_as_float(v[4 * g + u]) * mul;
+                            pass[u] = sc[u] >= th[u];
+                            any |= pass[u];
+                        }
+                        if (__any_sync(0xffffffffu, any)) {
+                            // rare: stage the survivors of these 4 columns in the warp's buffer
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                sc[u] = __uint_as_float(v[j4 + u]) * mul;
-                                pass[u] = (j4 + u < cend) && (sc[u] >= th[u]);
-                                any |= pass[u];
+                                const uint32_t m = __ballot_sync(0xffffffffu, pass[u]);
+                                if (pass[u]) {
+                                    const int e = wcount + __popc(m & lanemask_lt);
+                                    stg[e] = make_uint2(__float_as_uint(sc[u]),
+                                                        ((uint32_t)(q0 + c0 + 4 * g + u) << 5) | (uint32_t)lane);
+                                }
+                                wcount += __popc(m);
                             }
-                            if (__any_sync(0xffffffffu, any)) {
-                                // rare: stage the survivors of these 4 columns in the warp's buffer
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    const uint32_t m = __ballot_sync(0xffffffffu, pass[u]);
-                                    if (pass[u]) {
-                                        const int e = wcount + __popc(m & lanemask_lt);
-                                        stg[e] = make_uint2(__float_as_uint(sc[u]),
-                                                            ((uint32_t)(q0 + c0 + j4 + u) << 5) | (uint32_t)lane);
-                                    }
-                                    wcount += __popc(m);
-                                }
-                                if (wcount > kStageCap - 128) {
-                                    flush_staged(stg, wcount, lane, row_warp0, p);
-                                    wcount = 0;
-                                }
+                            if (wcount > kStageCap - 128) {
+                                flush_staged(stg, wcount, lane, row_warp0, p);
+                                wcount = 0;
                             }
                         }
                     }

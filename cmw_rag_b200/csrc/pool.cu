@@ -67,9 +67,19 @@ int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric
 // ---------------------------------------------------------------------------------------------
 // pool maintenance
 // ---------------------------------------------------------------------------------------------
-__global__ void pool_reset_kernel(Pool pool, int batch, int count) {
+// cnt/thr/ovf hold bpad entries: the padded queries of the last K2 group keep thr = +inf so that the
+// epilogue needs no column mask
+__global__ void pool_reset_kernel(Pool pool, int batch, int bpad, int count) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= batch) return;
+    if (b >= bpad) return;
+    if (b >= batch) {
+        if (count == 0) {
+            pool.cnt[b] = 0;
+            pool.thr[b] = INFINITY;
+            pool.ovf[b] = 0;
+        }
+        return;
+    }
     pool.cnt[b] = count;
     if (count == 0) {
         pool.thr[b] = -INFINITY;
@@ -77,15 +87,15 @@ __global__ void pool_reset_kernel(Pool pool, int batch, int count) {
     }
 }
 
-int launch_pool_reset(Pool pool, int batch, cudaStream_t stream) {
-    pool_reset_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(pool, batch, 0);
+int launch_pool_reset(Pool pool, int batch, int bpad, cudaStream_t stream) {
+    pool_reset_kernel<<<(bpad + 255) / 256, 256, 0, stream>>>(pool, batch, bpad, 0);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int launch_pool_set_count(Pool pool, int batch, int count, cudaStream_t stream) {
-    pool_reset_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(pool, batch, count);
+    pool_reset_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(pool, batch, batch, count);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;

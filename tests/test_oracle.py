@@ -196,3 +196,28 @@ def test_multivector_reduce_array_form(golden_dir):
     ids2[0, 3, 10:] = -1
     out2 = multivector_reduce(ids2, sc, gid, prl=0, limit=0)
     assert (out2["cand_ids"][0, : out2["cand_n"][0]] >= 0).all()
+
+
+def test_hnsw_baseline_recall_and_order():
+    """The hnswlib-equivalent CPU baseline: high recall on clustered data at Chroma's defaults, results
+    best-first with distance = 1 - cosine, exact on a corpus smaller than ef."""
+    from oracle.hnsw import HnswIndex
+
+    c = synth.make_clustered_corpus(6000, 64, n_centroids=64, seed=4)
+    q, _ = synth.make_queries(c, 40, seed=8, tie_probe=False)
+    ix = HnswIndex(64, 6000)
+    assert ix.add(c[:3000]) == 3000 and ix.add(c[3000:]) == 6000
+    ids, dist = ix.search(q, 10)
+    ref, ref_sc, _ = exact_topk_c(c, q, 10)
+    recall = np.mean([len(set(ids[b]) & set(ref[b])) / 10 for b in range(40)])
+    assert recall >= 0.9, recall
+    assert (np.diff(dist, axis=1) >= -1e-6).all()
+    hit = ids == ref
+    assert np.abs((1.0 - dist)[hit] - ref_sc[hit]).max() < 1e-5
+    small = HnswIndex(64, 50)
+    small.add(c[:50])
+    ids2, _ = small.search(q[:5], 10)
+    ref2, _, _ = exact_topk_c(c[:50], q[:5], 10)
+    assert (ids2 == ref2).all()
+    ix.close()
+    small.close()
