@@ -12,7 +12,9 @@
 //   BF16:      emit the pool's best k
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -77,6 +79,42 @@ static int pick_kprime(int k, int mode, bool gemm) {
     kp = (int)align_up((size_t)kp, 32);
     if (kp > kMaxKPrime) kp = kMaxKPrime;
     return kp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host staging for the *_host entry points
+// ---------------------------------------------------------------------------------------------
+static int stage_h2d(int device, uint8_t* pin, uint8_t* dev, const uint8_t* src, size_t bytes,
+                     cudaStream_t stream) {
+    const size_t piece = 1u << 20;
+    const size_t npieces = (bytes + piece - 1) / piece;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nthreads = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
+    if (npieces < 4) nthreads = 1;
+    std::atomic<int> err{0};
+    auto work = [&](size_t t) {
+        if (t != 0 && cudaSetDevice(device) != cudaSuccess) err.store(1);
+        for (size_t i = t; i < npieces; i += nthreads) {
+            const size_t off = i * piece;
+            const size_t n = bytes - off < piece ? bytes - off : piece;
+            memcpy(pin + off, src + off, n);
+            if (cudaMemcpyAsync(dev + off, pin + off, n, cudaMemcpyHostToDevice, stream) != cudaSuccess)
+                err.store(1);
+        }
+    };
+    if (nthreads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    if (err.load()) {
+        set_error("cmw_search_host: staging copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -2;
+    }
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -350,9 +388,12 @@ int cmw_search_host(cmw_store* h, const float* queries_host, int batch, int k, i
     uint8_t* dev = reinterpret_cast<uint8_t*>(s->dev_io);
 
     auto run = [&](const float* q_src, int nb, int run_mode) -> int {
-        memcpy(pin, q_src, (size_t)nb * s->dim * sizeof(float));
-        CMW_CUDA_OK(cudaMemcpyAsync(dev, pin, (size_t)nb * s->dim * sizeof(float),
-                                    cudaMemcpyHostToDevice, stream));
+        // pageable -> pinned -> device, pipelined: a few host threads copy 1 MB pieces into the pinned
+        // staging buffer and enqueue each piece's H2D as soon as it is staged, so the DMA of one piece
+        // overlaps the memcpy of the next (all pieces precede the search on the same stream)
+        if (stage_h2d(s->device, pin, dev, reinterpret_cast<const uint8_t*>(q_src), (size_t)nb * s->dim * sizeof(float),
+                      stream))
+            return -2;
         int r = cmw_search(h, reinterpret_cast<const float*>(dev), nb, k, metric, run_mode,
                            reinterpret_cast<float*>(dev + q_bytes),
                            reinterpret_cast<int64_t*>(dev + q_bytes + sc_bytes), nullptr,

@@ -100,7 +100,11 @@ struct Options {
     double bf16_eps = 5e-4;   // certificate bound on |bf16 filter score - exact score| (cosine units)
     double f32_eps = 4e-6;    // same for the fp32 FMA filter
     double kprime = 0;        // 0 = automatic
-    double scan_max_batch = 4;  // batches up to this use K1 (scan); larger use K2 (GEMM)
+    // Batches up to this use K1 (scan), larger ones K2 (GEMM).  0 = K2 for every batch size: even at
+    // batch 1 the tensor-core filter reads the bf16 tiles (half the bytes of the fp32 scan) and the
+    // fp64 rescoring keeps the answer exact, so it is the faster exact path; K1 remains the fp32-filter
+    // path (CMW_ALGO_SCAN), the fallback for failed certificates and the path of bf16-less stores.
+    double scan_max_batch = 0;
     double gemm_enabled = 1;
 };
 extern Options g_opt;

@@ -37,7 +37,8 @@ extern "C" {
 #define CMW_MODE_BF16 1      /* bf16 operands, fp32 accumulation; approximate (reported as recall@k) */
 /* optional algorithm override, OR-ed into `mode` (default: chosen from the batch size) */
 #define CMW_ALGO_AUTO (0 << 8)
-#define CMW_ALGO_SCAN (1 << 8) /* K1: TMA-staged streaming dot product (batch 1-4 per pass, HBM-bound) */
+#define CMW_ALGO_SCAN (1 << 8) /* K1: TMA-staged streaming dot product, 1-2 queries per pass (HBM-bound);
+                                  F32_EXACT scans the fp32 tiles, BF16 the bf16 tiles */
 #define CMW_ALGO_GEMM (2 << 8) /* K2: tcgen05/TMEM GEMM with fused top-k epilogue */
 /* slab schedule override, OR-ed into `mode`: fixed slabs small enough that the candidate pool can
  * never overflow, whatever the row order (slower; cmw_search_host falls back to it by itself) */
