@@ -426,6 +426,18 @@ def run_ours(args):
         ach = nbytes / (filt_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "scan_kernel (K1)", "achieved": ach, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (per step = the
+    # sum over that kernel's launches in one step), when this run is the workload that was profiled
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f).get("gemm_topk_kernel" if used_gemm else "scan_kernel")
+        if tr and (tr["rows"], tr["dim"], tr["batch"], tr["k"]) == (args.rows, args.dim, B, k):
+            roof["traffic"] = tr["traffic_bytes_per_step"]
+            roof["traffic_unit"] = "bytes per step (all launches of the kernel in one step)"
+            roof["algorithmic_hbm_bytes_per_step"] = tr["algorithmic_hbm_bytes_per_step"]
+            roof["traffic_source"] = tr["source"]
+    except (OSError, ValueError, KeyError):
+        pass
     roof["kernel_ms_per_step"] = filt_ms / args.steps
     roof["kernel_launches_per_step"] = filt_n / args.steps
     roof["share_of_step"] = filt_ms / dev_ms

@@ -58,6 +58,7 @@ SIGNATURES = {
     "cmw_store_tombstone": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "cmw_store_tombstone_host": (c_int, [c_void_p, c_void_p, c_int64]),
     "cmw_store_kb_gid_dev": (c_void_p, [c_void_p]),
+    "cmw_store_read_rows_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "cmw_search_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "cmw_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                            c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

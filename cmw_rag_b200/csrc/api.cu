@@ -323,8 +323,9 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
 
     const int64_t rows = s->rows;
     double growth = (double)(kPoolCap - kprime) / (3.0 * kprime);
-    if (growth < 1.0) growth = 1.0;
     if (growth > 8.0) growth = 8.0;
+    if (g_opt.slab_growth > 0 && g_opt.slab_growth < growth) growth = g_opt.slab_growth;
+    if (growth < 1.0) growth = 1.0;
     int64_t seen = 0;
     if (rows > 0) {
         const int64_t slab0 = rows < kDenseSlabRows ? rows : kDenseSlabRows;

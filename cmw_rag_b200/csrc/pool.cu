@@ -278,6 +278,7 @@ rescore_kernel(const float* __restrict__ f32, const double* __restrict__ norm64,
     const float4* qv = reinterpret_cast<const float4*>(q_raw + (size_t)b * dim);
     const int nvec = dim >> 2;
     double acc = 0.0;
+#pragma unroll 4
     for (int c = lane; c < nvec; c += 32) {
         const float4 v = __ldg(row + c);
         const float4 w = __ldg(qv + c);

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -162,6 +163,7 @@ int cmw_set_option(const char* name, double value) {
     else if (!strcmp(name, "kprime")) g_opt.kprime = value;
     else if (!strcmp(name, "scan_max_batch")) g_opt.scan_max_batch = value;
     else if (!strcmp(name, "gemm_enabled")) g_opt.gemm_enabled = value;
+    else if (!strcmp(name, "slab_growth")) g_opt.slab_growth = value;
     else {
         set_error("unknown option '%s'", name);
         return -1;
@@ -176,6 +178,7 @@ double cmw_get_option(const char* name) {
     if (!strcmp(name, "kprime")) return g_opt.kprime;
     if (!strcmp(name, "scan_max_batch")) return g_opt.scan_max_batch;
     if (!strcmp(name, "gemm_enabled")) return g_opt.gemm_enabled;
+    if (!strcmp(name, "slab_growth")) return g_opt.slab_growth;
     if (!strcmp(name, "pool_cap")) return (double)kPoolCap;
     return 0.0;
 }
@@ -390,6 +393,36 @@ int cmw_store_tombstone_host(cmw_store* h, const int64_t* rows_host, int64_t n) 
 
 const int32_t* cmw_store_kb_gid_dev(const cmw_store* h) {
     return h ? reinterpret_cast<const Store*>(h)->kb_gid : nullptr;
+}
+
+int cmw_store_read_rows_f32(cmw_store* h, int64_t row0, int64_t n, float* rows_host, int32_t* kb_gid_host,
+                            uint8_t* live_host) {
+    CMW_REQUIRE(h != nullptr, "cmw_store_read_rows_f32: store is NULL");
+    Store* s = reinterpret_cast<Store*>(h);
+    if (n == 0) return 0;
+    CMW_REQUIRE(row0 >= 0 && n > 0 && row0 + n <= s->rows, "cmw_store_read_rows_f32: rows [%lld, %lld) out of range",
+                (long long)row0, (long long)(row0 + n));
+    CMW_CUDA_OK(cudaSetDevice(s->device));
+    cudaStream_t st;
+    int rc = get_stream(s, &st);
+    if (rc) return rc;
+    if (rows_host != nullptr) {
+        CMW_REQUIRE(s->f32 != nullptr, "cmw_store_read_rows_f32: the store keeps no fp32 tiles");
+        CMW_CUDA_OK(cudaMemcpyAsync(rows_host, s->f32 + (size_t)row0 * s->dim, (size_t)n * s->dim * sizeof(float),
+                                    cudaMemcpyDeviceToHost, st));
+    }
+    if (kb_gid_host != nullptr)
+        CMW_CUDA_OK(cudaMemcpyAsync(kb_gid_host, s->kb_gid + row0, (size_t)n * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, st));
+    std::vector<float> live;
+    if (live_host != nullptr) {
+        live.resize((size_t)n);
+        CMW_CUDA_OK(cudaMemcpyAsync(live.data(), s->live + row0, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CMW_CUDA_OK(cudaStreamSynchronize(st));
+    if (live_host != nullptr)
+        for (int64_t i = 0; i < n; ++i) live_host[i] = (live[i] == live[i]) ? 1 : 0;
+    return 0;
 }
 
 }  // extern "C"

@@ -130,6 +130,17 @@ class DenseStore:
         N.check(lib.cmw_store_append_host_f32(self._h, arr.ctypes.data, gid_ptr, arr.shape[0]),
                 "cmw_store_append_host_f32")
 
+    def read_rows(self, row0: int, n: int, rows: bool = True):
+        """Read LOCAL rows back: (f32 [n, dim] or None, kb_gid i32[n], live bool[n])."""
+        out = np.empty((n, self.dim), np.float32) if rows else None
+        gid = np.empty((n,), np.int32)
+        live = np.empty((n,), np.uint8)
+        if n:
+            N.check(N.lib().cmw_store_read_rows_f32(self._h, int(row0), int(n),
+                                                    out.ctypes.data if rows else None, gid.ctypes.data,
+                                                    live.ctypes.data), "cmw_store_read_rows_f32")
+        return out, gid, live.astype(bool)
+
     def tombstone(self, rows) -> None:
         """Mark LOCAL row numbers dead (never returned again)."""
         arr = np.ascontiguousarray(rows, dtype=np.int64)

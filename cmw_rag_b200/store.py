@@ -321,6 +321,74 @@ class B200Store:
                 if not fut.done():
                     fut.set_exception(exc)
 
+    # -- persistence (the analogue of the Chroma server's --path directory) ----------
+    FORMAT_VERSION = 1
+
+    def save(self, path: str, chunk_rows: int = 65536) -> None:
+        """Write the collection to a directory: meta.json, rows.f32 (raw little-endian [rows, dim],
+        as appended), kb_gid.i32, alive.u8 and sidecar.jsonl (id, document, metadata per row)."""
+        import json
+        import os
+
+        os.makedirs(path, exist_ok=True)
+        with self._lock:
+            n = len(self._ids)
+            meta = {"format": self.FORMAT_VERSION, "collection_name": self.collection_name, "metric": self.metric,
+                    "mode": self.mode, "dim": self._dim, "padded_dim": getattr(self, "_pdim", None), "rows": n,
+                    "id_offset": self._id_offset, "group_keys": self._key_of_gid}
+            with open(os.path.join(path, "rows.f32"), "wb") as fr, open(os.path.join(path, "kb_gid.i32"), "wb") as fg:
+                for lo in range(0, n, chunk_rows):
+                    m = min(chunk_rows, n - lo)
+                    rows, gid, _ = self._dense.read_rows(lo, m)
+                    fr.write(np.ascontiguousarray(rows[:, : self._dim]).tobytes())
+                    fg.write(gid.tobytes())
+            np.asarray(self._alive, np.uint8).tofile(os.path.join(path, "alive.u8"))
+            with open(os.path.join(path, "sidecar.jsonl"), "w", encoding="utf-8") as f:
+                for i in range(n):
+                    f.write(json.dumps({"id": self._ids[i], "document": self._docs[i], "metadata": self._metas[i]},
+                                       ensure_ascii=False) + "\n")
+            with open(os.path.join(path, "meta.json"), "w") as f:  # written last: marks a complete save
+                json.dump(meta, f)
+
+    @classmethod
+    def load(cls, path: str, capacity: int | None = None, device: int = 0, chunk_rows: int = 65536, **kw) -> "B200Store":
+        """Rebuild a collection saved by save(): rows stream from the memory-mapped file through the
+        pinned staging buffer into HBM (K0 recomputes the bf16 tiles and norms), tombstones are replayed."""
+        import json
+        import os
+
+        with open(os.path.join(path, "meta.json")) as f:
+            meta = json.load(f)
+        if meta.get("format") != cls.FORMAT_VERSION:
+            raise ValueError(f"unsupported store format {meta.get('format')!r}")
+        n, dim = int(meta["rows"]), meta["dim"]
+        store = cls(meta["collection_name"], dim=dim, capacity=max(int(capacity or 0), n, 1), device=device,
+                    metric=meta["metric"], mode=meta["mode"], id_offset=int(meta.get("id_offset", 0)), **kw)
+        store._key_of_gid = list(meta["group_keys"])
+        store._gid_of_key = {k: i for i, k in enumerate(store._key_of_gid)}
+        if n == 0:
+            return store
+        rows = np.memmap(os.path.join(path, "rows.f32"), dtype=np.float32, mode="r", shape=(n, dim))
+        gid = np.fromfile(os.path.join(path, "kb_gid.i32"), dtype=np.int32)
+        alive = np.fromfile(os.path.join(path, "alive.u8"), dtype=np.uint8).astype(bool)
+        dense = store._ensure(dim)
+        for lo in range(0, n, chunk_rows):
+            hi = min(n, lo + chunk_rows)
+            dense.append(store._pad(np.ascontiguousarray(rows[lo:hi])), gid[lo:hi])
+        with open(os.path.join(path, "sidecar.jsonl"), encoding="utf-8") as f:
+            for i, line in enumerate(f):
+                rec = json.loads(line)
+                store._ids.append(rec["id"])
+                store._docs.append(rec["document"])
+                store._metas.append(rec["metadata"])
+                store._alive.append(bool(alive[i]))
+                if alive[i]:
+                    store._row_of[rec["id"]] = i
+        dead = np.flatnonzero(~alive)
+        if dead.size:
+            dense.tombstone(dead)
+        return store
+
     def search_multivector(self, segment_embeddings, k: int, prl: int = 0, limit: int = 0):
         """[Q, S, dim] host array -> (MultiVectorResult on CPU, ids [Q,S,k], scores [Q,S,k])."""
         import torch

@@ -89,6 +89,11 @@ int cmw_store_tombstone(cmw_store* s, const int64_t* rows_dev, int64_t n, void* 
 int cmw_store_tombstone_host(cmw_store* s, const int64_t* rows_host, int64_t n);
 /* device pointer to kb_gid[rows] (for cmw_multivector) */
 const int32_t* cmw_store_kb_gid_dev(const cmw_store* s);
+/* Read rows back to the host (persistence: the analogue of the Chroma server's --path directory,
+ * systemd/cmw-rag-chroma.service:11 of the reference).  rows_host f32 [n, dim] (needs CMW_STORE_F32),
+ * kb_gid_host i32 [n], live_host u8 [n] (0 = tombstoned); any may be NULL.  Synchronises. */
+int cmw_store_read_rows_f32(cmw_store* s, int64_t row0, int64_t n, float* rows_host, int32_t* kb_gid_host,
+                            uint8_t* live_host);
 
 /* ---- search: replaces collection.query(query_embeddings, n_results) of
  *      vector_store.py:54-66 for a whole batch of query vectors ---- */

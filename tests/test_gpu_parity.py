@@ -407,3 +407,25 @@ def test_gemm_device_certificate_and_fallback(cfg1, torch_cuda):
         N.set_option("bf16_eps", old)
     _check_exact(ids, sc, cfg1["ref_ids"], cfg1["ref_sc"])
     assert (fl == 0).all()
+
+
+def test_save_load_roundtrip_gpu(torch_cuda, tmp_path):
+    """Persistence through the C ABI (cmw_store_read_rows_f32): a reloaded collection answers
+    identically, tombstones included."""
+    from cmw_rag_b200 import B200Store
+
+    c = synth.make_corpus(3000, 96, seed=8)
+    store = B200Store("persist", capacity=4096)
+    store.add([f"t{i}" for i in range(3000)], [{"stable_id": f"{i}", "kbId": str(i // 8)} for i in range(3000)],
+              ids=[str(i) for i in range(3000)], embeddings=c)
+    store.delete(ids=["5", "17", "2999"])
+    store.save(str(tmp_path / "col"))
+    again = B200Store.load(str(tmp_path / "col"))
+    q, _ = synth.make_queries(c, 9, seed=2)
+    s1, i1, f1 = store.search(q, 30)
+    s2, i2, f2 = again.search(q, 30)
+    assert (i1 == i2).all() and np.array_equal(s1, s2) and again.count() == 2997
+    live = np.ones(3000, bool)
+    live[[5, 17, 2999]] = False
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, 30, live=live)
+    _check_exact(i2, s2, ref_ids, ref_sc)

@@ -114,6 +114,9 @@ class FakeDense:
     def tombstone(self, rows):
         self.live[np.asarray(rows, np.int64)] = False
 
+    def read_rows(self, row0, n, rows=True):
+        return self.rows_[row0:row0 + n].copy(), self.gid[row0:row0 + n].copy(), self.live[row0:row0 + n].copy()
+
     def search_host(self, q, k, metric="cosine", mode="f32", algo=None):
         self.calls.append(q.shape[0])
         ids, sc, _ = exact_topk(self.rows_, q, k, metric=metric, live=self.live, id_offset=self.id_offset)
@@ -203,6 +206,30 @@ def test_seam_and_await_coalescing(fake_store):
     rec = Recorder()
     assert asyncio.run(top_k_search_async(rec, [0.1, 0.2], 3)) == ["x"]
     assert rec.kw == {"query_embedding": [0.1, 0.2], "k": 3}
+
+
+def test_save_load_roundtrip_host_layer(fake_store, tmp_path):
+    """the on-disk format restores rows, tombstones, sidecar and the kbId group table."""
+    import cmw_rag_b200.store as store_mod
+
+    store = fake_store
+    rng = np.random.default_rng(5)
+    emb = rng.standard_normal((40, 12)).astype(np.float32)  # 12 -> padded to 16 internally
+    metas = [{"stable_id": f"s{i}", "kbId": f"{100 + i // 4}" + ("-toc" if i % 7 == 0 else ""), "n": i} for i in range(40)]
+    store.add([f"doc {i}" for i in range(40)], metas, ids=[f"s{i}" for i in range(40)], embeddings=emb)
+    store.delete(where={"n": {"$in": [3, 17]}})
+    store.save(str(tmp_path / "col"))
+    again = store_mod.B200Store.load(str(tmp_path / "col"))
+    assert again.count() == 38 and again.collection_name == "t"
+    q = rng.standard_normal((5, 12)).astype(np.float32)
+    s1, i1, _ = store.search(q, 7)
+    s2, i2, _ = again.search(q, 7)
+    assert (i1 == i2).all() and np.array_equal(s1, s2)
+    assert [d.metadata for d in again.similarity_search(q[0], 5)] == [d.metadata for d in store.similarity_search(q[0], 5)]
+    assert again.get(where={"n": 3})["ids"] == [] and again.get(where={"n": 4})["ids"] == ["s4"]
+    assert again.gid_for("100") == store.gid_for("100-toc")
+    again.add(["new"], [{"kbId": "999"}], ids=["new"], embeddings=rng.standard_normal((1, 12)))
+    assert again.count() == 39
 
 
 def test_shard_bounds():
