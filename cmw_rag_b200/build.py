@@ -17,8 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libcmwdense.so")
-SOURCES = ["store.cu", "scan.cu", "gemm.cu", "pool.cu", "multivector.cu", "api.cu"]
-HEADERS = ["common.cuh", "ptx.cuh", os.path.join("..", "..", "include", "cmw_dense.h")]
+SOURCES = ["store.cu", "scan.cu", "gemm.cu", "gemm2.cu", "pool.cu", "multivector.cu", "api.cu"]
+HEADERS = ["common.cuh", "ptx.cuh", "gemm_common.cuh", os.path.join("..", "..", "include", "cmw_dense.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

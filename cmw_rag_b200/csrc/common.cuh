@@ -106,6 +106,8 @@ struct Options {
     // path (CMW_ALGO_SCAN), the fallback for failed certificates and the path of bf16-less stores.
     double scan_max_batch = 0;
     double gemm_enabled = 1;
+    double gemm_2cta = 1;            // CTA-pair (cta_group::2) K2 kernel for large batches
+    double gemm_2cta_min_batch = 256;
     double slab_growth = 0;   // 0 = automatic ((cap - K') / (3 K'), at most 8); else the fixed growth factor
 };
 extern Options g_opt;

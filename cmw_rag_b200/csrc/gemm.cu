@@ -23,77 +23,17 @@
 // Work items: (row tile, query group), row-tile-major so that the CTAs running concurrently read the
 // same corpus rows for different query groups (one HBM read, L2 hits for the rest).
 // Algorithmic work per item: 2 * 128 * NT * D flop; HBM bytes per row tile: 128 * D * 2.
-#include "common.cuh"
-#include "ptx.cuh"
+#include "gemm_common.cuh"
 
 namespace cmw {
 
 constexpr int kGemmThreads = 192;
-constexpr int kTileM = 128;          // corpus rows per item
-constexpr int kBlockK = 64;          // bf16 elements per k-block = one 128-byte swizzle atom
-constexpr int kUmmaK = 16;
-constexpr int kMaxNT = 256;
-constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KB
-constexpr int kMaxStages = 8;
-constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;      // TMEM columns per accumulator stage
-constexpr int kStageCap = 512;       // staged survivors per epilogue warp (8 bytes each)
-
-struct GemmParams {
-    int dim;
-    int num_kb;           // ceil(dim / 64)
-    int nt;               // queries per group (multiple of 16, <= 256)
-    int n_groups;
-    int batch;            // real queries
-    int64_t row_begin, row_end;
-    int n_tiles;
-    int nstages;
-    int stage_bytes;
-    int dense;
-    uint32_t idesc;
-    const float* row_mul;
-    float* pool_scores;
-    int32_t* pool_ids;
-    int32_t* pool_cnt;
-    const float* pool_thr;
-};
-
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-    // K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), LBO unused,
-    // descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
-    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
-           (2ull << 61);
-}
-
-// Append the survivors a warp staged in shared memory to their queries' pools: every lane takes one
-// entry, so 32 global atomics are in flight per round trip instead of one per admitted column.
-__device__ __forceinline__ void flush_staged(const uint2* stg, int wcount, int lane, int64_t row_warp0,
-                                             const GemmParams& p) {
-    __syncwarp();
-    for (int e = lane; e < wcount; e += 64) {
-        const bool two = (e + 32 < wcount);
-        const uint2 en0 = stg[e];
-        const uint2 en1 = two ? stg[e + 32] : make_uint2(0u, 0u);
-        const int qa = (int)(en0.y >> 5), qb = (int)(en1.y >> 5);
-        const int pos0 = atomicAdd(p.pool_cnt + qa, 1);
-        const int pos1 = two ? atomicAdd(p.pool_cnt + qb, 1) : kPoolCap;
-        if (pos0 < kPoolCap) {
-            p.pool_scores[(size_t)qa * kPoolCap + pos0] = __uint_as_float(en0.x);
-            p.pool_ids[(size_t)qa * kPoolCap + pos0] = (int32_t)(row_warp0 + (int)(en0.y & 31u));
-        }
-        if (pos1 < kPoolCap) {
-            p.pool_scores[(size_t)qb * kPoolCap + pos1] = __uint_as_float(en1.x);
-            p.pool_ids[(size_t)qb * kPoolCap + pos1] = (int32_t)(row_warp0 + (int)(en1.y & 31u));
-        }
-    }
-    __syncwarp();
-}
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
 
     // 128-byte-swizzled operand tiles must start on 1024-byte boundaries of the shared window
@@ -159,42 +99,46 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        // The whole warp walks the pipeline (uniform control flow, operands in uniform registers); one
+        // elected lane issues the MMAs and the commits.
+        const uint32_t stage0_lo = (ptx::smem_u32(stages) >> 4);
+        const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
+        constexpr uint32_t kDescHi = (uint32_t)(1024u >> 4) | (1u << 14) | (2u << 29);  // SBO, version, SW128
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                ptx::mbar_wait(&full[stage], phase);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    ptx::mbar_wait(&full[stage], phase);
-                    ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(stages + (size_t)stage * p.stage_bytes);
-                    const uint32_t sb = sa + kABytes;
+                const uint32_t a_lo = (stage0_lo + (uint32_t)stage * stage_step) & 0x3fffu;
+                const uint32_t b_lo = (stage0_lo + (uint32_t)stage * stage_step + (kABytes >> 4)) & 0x3fffu;
+                if (ptx::elect_one()) {
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        const uint64_t da = make_sw128_desc(sa + k * kUmmaK * 2);
-                        const uint64_t db = make_sw128_desc(sb + k * kUmmaK * 2);
+                        const uint64_t da = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + 2u * k);
+                        const uint64_t db = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + 2u * k);
                         ptx::umma_bf16(d_tmem, da, db, p.idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     ptx::umma_commit(&empty[stage]);  // frees the stage once these MMAs have read it
-                    if (++stage == p.nstages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                    if (kb == p.num_kb - 1) ptx::umma_commit(&tmem_full[acc]);  // accumulator complete
                 }
-                ptx::umma_commit(&tmem_full[acc]);  // accumulator complete
+                __syncwarp();
+                if (++stage == p.nstages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
             }
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter + 32) belong to this warp
         uint2* stg = stage_buf + (size_t)(warp - 2) * kStageCap;
-        const uint32_t lanemask_lt = (1u << lane) - 1u;
-        int wcount = 0;  // survivors staged by this warp (warp-uniform)
         int it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int tile = item / p.n_groups;
@@ -202,98 +146,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             const int64_t row_warp0 = p.row_begin + (int64_t)tile * kTileM + quarter * 32;
-            const int64_t row = row_warp0 + lane;
-            const bool row_ok = row < p.row_end;
-            const float mul = row_ok ? __ldg(p.row_mul + row) : __int_as_float(0x7fc00000);
             const int q0 = group * p.nt;
             int ncols = p.batch - q0;  // real (unpadded) queries in this group
             if (ncols > p.nt) ncols = p.nt;
-
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccStride);
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
-                uint32_t v[32];
-                const bool wide = (p.nt - c0 >= 32);
-                if (wide) {
-                    ptx::tmem_ld_32x32(taddr + (uint32_t)c0, v);
-                } else {
-                    uint32_t w[16];
-                    ptx::tmem_ld_32x16(taddr + (uint32_t)c0, w);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        v[j] = w[j];
-                        v[16 + j] = 0u;
-                    }
-                }
-                // Admission thresholds of these 32 queries: constant during the launch, so these are
-                // broadcast, L1-resident loads -- issued as one batch while the TMEM load is in flight.
-                // Padded queries (>= batch) carry thr = +inf, so no column mask is needed below.
-                float4 t4[8];
-                if (!p.dense) {
-                    const float4* tp = reinterpret_cast<const float4*>(p.pool_thr + q0 + c0);
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        t4[g] = (wide || g < 4) ? __ldg(tp + g) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
-                }
-                ptx::tmem_ld_wait();
-                if (p.dense) {
-                    const int cend = (ncols - c0 < 32) ? (ncols - c0) : 32;
-                    const size_t slot = (size_t)(row - p.row_begin);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (j < cend && row_ok) {
-                            const float s = __uint_as_float(v[j]) * mul;
-                            const size_t pos = (size_t)(q0 + c0 + j) * kPoolCap + slot;
-                            p.pool_scores[pos] = (s == s) ? s : -INFINITY;
-                            p.pool_ids[pos] = (int32_t)row;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const float th[4] = {t4[g].x, t4[g].y, t4[g].z, t4[g].w};
-                        float sc[4];
-                        bool pass[4];
-                        bool any = false;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            sc[u] = __uint_as_float(v[4 * g + u]) * mul;
-                            pass[u] = sc[u] >= th[u];
-                            any |= pass[u];
-                        }
-                        if (__any_sync(0xffffffffu, any)) {
-                            // rare: stage the survivors of these 4 columns in the warp's buffer
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const uint32_t m = __ballot_sync(0xffffffffu, pass[u]);
-                                if (pass[u]) {
-                                    const int e = wcount + __popc(m & lanemask_lt);
-                                    stg[e] = make_uint2(__float_as_uint(sc[u]),
-                                                        ((uint32_t)(q0 + c0 + 4 * g + u) << 5) | (uint32_t)lane);
-                                }
-                                wcount += __popc(m);
-                            }
-                            if (wcount > kStageCap - 128) {
-                                flush_staged(stg, wcount, lane, row_warp0, p);
-                                wcount = 0;
-                            }
-                        }
-                    }
-                }
-            }
-            // all tcgen05.ld of this accumulator stage have completed (wait::ld above): hand the
-            // accumulator back to the MMA warp before the (global-atomic) flush of the survivors
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-            if (wcount > 0) {
-                flush_staged(stg, wcount, lane, row_warp0, p);
-                wcount = 0;
-            }
+            uint64_t* rel = &tmem_empty[acc];
+            epilogue_item(p, taddr, row_warp0, lane, q0, ncols, stg,
+                          [rel, lane]() { if (lane == 0) ptx::mbar_arrive(rel); });
         }
     }
 
+    __syncwarp();
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -325,7 +190,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 row-major [rows, dim] tensor, box = 64 elements (128 bytes) x box_rows, 128-byte swizzle
-static int encode_2d(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows) {
+int encode_2d(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     CMW_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
@@ -346,10 +211,18 @@ int encode_bf16_tmap(Store* s) {
 
 bool gemm_supported(const Store* s) { return s->bf16 != nullptr && s->tmap_ok; }
 
+int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream);  // gemm2.cu
+
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     const Store* s = a.store;
     CMW_REQUIRE(gemm_supported(s), "launch_gemm: store has no bf16 tiles / TMA descriptor");
     if (a.row_end <= a.row_begin) return 0;
+    if (a.dense)
+        CMW_REQUIRE(a.row_end - a.row_begin <= kPoolCap, "launch_gemm: dense slab larger than the pool");
+    // tensor-bound batches run on CTA pairs (cta_group::2); the HBM-bound ones on single CTAs
+    if (g_opt.gemm_2cta != 0 && a.bpad >= (int)g_opt.gemm_2cta_min_batch && a.bpad % 256 == 0 &&
+        (a.row_begin % (2 * kTileM)) == 0)
+        return launch_gemm_2cta(a, stream);
     GemmParams p;
     p.dim = s->dim;
     p.num_kb = (s->dim + kBlockK - 1) / kBlockK;
@@ -373,8 +246,6 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.pool_ids = a.pool.ids;
     p.pool_cnt = a.pool.cnt;
     p.pool_thr = a.pool.thr;
-    if (a.dense)
-        CMW_REQUIRE(a.row_end - a.row_begin <= kPoolCap, "launch_gemm: dense slab larger than the pool");
     CUtensorMap tmap_b;
     int rc = encode_2d(&tmap_b, a.q_bf16, a.bpad, s->dim, p.nt);
     if (rc) return rc;

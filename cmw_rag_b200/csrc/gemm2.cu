@@ -1,0 +1,281 @@
+// gemm2.cu -- K2 for large batches: the CTA-pair (cta_group::2) variant of the tcgen05 filter.
+//
+// Same contract and epilogue as gemm.cu; what changes is the MMA shape and the operand traffic.  Two
+// CTAs of a cluster (the two SMs of a TPC) cooperate on one item = 256 corpus rows x NT queries:
+//   * each CTA TMA-loads its own 128 corpus rows (A) and HALF of the query tile (B, NT/2 rows), so the
+//     query operand is fetched once per pair instead of once per SM: L2 -> shared-memory traffic per
+//     k-block drops from 16 KB + NT*128 B to 16 KB + NT*64 B per SM;
+//   * the leader CTA's MMA thread issues tcgen05.mma.cta_group::2 (M = 256, N = NT, K = 16): the tensor
+//     cores of both SMs read A from their own shared memory and B from both halves; each SM's TMEM
+//     receives the 128 x NT accumulator of its own rows;
+//   * TMA completions of both CTAs signal the LEADER's full barrier (peer bit of the barrier address
+//     cleared); tcgen05.commit multicasts to both CTAs' empty / tmem_full barriers; the epilogue warps of
+//     both CTAs release the accumulator on the leader's tmem_empty barrier (remote mbarrier arrive).
+// Used when NT is a multiple of 32 and the batch is large enough to be tensor-bound; otherwise the
+// 1-CTA kernel (HBM-bound regime) runs.
+#include "gemm_common.cuh"
+
+namespace cmw {
+
+namespace ptx2 {
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(ptx::smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit: address in the even (leader) CTA
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst_smem, const CUtensorMap* m, int c0, int c1,
+                                                uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(ptx::smem_u32(dst_smem)),
+        "l"(m), "r"(c0), "r"(c1), "r"(ptx::smem_u32(bar) & kPeerBitMask), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     ptx::smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .b16 msk;\n"
+        "mov.b16 msk, 3;\n"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], msk;\n"
+        "}\n" ::"r"(ptx::smem_u32(bar))
+        : "memory");
+}
+
+}  // namespace ptx2
+
+constexpr int kGemm2Threads = 192;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
+gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx2::cluster_ctarank();
+    const bool leader = (rank == 0);
+
+    uint8_t* stages = smem + ((1024u - (ptx::smem_u32(smem) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)p.nstages * p.stage_bytes);
+    uint64_t* full = bars;                          // [kMaxStages]  used in the leader only
+    uint64_t* empty = bars + kMaxStages;            // [kMaxStages]  one set per CTA
+    uint64_t* tmem_full = bars + 2 * kMaxStages;    // [2]           one set per CTA
+    uint64_t* tmem_empty = tmem_full + 2;           // [2]           used in the leader only
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint2* stage_buf = reinterpret_cast<uint2*>(tmem_empty + 4);
+
+    const int n_items = p.n_tiles * p.n_groups;
+    const int cid = blockIdx.x >> 1;
+    const int ncl = gridDim.x >> 1;
+    const int half_nt = p.nt >> 1;
+    const int b_bytes = half_nt * kBlockK * 2;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < p.nstages; ++s) {
+            ptx::mbar_init(&full[s], 2);   // leader's arrive.expect_tx + the peer's remote arrive
+            ptx::mbar_init(&empty[s], 1);  // multicast tcgen05.commit
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tmem_full[s], 1);   // multicast tcgen05.commit
+            ptx::mbar_init(&tmem_empty[s], 8);  // 4 epilogue warps x 2 CTAs
+        }
+        ptx::fence_barrier_init();
+    }
+    ptx2::cluster_sync();  // barriers of both CTAs initialised before any remote arrive / 2-SM alloc
+    if (warp == 1) {
+        ptx2::tmem_alloc_2sm(tmem_base_smem, kTmemCols);
+        ptx2::tmem_relinquish_2sm();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            const uint64_t pol_a = (p.n_groups > 1) ? ptx::l2_policy_evict_last() : ptx::l2_policy_evict_first();
+            const uint64_t pol_b = ptx::l2_policy_evict_last();
+            const uint32_t pair_bytes = 2u * (uint32_t)(kABytes + b_bytes);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = cid; item < n_items; item += ncl) {
+                const int tile = item / p.n_groups;
+                const int group = item - tile * p.n_groups;
+                const int row0 = (int)(p.row_begin + (int64_t)tile * (2 * kTileM)) + (int)rank * kTileM;
+                const int q0 = group * p.nt + (int)rank * half_nt;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    ptx::mbar_wait(&empty[stage], phase ^ 1u);
+                    uint8_t* sa = stages + (size_t)stage * p.stage_bytes;
+                    uint8_t* sb = sa + kABytes;
+                    if (leader) ptx::mbar_arrive_expect_tx(&full[stage], pair_bytes);
+                    else ptx2::mbar_arrive_cluster(&full[stage], 0);
+                    ptx2::tma_load_2d_2sm(sa, &tmap_a, kb * kBlockK, row0, &full[stage], pol_a);
+                    ptx2::tma_load_2d_2sm(sb, &tmap_b, kb * kBlockK, q0, &full[stage], pol_b);
+                    if (++stage == p.nstages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            const uint32_t stage0_lo = (ptx::smem_u32(stages) >> 4);
+            const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
+            constexpr uint32_t kDescHi = (uint32_t)(1024u >> 4) | (1u << 14) | (2u << 29);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int item = cid; item < n_items; item += ncl, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_lo = (stage0_lo + (uint32_t)stage * stage_step) & 0x3fffu;
+                    const uint32_t b_lo = (stage0_lo + (uint32_t)stage * stage_step + (kABytes >> 4)) & 0x3fffu;
+                    if (ptx::elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            const uint64_t da = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + 2u * k);
+                            const uint64_t db = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + 2u * k);
+                            ptx2::umma_bf16_2sm(d_tmem, da, db, p.idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        ptx2::umma_commit_2sm(&empty[stage]);
+                        if (kb == p.num_kb - 1) ptx2::umma_commit_2sm(&tmem_full[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == p.nstages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5 of both CTAs) =====================
+        const int quarter = warp & 3;
+        uint2* stg = stage_buf + (size_t)(warp - 2) * kStageCap;
+        int it = 0;
+        for (int item = cid; item < n_items; item += ncl, ++it) {
+            const int tile = item / p.n_groups;
+            const int group = item - tile * p.n_groups;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            const int64_t row_warp0 =
+                p.row_begin + (int64_t)tile * (2 * kTileM) + (int64_t)rank * kTileM + quarter * 32;
+            const int q0 = group * p.nt;
+            int ncols = p.batch - q0;
+            if (ncols > p.nt) ncols = p.nt;
+            ptx::mbar_wait(&tmem_full[acc], acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccStride);
+            uint64_t* rel = &tmem_empty[acc];
+            epilogue_item(p, taddr, row_warp0, lane, q0, ncols, stg,
+                          [rel, lane]() { if (lane == 0) ptx2::mbar_arrive_cluster(rel, 0); });
+        }
+    }
+
+    // no CTA may exit (or free its TMEM) while its peer can still signal its barriers / read its smem
+    __syncwarp();
+    ptx::tc_fence_before();
+    ptx2::cluster_sync();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx2::tmem_dealloc_2sm(tmem_base, kTmemCols);
+    }
+}
+
+int encode_2d(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows);  // gemm.cu
+
+int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
+    const Store* s = a.store;
+    GemmParams p;
+    p.dim = s->dim;
+    p.num_kb = (s->dim + kBlockK - 1) / kBlockK;
+    p.nt = a.bpad < kMaxNT ? a.bpad : kMaxNT;
+    CMW_REQUIRE(p.nt % 32 == 0 && a.bpad % p.nt == 0, "launch_gemm_2cta: bad query padding %d", a.bpad);
+    p.n_groups = a.bpad / p.nt;
+    p.batch = a.batch;
+    p.row_begin = a.row_begin;
+    p.row_end = a.row_end;
+    p.n_tiles = (int)((a.row_end - a.row_begin + 2 * kTileM - 1) / (2 * kTileM));
+    p.stage_bytes = kABytes + (p.nt / 2) * kBlockK * 2;
+    const size_t tail = (2 * kMaxStages + 4) * sizeof(uint64_t) + 64 + 4 * kStageCap * sizeof(uint2);
+    int nst = (int)((220 * 1024 - tail - 1024) / (size_t)p.stage_bytes);
+    if (nst > kMaxStages) nst = kMaxStages;
+    p.nstages = nst;
+    p.dense = a.dense;
+    // instruction descriptor: D = f32, A = B = bf16, K-major, N >> 3 at bit 17, M = 256 >> 4 at bit 24
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    p.row_mul = a.row_mul;
+    p.pool_scores = a.pool.scores;
+    p.pool_ids = a.pool.ids;
+    p.pool_cnt = a.pool.cnt;
+    p.pool_thr = a.pool.thr;
+    CUtensorMap tmap_b;
+    int rc = encode_2d(&tmap_b, a.q_bf16, a.bpad, s->dim, p.nt / 2);
+    if (rc) return rc;
+    const size_t smem = (size_t)nst * p.stage_bytes + tail + 1024;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        CMW_CUDA_OK(cudaFuncSetAttribute(gemm_topk_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+        smem_set = smem;
+    }
+    const int n_items = p.n_tiles * p.n_groups;
+    int clusters = s->sm_count / 2;
+    if (n_items < clusters) clusters = n_items;
+    gemm_topk_kernel_2cta<<<2 * clusters, kGemm2Threads, smem, stream>>>(s->tmap_bf16, tmap_b, p);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cmw

@@ -1,0 +1,157 @@
+// gemm_common.cuh -- pieces shared by the two K2 kernels (1-CTA in gemm.cu, CTA-pair in gemm2.cu):
+// parameters, the shared-memory operand descriptor and the fused top-k admission epilogue.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cmw {
+
+constexpr int kTileM = 128;          // corpus rows per CTA per item (= TMEM lanes)
+constexpr int kBlockK = 64;          // bf16 elements per k-block = one 128-byte swizzle atom
+constexpr int kUmmaK = 16;
+constexpr int kMaxNT = 256;
+constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;      // TMEM columns per accumulator stage
+constexpr int kStageCap = 512;       // staged survivors per epilogue warp (8 bytes each)
+
+struct GemmParams {
+    int dim;
+    int num_kb;           // ceil(dim / 64)
+    int nt;               // queries per group (multiple of 16, <= 256)
+    int n_groups;
+    int batch;            // real queries
+    int64_t row_begin, row_end;
+    int n_tiles;          // row tiles (1-CTA: 128 rows, CTA pair: 256 rows)
+    int nstages;
+    int stage_bytes;
+    int dense;
+    uint32_t idesc;
+    const float* row_mul;
+    float* pool_scores;
+    int32_t* pool_ids;
+    int32_t* pool_cnt;
+    const float* pool_thr;
+};
+
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    // K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), LBO unused,
+    // descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+// Append the survivors a warp staged in shared memory to their queries' pools: every lane takes
+// entries, so 32-64 global atomics are in flight per round trip instead of one per admitted column.
+__device__ __forceinline__ void flush_staged(const uint2* stg, int wcount, int lane, int64_t row_warp0,
+                                             const GemmParams& p) {
+    __syncwarp();
+    for (int e = lane; e < wcount; e += 64) {
+        const bool two = (e + 32 < wcount);
+        const uint2 en0 = stg[e];
+        const uint2 en1 = two ? stg[e + 32] : make_uint2(0u, 0u);
+        const int qa = (int)(en0.y >> 5), qb = (int)(en1.y >> 5);
+        const int pos0 = atomicAdd(p.pool_cnt + qa, 1);
+        const int pos1 = two ? atomicAdd(p.pool_cnt + qb, 1) : kPoolCap;
+        if (pos0 < kPoolCap) {
+            p.pool_scores[(size_t)qa * kPoolCap + pos0] = __uint_as_float(en0.x);
+            p.pool_ids[(size_t)qa * kPoolCap + pos0] = (int32_t)(row_warp0 + (int)(en0.y & 31u));
+        }
+        if (pos1 < kPoolCap) {
+            p.pool_scores[(size_t)qb * kPoolCap + pos1] = __uint_as_float(en1.x);
+            p.pool_ids[(size_t)qb * kPoolCap + pos1] = (int32_t)(row_warp0 + (int)(en1.y & 31u));
+        }
+    }
+    __syncwarp();
+}
+
+// One epilogue warp, one finished accumulator: 32 TMEM lanes (corpus rows row_warp0 .. +31) x ncols
+// query columns starting at TMEM address `taddr`.  Scores = accumulator x per-row multiplier (NaN for
+// tombstoned / out-of-range rows).  Dense slab: every score goes to its own pool slot.  Otherwise the
+// score is compared with the query's admission threshold (thresholds of 32 queries are fetched as one
+// batch of broadcast, L1-resident loads while the TMEM load is in flight; padded queries carry +inf)
+// and the rare survivors are staged in the warp's shared-memory buffer (ballot + popc, no atomics).
+// `release()` is called once every tcgen05.ld of this accumulator has completed -- before the
+// global-atomic flush, so the MMA warp gets the accumulator back as early as possible.
+template <typename Release>
+__device__ __forceinline__ void epilogue_item(const GemmParams& p, uint32_t taddr, int64_t row_warp0, int lane,
+                                              int q0, int ncols, uint2* stg, Release release) {
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
+    const int64_t row = row_warp0 + lane;
+    const bool row_ok = row < p.row_end;
+    const float mul = row_ok ? __ldg(p.row_mul + row) : __int_as_float(0x7fc00000);
+    int wcount = 0;  // survivors staged by this warp (warp-uniform)
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        const bool wide = (p.nt - c0 >= 32);
+        if (wide) {
+            ptx::tmem_ld_32x32(taddr + (uint32_t)c0, v);
+        } else {
+            uint32_t w[16];
+            ptx::tmem_ld_32x16(taddr + (uint32_t)c0, w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                v[j] = w[j];
+                v[16 + j] = 0u;
+            }
+        }
+        float4 t4[8];
+        if (!p.dense) {
+            const float4* tp = reinterpret_cast<const float4*>(p.pool_thr + q0 + c0);
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                t4[g] = (wide || g < 4) ? __ldg(tp + g) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+        }
+        ptx::tmem_ld_wait();
+        if (p.dense) {
+            const int cend = (ncols - c0 < 32) ? (ncols - c0) : 32;
+            const size_t slot = (size_t)(row - p.row_begin);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (j < cend && row_ok) {
+                    const float s = __uint_as_float(v[j]) * mul;
+                    const size_t pos = (size_t)(q0 + c0 + j) * kPoolCap + slot;
+                    p.pool_scores[pos] = (s == s) ? s : -INFINITY;
+                    p.pool_ids[pos] = (int32_t)row;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float th[4] = {t4[g].x, t4[g].y, t4[g].z, t4[g].w};
+                float sc[4];
+                bool pass[4];
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    sc[u] = __uint_as_float(v[4 * g + u]) * mul;
+                    pass[u] = sc[u] >= th[u];
+                    any |= pass[u];
+                }
+                if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t m = __ballot_sync(0xffffffffu, pass[u]);
+                        if (pass[u]) {
+                            const int e = wcount + __popc(m & lanemask_lt);
+                            stg[e] = make_uint2(__float_as_uint(sc[u]),
+                                                ((uint32_t)(q0 + c0 + 4 * g + u) << 5) | (uint32_t)lane);
+                        }
+                        wcount += __popc(m);
+                    }
+                    if (wcount > kStageCap - 128) {
+                        flush_staged(stg, wcount, lane, row_warp0, p);
+                        wcount = 0;
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncwarp();
+    release();
+    if (wcount > 0) flush_staged(stg, wcount, lane, row_warp0, p);
+}
+
+}  // namespace cmw
