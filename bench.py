@@ -374,12 +374,20 @@ def run_ours(args):
         for _ in range(20):
             st.search_host(q_host[:1], k, mode=args.mode, algo=algo)
         host_ms = (time.perf_counter() - t_host0) / 20 * 1e3
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f).get("gemm_topk_kernel_batch1" if algo == "auto" else "scan_kernel_batch1")
+            if tr and (tr["rows"], tr["dim"], tr["k"]) == (args.rows, args.dim, k):
+                traffic = tr["traffic_bytes_per_step"]
+        except (OSError, ValueError, KeyError):
+            pass
         return {
             "algo": algo, "qps": 1e3 / float(np.mean(lat)), "p50_ms": float(np.median(lat)),
             "p99_ms": float(np.percentile(lat, 99)), "e2e_qps": 1e3 / host_ms, "e2e_ms": host_ms,
             "roofline": {"bound": "hbm", "kernel": kernel_name, "algorithmic_bytes": bytes_scan,
                          "achieved": bytes_scan / (filt_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": bytes_scan / (filt_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                         "frac": bytes_scan / (filt_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": traffic,
                          "peak_source": pk["source"], "filter_ms": filt_ms,
                          "whole_query_frac": bytes_scan / (float(np.mean(lat)) * 1e-3) / 1e9 / pk["hbm_gbs"]},
         }

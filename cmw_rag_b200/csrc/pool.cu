@@ -110,7 +110,7 @@ int launch_pool_set_count(Pool pool, int batch, int count, cudaStream_t stream) 
 constexpr int kCompactThreads = 256;
 constexpr int kCompactPer = kPoolCap / kCompactThreads;  // 16 entries per thread, in registers
 
-__global__ void __launch_bounds__(kCompactThreads) pool_compact_kernel(Pool pool, int kprime, int final) {
+__global__ void __launch_bounds__(kCompactThreads, 5) pool_compact_kernel(Pool pool, int kprime, int final) {
     extern __shared__ __align__(16) uint8_t cmp_smem[];
     __shared__ int hist[256];
     __shared__ int warp_sums[32];
@@ -258,49 +258,53 @@ rescore_kernel(const float* __restrict__ f32, const double* __restrict__ norm64,
                const uint32_t* __restrict__ maxnorm_bits, int k, double eps, double* __restrict__ exact) {
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
-    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int wpb = blockDim.x >> 5;
     const int n = pool.cnt[b] < kprime ? pool.cnt[b] : kprime;
-    if (j >= n) return;
     // The pool is sorted by filter score.  With a_k its k-th filter score, every row whose filter score
     // is below a_k - 2*eps has an exact score below a_k - eps <= (k-th exact score): it cannot be in the
     // exact top-k, so it is not rescored (its slot gets -inf and sorts last).
+    double cut = -INFINITY;
     if (n > k) {
         double e = eps;
         if (metric == CMW_METRIC_IP) e *= qn64[b] * (double)__uint_as_float(*maxnorm_bits);
-        const double cut = (double)pool.scores[(size_t)b * kPoolCap + (k - 1)] - 2.0 * e;
-        if ((double)pool.scores[(size_t)b * kPoolCap + j] < cut) {
-            if (lane == 0) exact[(size_t)b * kprime + j] = -INFINITY;
-            return;
-        }
+        cut = (double)pool.scores[(size_t)b * kPoolCap + (k - 1)] - 2.0 * e;
     }
-    const int32_t id = pool.ids[(size_t)b * kPoolCap + j];
-    const float4* row = reinterpret_cast<const float4*>(f32 + (size_t)id * dim);
     const float4* qv = reinterpret_cast<const float4*>(q_raw + (size_t)b * dim);
     const int nvec = dim >> 2;
-    double acc = 0.0;
-#pragma unroll 4
-    for (int c = lane; c < nvec; c += 32) {
-        const float4 v = __ldg(row + c);
-        const float4 w = __ldg(qv + c);
-        acc += (double)v.x * (double)w.x;
-        acc += (double)v.y * (double)w.y;
-        acc += (double)v.z * (double)w.z;
-        acc += (double)v.w * (double)w.w;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-        double s;
-        const float lv = live[id];
-        if (lv != lv) {
-            s = -INFINITY;  // tombstoned row that entered through the dense slab
-        } else if (metric == CMW_METRIC_COSINE) {
-            const double den = qn64[b] * norm64[id];
-            s = den > 0.0 ? acc / den : 0.0;
-        } else {
-            s = acc;
+    // gridDim.x blocks share a query (many for small batches, one for large ones); a warp walks its
+    // candidates in pool order, several rows' loads in flight
+    for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < n; j += gridDim.x * wpb) {
+        if ((double)pool.scores[(size_t)b * kPoolCap + j] < cut) {
+            if (lane == 0) exact[(size_t)b * kprime + j] = -INFINITY;
+            continue;
         }
-        exact[(size_t)b * kprime + j] = s;
+        const int32_t id = pool.ids[(size_t)b * kPoolCap + j];
+        const float4* row = reinterpret_cast<const float4*>(f32 + (size_t)id * dim);
+        double acc = 0.0;
+#pragma unroll 4
+        for (int c = lane; c < nvec; c += 32) {
+            const float4 v = __ldg(row + c);
+            const float4 w = __ldg(qv + c);
+            acc += (double)v.x * (double)w.x;
+            acc += (double)v.y * (double)w.y;
+            acc += (double)v.z * (double)w.z;
+            acc += (double)v.w * (double)w.w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            double s;
+            const float lv = live[id];
+            if (lv != lv) {
+                s = -INFINITY;  // tombstoned row that entered through the dense slab
+            } else if (metric == CMW_METRIC_COSINE) {
+                const double den = qn64[b] * norm64[id];
+                s = den > 0.0 ? acc / den : 0.0;
+            } else {
+                s = acc;
+            }
+            exact[(size_t)b * kprime + j] = s;
+        }
     }
 }
 
@@ -365,7 +369,12 @@ int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprim
                           int32_t* out_flags, cudaStream_t stream) {
     CMW_REQUIRE(s->f32 != nullptr, "CMW_MODE_F32_EXACT needs a store created with CMW_STORE_F32");
     const int wpb = 8;
-    dim3 grid((kprime + wpb - 1) / wpb, batch);
+    // enough blocks to fill the GPU a few times over, at most one warp per candidate
+    int per_query = (s->sm_count * 16 + batch - 1) / batch;
+    const int max_per_query = (kprime + wpb - 1) / wpb;
+    if (per_query > max_per_query) per_query = max_per_query;
+    if (per_query < 1) per_query = 1;
+    dim3 grid(per_query, batch);
     rescore_kernel<<<grid, wpb * 32, 0, stream>>>(s->f32, s->norm64, s->live, s->dim, pool, kprime,
                                                  metric, q_raw, qn64, s->maxnorm_bits, k, eps, exact_ws);
     CMW_LAUNCHED();

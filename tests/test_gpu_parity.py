@@ -459,3 +459,35 @@ def test_clustered_corpus_exact_and_recall(torch_cuda):
     recall = np.mean([len(set(ids_b[b]) & set(ref_ids[b])) / k for b in range(q.shape[0])])
     assert recall >= 0.9, recall
     st.close()
+
+
+def test_rerank_side_grouping_matches_reference_semantics(torch_cuda):
+    """scored chunks -> articles (retriever.py:234-260,307-316) through K4 with one
+    segment per query, against the CPU restatement; boosts as in reranker.py:165-181."""
+    from cmw_rag_b200 import B200Store
+    from cmw_rag_b200.articles import boost_and_order, group_scored_chunks
+    from oracle.multivector import group_by_kbid, normalized_ranks
+
+    rng = np.random.default_rng(12)
+    n = 400
+    kb = [("" if i % 37 == 0 else str(500 + i // 5) + ("-toc" if i % 11 == 0 else "")) for i in range(n)]
+    store = B200Store("articles", capacity=512)
+    store.add([f"c{i}" for i in range(n)],
+              [{"stable_id": str(i), "kbId": kb[i], "has_code": i % 3 == 0, "tags": "x" if i % 4 == 0 else ""} for i in range(n)],
+              ids=[str(i) for i in range(n)], embeddings=rng.standard_normal((n, 16)).astype(np.float32))
+    rows = rng.permutation(n)[:60]
+    raw = rng.random(60).astype(np.float32)
+    weights = {"tag_match": 0.1, "code_presence": 0.05, "section_match": 0.0}
+    order, final = boost_and_order(raw, [store._metas[r] for r in rows], weights, top_k=40)
+    rows_o = rows[order]
+    final32 = np.asarray(final, np.float32)
+    for threshold in (None, 0.5):
+        arts = group_scored_chunks(store, rows_o[None, :], final32[None, :], threshold=threshold)[0]
+        gid = np.array([store.gid_for(k) for k in kb])
+        ref = group_by_kbid(rows_o.tolist(), [float(x) for x in final32], gid)
+        keep = [gi for gi in ref["order"] if threshold is None or ref["max"][gi] >= threshold]
+        assert [a.kb_id for a in arts] == [store.key_of_gid(ref["gid"][gi]) for gi in keep]
+        assert [a.score for a in arts] == [ref["max"][gi] for gi in keep]
+        assert [a.rows for a in arts] == [[rows_o[m] for m in ref["members"][gi]] for gi in keep]
+        assert [a.normalized_rank for a in arts] == normalized_ranks(len(keep))
+        assert all(a.metadata["stable_id"] == str(a.rows[0]) for a in arts)
