@@ -173,6 +173,8 @@ class B200Store:
             dense = self._ensure(emb.shape[1])
             gids = np.array([self.gid_for((metadatas[i] or {}).get("kbId", "")) for i in keep], np.int32)
             base = len(self._ids)
+            if base + len(keep) > self._capacity:
+                dense = self._grow(base + len(keep))
             dense.append(self._pad(emb[keep]), gids)
             for j, i in enumerate(keep):
                 self._row_of[ids[i]] = base + j
@@ -180,6 +182,29 @@ class B200Store:
                 self._docs.append(texts[i])
                 self._metas.append(dict(metadatas[i]) if metadatas[i] is not None else None)
                 self._alive.append(True)
+
+    def _grow(self, needed: int, chunk_rows: int = 65536) -> DenseStore:
+        """A Chroma collection grows without bound; the HBM store is sized up front.  When an add would
+        overflow it, a store twice as large is created and the rows are copied over through the
+        read-back entry point (tombstones replayed).  Needs the fp32 tiles."""
+        if not self._keep[0]:
+            raise RuntimeError(f"collection is full ({self._capacity} rows) and keeps no fp32 tiles to grow from")
+        new_cap = max(needed, 2 * self._capacity)
+        old = self._dense
+        new = DenseStore(self._pdim, new_cap, device=self._device, f32=self._keep[0], bf16=self._keep[1],
+                         id_offset=self._id_offset)
+        n = len(self._ids)
+        for lo in range(0, n, chunk_rows):
+            m = min(chunk_rows, n - lo)
+            rows, gid, _ = old.read_rows(lo, m)
+            new.append(rows, gid)
+        dead = [r for r, alive in enumerate(self._alive) if not alive]
+        if dead:
+            new.tombstone(dead)
+        old.close()
+        self._dense = new
+        self._capacity = new_cap
+        return new
 
     def _rows_where(self, where, limit: int | None = None) -> list[int]:
         out = []

@@ -491,3 +491,30 @@ def test_rerank_side_grouping_matches_reference_semantics(torch_cuda):
         assert [a.rows for a in arts] == [[rows_o[m] for m in ref["members"][gi]] for gi in keep]
         assert [a.normalized_rank for a in arts] == normalized_ranks(len(keep))
         assert all(a.metadata["stable_id"] == str(a.rows[0]) for a in arts)
+
+
+@pytest.mark.parametrize("k,batch", [(1, 3), (1, 40), (1000, 2), (257, 300)])
+def test_extreme_k(cfg1, k, batch):
+    """k = 1 and k near the K' ceiling (1024): the certificate has little or no head-room, so the host
+    API may have to fall back -- the ids must be the oracle's either way."""
+    c = cfg1["c"]
+    q, _ = synth.make_queries(c, batch, seed=41 + k, tie_probe=False)
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, k)
+    sc, ids, fl = cfg1["store"].search_host(q, k, mode="f32")
+    _check_exact(ids, sc, ref_ids, ref_sc)
+    assert (fl == 0).all()
+
+
+def test_batch_larger_than_4096_and_store_growth(torch_cuda):
+    from cmw_rag_b200 import B200Store
+
+    c = synth.make_corpus(6000, 128, seed=3)
+    store = B200Store("grow", capacity=1024)  # forces two growth steps
+    for lo in range(0, 6000, 1500):
+        store.add([f"t{i}" for i in range(lo, lo + 1500)], [{"kbId": str(i // 4)} for i in range(lo, lo + 1500)],
+                  ids=[str(i) for i in range(lo, lo + 1500)], embeddings=c[lo:lo + 1500])
+    assert store.count() == 6000 and store.dense.info()["capacity_rows"] >= 6000
+    q, _ = synth.make_queries(c, 4200, seed=6, tie_probe=False)  # 4200 -> 17 query groups of 256
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, 10)
+    sc, ids, fl = store.search(q, 10)
+    _check_exact(ids, sc, ref_ids, ref_sc)

@@ -114,6 +114,9 @@ class FakeDense:
     def tombstone(self, rows):
         self.live[np.asarray(rows, np.int64)] = False
 
+    def close(self):
+        pass
+
     def read_rows(self, row0, n, rows=True):
         return self.rows_[row0:row0 + n].copy(), self.gid[row0:row0 + n].copy(), self.live[row0:row0 + n].copy()
 
@@ -230,6 +233,25 @@ def test_save_load_roundtrip_host_layer(fake_store, tmp_path):
     assert again.gid_for("100") == store.gid_for("100-toc")
     again.add(["new"], [{"kbId": "999"}], ids=["new"], embeddings=rng.standard_normal((1, 12)))
     assert again.count() == 39
+
+
+def test_collection_grows_past_its_capacity(monkeypatch):
+    import cmw_rag_b200.store as store_mod
+
+    monkeypatch.setattr(store_mod, "DenseStore", FakeDense)
+    store = store_mod.B200Store(collection_name="g", capacity=8)
+    rng = np.random.default_rng(1)
+    emb = rng.standard_normal((30, 8)).astype(np.float32)
+    store.add([f"a{i}" for i in range(6)], [{"kbId": str(i)} for i in range(6)], ids=[f"a{i}" for i in range(6)], embeddings=emb[:6])
+    store.delete(ids=["a2"])
+    store.add([f"b{i}" for i in range(24)], [{"kbId": str(100 + i)} for i in range(24)], ids=[f"b{i}" for i in range(24)],
+              embeddings=emb[6:])
+    assert store.count() == 29 and store._capacity >= 30
+    live = np.ones(30, bool)
+    live[2] = False
+    ref, _, _ = exact_topk(emb, emb[:4], 5, live=live)
+    _, ids, _ = store.search(emb[:4], 5)
+    assert (ids == ref).all()
 
 
 def test_shard_bounds():
