@@ -282,8 +282,14 @@ def run_ours(args):
     if row_shard:  # every shard must answer the same queries; the needles live in rank 0's shard
         dist.broadcast(q, 0)
         dist.broadcast(needle, 0)
-    q_host = q.cpu().numpy()
+    # the end-to-end leg hands the library page-locked host buffers (driver contract: "host->device copy
+    # of that step's inputs from pinned host memory")
+    from cmw_rag_b200.engine import pinned_empty
+
     k, B = args.k, args.batch
+    q_host = pinned_empty((B, args.dim), np.float32)
+    q_host[:] = q.cpu().numpy()
+    out_host = (pinned_empty((B, k), np.float32), pinned_empty((B, k), np.int64), np.zeros((B,), np.int32))
 
     def step_device():
         if not row_shard:
@@ -337,9 +343,11 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        st.search_host(q_host, k, mode=args.mode, algo=args.algo)
+        st.search_host(q_host, k, mode=args.mode, algo=args.algo, out=out_host)
     torch.cuda.synchronize(device)
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    if not row_shard:
+        assert (out_host[1] == ids0_h).all(), "host-buffer path and device path disagree"
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:

@@ -388,32 +388,58 @@ int cmw_search_host(cmw_store* h, const float* queries_host, int batch, int k, i
     uint8_t* pin = reinterpret_cast<uint8_t*>(s->pinned);
     uint8_t* dev = reinterpret_cast<uint8_t*>(s->dev_io);
 
-    auto run = [&](const float* q_src, int nb, int run_mode) -> int {
-        // pageable -> pinned -> device, pipelined: a few host threads copy 1 MB pieces into the pinned
-        // staging buffer and enqueue each piece's H2D as soon as it is staged, so the DMA of one piece
-        // overlaps the memcpy of the next (all pieces precede the search on the same stream)
-        if (stage_h2d(s->device, pin, dev, reinterpret_cast<const uint8_t*>(q_src), (size_t)nb * s->dim * sizeof(float),
-                      stream))
+    // page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used for
+    // DMA directly; pageable ones go through the store's pinned staging buffer
+    auto is_pinned = [](const void* p) -> bool {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return attr.type == cudaMemoryTypeHost;
+    };
+    const bool out_pinned = is_pinned(out_scores_host) && is_pinned(out_ids_host);
+
+    auto run = [&](const float* q_src, int nb, int run_mode, bool direct_out) -> int {
+        const size_t qb = (size_t)nb * s->dim * sizeof(float);
+        if (is_pinned(q_src)) {
+            CMW_CUDA_OK(cudaMemcpyAsync(dev, q_src, qb, cudaMemcpyHostToDevice, stream));
+        } else if (stage_h2d(s->device, pin, dev, reinterpret_cast<const uint8_t*>(q_src), qb, stream)) {
+            // pageable -> pinned -> device, pipelined: a few host threads copy 1 MB pieces into the pinned
+            // staging buffer and enqueue each piece's H2D as soon as it is staged, so the DMA of one
+            // piece overlaps the memcpy of the next (all pieces precede the search on the same stream)
             return -2;
+        }
         int r = cmw_search(h, reinterpret_cast<const float*>(dev), nb, k, metric, run_mode,
                            reinterpret_cast<float*>(dev + q_bytes),
                            reinterpret_cast<int64_t*>(dev + q_bytes + sc_bytes), nullptr,
                            reinterpret_cast<int32_t*>(dev + q_bytes + sc_bytes + id_bytes), s->ws,
                            s->ws_bytes, stream);
         if (r) return r;
-        // one D2H for scores + ids + flags (contiguous in dev_io)
-        CMW_CUDA_OK(cudaMemcpyAsync(pin + q_bytes, dev + q_bytes, sc_bytes + id_bytes + fl_bytes,
-                                    cudaMemcpyDeviceToHost, stream));
+        if (direct_out) {
+            CMW_CUDA_OK(cudaMemcpyAsync(out_scores_host, dev + q_bytes, (size_t)nb * k * sizeof(float),
+                                        cudaMemcpyDeviceToHost, stream));
+            CMW_CUDA_OK(cudaMemcpyAsync(out_ids_host, dev + q_bytes + sc_bytes, (size_t)nb * k * sizeof(int64_t),
+                                        cudaMemcpyDeviceToHost, stream));
+            CMW_CUDA_OK(cudaMemcpyAsync(pin + q_bytes + sc_bytes + id_bytes, dev + q_bytes + sc_bytes + id_bytes,
+                                        fl_bytes, cudaMemcpyDeviceToHost, stream));
+        } else {
+            // one D2H for scores + ids + flags (contiguous in dev_io)
+            CMW_CUDA_OK(cudaMemcpyAsync(pin + q_bytes, dev + q_bytes, sc_bytes + id_bytes + fl_bytes,
+                                        cudaMemcpyDeviceToHost, stream));
+        }
         CMW_CUDA_OK(cudaStreamSynchronize(stream));
         return 0;
     };
 
-    if ((rc = run(queries_host, batch, mode))) return rc;
+    if ((rc = run(queries_host, batch, mode, out_pinned))) return rc;
     const float* sc = reinterpret_cast<const float*>(pin + q_bytes);
     const int64_t* id = reinterpret_cast<const int64_t*>(pin + q_bytes + sc_bytes);
     const int32_t* fl = reinterpret_cast<const int32_t*>(pin + q_bytes + sc_bytes + id_bytes);
-    memcpy(out_scores_host, sc, (size_t)batch * k * sizeof(float));
-    memcpy(out_ids_host, id, (size_t)batch * k * sizeof(int64_t));
+    if (!out_pinned) {
+        memcpy(out_scores_host, sc, (size_t)batch * k * sizeof(float));
+        memcpy(out_ids_host, id, (size_t)batch * k * sizeof(int64_t));
+    }
     std::vector<int> redo;
     for (int b = 0; b < batch; ++b) {
         if (out_flags_host) out_flags_host[b] = fl[b];
@@ -428,7 +454,7 @@ int cmw_search_host(cmw_store* h, const float* queries_host, int batch, int k, i
         for (size_t i = 0; i < redo.size(); ++i)
             memcpy(q2.data() + i * s->dim, queries_host + (size_t)redo[i] * s->dim,
                    (size_t)s->dim * sizeof(float));
-        if ((rc = run(q2.data(), (int)redo.size(), CMW_MODE_F32_EXACT | CMW_ALGO_SCAN | CMW_SLABS_SAFE)))
+        if ((rc = run(q2.data(), (int)redo.size(), CMW_MODE_F32_EXACT | CMW_ALGO_SCAN | CMW_SLABS_SAFE, false)))
             return rc;
         for (size_t i = 0; i < redo.size(); ++i) {
             const int b = redo[i];

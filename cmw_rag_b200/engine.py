@@ -189,15 +189,23 @@ class DenseStore:
         )
         return (scores, ids, flags, s64) if return_scores64 else (scores, ids, flags)
 
-    def search_host(self, queries, k: int, metric="cosine", mode="f32", algo=None):
-        """End-to-end form with HOST buffers (numpy in, numpy out): pinned staging, H2D, kernels,
-        D2H, synchronised.  This is the call that stands in for one HTTP round trip to Chroma."""
+    def search_host(self, queries, k: int, metric="cosine", mode="f32", algo=None, out=None):
+        """End-to-end form with HOST buffers (numpy in, numpy out): H2D, kernels, D2H, synchronised.
+        This is the call that stands in for one HTTP round trip to Chroma.  Pageable arrays go through
+        the store's pinned staging buffer; page-locked ones (``pinned_empty``) are used for DMA
+        directly.  ``out`` = optional preallocated (scores f32[B,k], ids i64[B,k], flags i32[B])."""
         q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
         assert q.shape[1] == self.dim
         b = q.shape[0]
-        scores = np.empty((b, k), np.float32)
-        ids = np.empty((b, k), np.int64)
-        flags = np.zeros((b,), np.int32)
+        if out is not None:
+            scores, ids, flags = out
+            assert scores.shape == (b, k) and scores.dtype == np.float32 and scores.flags.c_contiguous
+            assert ids.shape == (b, k) and ids.dtype == np.int64 and ids.flags.c_contiguous
+            assert flags.shape == (b,) and flags.dtype == np.int32
+        else:
+            scores = np.empty((b, k), np.float32)
+            ids = np.empty((b, k), np.int64)
+            flags = np.zeros((b,), np.int32)
         if b:
             N.check(
                 N.lib().cmw_search_host(self._h, q.ctypes.data, b, k, N.METRICS[metric],
@@ -268,6 +276,13 @@ class DenseStore:
         scores, ids, flags = self.search(flat, k, metric=metric, mode=mode, algo=algo)
         res = self.multivector(ids.view(qn, s, k), scores.view(qn, s, k), prl=prl, limit=limit)
         return res, scores.view(qn, s, k), ids.view(qn, s, k), flags.view(qn, s)
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """A page-locked numpy array (backed by a torch pinned tensor kept alive by the array)."""
+    torch = _torch()
+    t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+    return t.numpy()
 
 
 def merge_topk(scores64, ids, k_out: int):
