@@ -50,7 +50,7 @@ extern std::atomic<long long> g_kernel_launches;
 //   appended so far (may exceed CAP -> overflow), thr[b] admission threshold (score >= thr).
 // ---------------------------------------------------------------------------------------------
 constexpr int kPoolCap = 4096;      // entries per query
-constexpr int kDenseSlabRows = 2048;  // first slab: every row is written (no threshold yet)
+constexpr int kDenseSlabRows = 4096;  // first slab: every row is written (no threshold yet); = kPoolCap
 constexpr int kMaxKPrime = 1024;
 
 struct Pool {

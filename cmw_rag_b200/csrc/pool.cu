@@ -281,14 +281,30 @@ rescore_kernel(const float* __restrict__ f32, const double* __restrict__ norm64,
         const int32_t id = pool.ids[(size_t)b * kPoolCap + j];
         const float4* row = reinterpret_cast<const float4*>(f32 + (size_t)id * dim);
         double acc = 0.0;
+        if (nvec == 384) {
+            // D = 1536: the whole row (12 x 128-bit per lane) is requested before the first use, so a
+            // warp keeps 6 KB in flight; same summation order as the generic loop
+            float4 v[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) v[i] = __ldg(row + lane + 32 * i);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const float4 w = __ldg(qv + lane + 32 * i);
+                acc += (double)v[i].x * (double)w.x;
+                acc += (double)v[i].y * (double)w.y;
+                acc += (double)v[i].z * (double)w.z;
+                acc += (double)v[i].w * (double)w.w;
+            }
+        } else {
 #pragma unroll 4
-        for (int c = lane; c < nvec; c += 32) {
-            const float4 v = __ldg(row + c);
-            const float4 w = __ldg(qv + c);
-            acc += (double)v.x * (double)w.x;
-            acc += (double)v.y * (double)w.y;
-            acc += (double)v.z * (double)w.z;
-            acc += (double)v.w * (double)w.w;
+            for (int c = lane; c < nvec; c += 32) {
+                const float4 v = __ldg(row + c);
+                const float4 w = __ldg(qv + c);
+                acc += (double)v.x * (double)w.x;
+                acc += (double)v.y * (double)w.y;
+                acc += (double)v.z * (double)w.z;
+                acc += (double)v.w * (double)w.w;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
