@@ -263,12 +263,13 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
     double* exact = reinterpret_cast<double*>(ws + w.exact);
 
     int rc;
+    const int64_t rows = s->rows;
+    const int64_t slab0 = rows < kDenseSlabRows ? rows : kDenseSlabRows;
     {
         PhaseTimer t(3, stream);
         if ((rc = launch_prep_queries(queries_dev, batch, w.bpad, s->dim, metric, qn64, q_f32,
-                                      gemm ? q_bf16 : nullptr, stream)))
+                                      gemm ? q_bf16 : nullptr, pool, (int)slab0, stream)))
             return rc;
-        if ((rc = launch_pool_reset(pool, batch, w.bpad, stream))) return rc;
     }
 
     // which tiles the filter reads, and the per-row multiplier that goes with them
@@ -321,15 +322,12 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
         return launch_pool_compact(pool, batch, kprime, last ? 1 : 0, stream);
     };
 
-    const int64_t rows = s->rows;
     double growth = (double)(kPoolCap - kprime) / (3.0 * kprime);
     if (growth > 8.0) growth = 8.0;
     if (g_opt.slab_growth > 0 && g_opt.slab_growth < growth) growth = g_opt.slab_growth;
     if (growth < 1.0) growth = 1.0;
     int64_t seen = 0;
     if (rows > 0) {
-        const int64_t slab0 = rows < kDenseSlabRows ? rows : kDenseSlabRows;
-        if ((rc = launch_pool_set_count(pool, batch, (int)slab0, stream))) return rc;
         if ((rc = run_filter(0, slab0, 1))) return rc;
         if ((rc = compact(slab0 == rows))) return rc;
         seen = slab0;

@@ -143,9 +143,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 bool gemm_supported(const Store* s);
 
 int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64,
-                        float* q_f32, __nv_bfloat16* q_bf16, cudaStream_t stream);
-int launch_pool_reset(Pool pool, int batch, int bpad, cudaStream_t stream);
-int launch_pool_set_count(Pool pool, int batch, int count, cudaStream_t stream);
+                        float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count,
+                        cudaStream_t stream);
 int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_t stream);
 // exact fp64 rescoring of the pool's first min(cnt, kprime) entries + final (score desc, id asc)
 // selection with the exactness certificate

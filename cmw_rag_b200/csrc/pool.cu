@@ -14,11 +14,19 @@ namespace cmw {
 __global__ void __launch_bounds__(256)
 prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, int metric,
                     double* __restrict__ qn64, float* __restrict__ q_f32,
-                    __nv_bfloat16* __restrict__ q_bf16) {
+                    __nv_bfloat16* __restrict__ q_bf16, Pool pool, int dense_count) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= bpad) return;
     const int nvec = dim >> 2;
+    // pool state for the new search: the dense slab will fill `dense_count` slots of every real query;
+    // cnt/thr/ovf hold bpad entries and the padded queries of the last K2 group keep thr = +inf so that
+    // the epilogue needs no column mask
+    if (lane == 0) {
+        pool.cnt[b] = (b < batch) ? dense_count : 0;
+        pool.thr[b] = (b < batch) ? -INFINITY : INFINITY;
+        pool.ovf[b] = 0;
+    }
     if (b >= batch) {
         if (q_bf16 != nullptr) {
             uint2* out = reinterpret_cast<uint2*>(q_bf16 + (size_t)b * dim);
@@ -55,10 +63,11 @@ prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, i
 }
 
 int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64,
-                        float* q_f32, __nv_bfloat16* q_bf16, cudaStream_t stream) {
+                        float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count,
+                        cudaStream_t stream) {
     const int wpb = 8;
     prep_queries_kernel<<<(bpad + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, batch, bpad, dim, metric,
-                                                                        qn64, q_f32, q_bf16);
+                                                                        qn64, q_f32, q_bf16, pool, dense_count);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
@@ -67,40 +76,6 @@ int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric
 // ---------------------------------------------------------------------------------------------
 // pool maintenance
 // ---------------------------------------------------------------------------------------------
-// cnt/thr/ovf hold bpad entries: the padded queries of the last K2 group keep thr = +inf so that the
-// epilogue needs no column mask
-__global__ void pool_reset_kernel(Pool pool, int batch, int bpad, int count) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= bpad) return;
-    if (b >= batch) {
-        if (count == 0) {
-            pool.cnt[b] = 0;
-            pool.thr[b] = INFINITY;
-            pool.ovf[b] = 0;
-        }
-        return;
-    }
-    pool.cnt[b] = count;
-    if (count == 0) {
-        pool.thr[b] = -INFINITY;
-        pool.ovf[b] = 0;
-    }
-}
-
-int launch_pool_reset(Pool pool, int batch, int bpad, cudaStream_t stream) {
-    pool_reset_kernel<<<(bpad + 255) / 256, 256, 0, stream>>>(pool, batch, bpad, 0);
-    CMW_LAUNCHED();
-    CMW_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-int launch_pool_set_count(Pool pool, int batch, int count, cudaStream_t stream) {
-    pool_reset_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(pool, batch, batch, count);
-    CMW_LAUNCHED();
-    CMW_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
 // One CTA per query.  Intermediate slabs only need the best kprime entries and the admission
 // threshold, not their order: an MSB-first radix select (4 passes of 8 bits over the order-preserving
 // score keys, shared-memory histograms) finds the kprime-th best score T, entries with score >= T are
