@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--mode", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--shard", default="queries", choices=["queries", "rows"])
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="--shard rows: NCCL all-gather + merge kernel, or the fused NVLink peer-memory exchange")
     ap.add_argument("--no-f32", action="store_true", help="bf16 tiles only (rows-sharded 200M config)")
     ap.add_argument("--cpu-queries", type=int, default=16, help="queries in the bounded CPU sample")
     ap.add_argument("--hnsw-rows", type=int, default=50_000, help="rows in the CPU HNSW index (bounded sample)")
@@ -291,10 +293,19 @@ def run_ours(args):
     q_host[:] = q.cpu().numpy()
     out_host = (pinned_empty((B, k), np.float32), pinned_empty((B, k), np.int64), np.zeros((B,), np.int32))
 
+    peer_ex = None
+    if row_shard and args.exchange == "peer":
+        from cmw_rag_b200.sharded import PeerExchange
+
+        peer_ex = PeerExchange(device=local_rank, max_batch=B, max_k=k)
+
     def step_device():
         if not row_shard:
             return st.search(q, k, mode=args.mode, algo=args.algo)
         sc, ids, fl, s64 = st.search(q, k, mode=args.mode, algo=args.algo, return_scores64=True)
+        if peer_ex is not None:
+            ms, mi, _ = peer_ex.exchange_merge(s64, ids, k)
+            return ms, mi, fl
         g_s = torch.empty((world * B, k), dtype=s64.dtype, device=device)
         g_i = torch.empty((world * B, k), dtype=ids.dtype, device=device)
         dist.all_gather_into_tensor(g_s, s64)
@@ -492,7 +503,7 @@ def run_ours(args):
             "workload": f"{total_rows}x{args.dim} {'fp32+bf16' if not args.no_f32 else 'bf16'} corpus, "
                         f"query batch {B} per GPU, top-{k} {'exact' if args.mode == 'f32' else 'bf16'} cosine",
             "parallelism": ("single GPU" if world == 1 else
-                            (f"corpus row-sharded over {world} GPUs, NCCL all-gather + merge kernel" if row_shard
+                            (f"corpus row-sharded over {world} GPUs, " + ("fused NVLink peer-store exchange + merge kernels (no collective)" if args.exchange == "peer" else "NCCL all-gather + merge kernel") if row_shard
                              else f"corpus replicated, query batch sharded over {world} GPUs (no collective)")),
             "l2": "inputs larger than L2 (corpus tiles >= 3 GB per pass vs 126 MB), no flush",
             "mode": args.mode, "algo": args.algo, "uncertified_queries": uncertified,

@@ -68,6 +68,13 @@ SIGNATURES = {
                                 c_int, c_int] + [c_void_p] * 11 + [c_void_p]),
     "cmw_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
+    "cmw_peer_buffer_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "cmw_peer_alloc": (c_int, [c_int, c_size_t, POINTER(c_void_p), c_void_p]),
+    "cmw_peer_open": (c_int, [c_int, c_void_p, POINTER(c_void_p)]),
+    "cmw_peer_close": (c_int, [c_void_p]),
+    "cmw_peer_free": (c_int, [c_void_p]),
+    "cmw_exchange_merge": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_uint32,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cmw_kernel_launches": (c_int64, []),
     "cmw_profile_enable": (c_int, [c_int]),
     "cmw_profile_read": (c_int, [POINTER(c_double), POINTER(c_int64), c_int]),

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libcmwdense.so")
-SOURCES = ["store.cu", "scan.cu", "gemm.cu", "gemm2.cu", "pool.cu", "multivector.cu", "api.cu"]
+SOURCES = ["store.cu", "scan.cu", "gemm.cu", "gemm2.cu", "pool.cu", "multivector.cu", "exchange.cu", "api.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", "gemm_common.cuh", os.path.join("..", "..", "include", "cmw_dense.h")]
 
 NVCC_FLAGS = [

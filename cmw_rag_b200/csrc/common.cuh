@@ -163,6 +163,21 @@ int ensure_dev_io(Store* s, size_t bytes);
 int ensure_ws(Store* s, size_t bytes);
 int get_stream(Store* s, cudaStream_t* out);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remember what was set where
+struct SmemAttrCache {
+    size_t set[64] = {};
+    bool needs(size_t bytes) const {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return bytes > set[dev & 63];
+    }
+    void done(size_t bytes) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        set[dev & 63] = bytes;
+    }
+};
+
 inline int next_pow2_host(int v) {
     int p = 1;
     while (p < v) p <<= 1;

@@ -1,0 +1,210 @@
+// exchange.cu -- K5x: the cross-shard candidate exchange fused with the merge, over NVLink peer memory.
+//
+// Row-sharded corpus: every rank holds a local top-k per query as (fp64 score, global
+// id).  Instead of two NCCL all-gathers followed by the merge kernel, each rank's SEND kernel stores its
+// candidates straight into the gather buffer of EVERY peer (st.global on cudaIpc-mapped peer pointers:
+// NVLink 5 / NVSwitch writes), fences, and the last block publishes an epoch flag on each peer; the
+// MERGE kernel of each rank spins on its own flags (one per source rank) and then reduces G*k -> k per
+// query with the usual (score desc, id asc) rule.  The send kernel never waits, so every rank's flags
+// are eventually published whatever the launch skew; buffers are double-buffered by epoch parity
+// (a rank can only reach epoch n+2 after all peers have published n+1, i.e. finished reading n).
+// The reference has no counterpart (single Chroma server).
+//
+// Peer buffer layout (one per rank, allocated by cmw_peer_alloc, zero-initialised):
+//   [0, 1024)            header: uint32 flags[2][64] (parity, source rank), uint32 done[2]
+//   [1024, ...)          2 parities x { f64 scores [G, Bmax, kmax] ; i64 ids [G, Bmax, kmax] }
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cmw {
+
+constexpr int kXMaxRanks = 64;
+constexpr size_t kXHeaderBytes = 1024;
+
+struct XPeers {
+    uint8_t* buf[kXMaxRanks];
+};
+
+__device__ __forceinline__ uint32_t* x_flags(uint8_t* base, int parity) {
+    return reinterpret_cast<uint32_t*>(base) + parity * kXMaxRanks;
+}
+__device__ __forceinline__ uint32_t* x_done(uint8_t* base, int parity) {
+    return reinterpret_cast<uint32_t*>(base) + 2 * kXMaxRanks + parity;
+}
+
+__global__ void __launch_bounds__(256)
+exchange_send_kernel(XPeers peers, int G, int rank, int B, int k, size_t slot_elems, size_t parity_bytes, int parity,
+                     uint32_t epoch, const double* __restrict__ scores, const int64_t* __restrict__ ids) {
+    const size_t n = (size_t)B * k;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int g = 0; g < G; ++g) {
+        uint8_t* base = peers.buf[g] + kXHeaderBytes + (size_t)parity * parity_bytes;
+        double* ds = reinterpret_cast<double*>(base) + (size_t)rank * slot_elems;
+        int64_t* di = reinterpret_cast<int64_t*>(base + (size_t)G * slot_elems * sizeof(double)) + (size_t)rank * slot_elems;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            ds[i] = scores[i];
+            di[i] = ids[i];
+        }
+    }
+    // publish: every block fences its peer stores system-wide; the last one to finish raises the flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t* done = x_done(peers.buf[rank], parity);
+        const uint32_t prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) {
+            *done = 0;  // ready for the next use of this parity
+            __threadfence_system();
+            for (int g = 0; g < G; ++g) {
+                volatile uint32_t* f = x_flags(peers.buf[g], parity) + rank;
+                *f = epoch;
+            }
+            __threadfence_system();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+exchange_merge_kernel(uint8_t* self, int G, int B, int k, int k_out, size_t slot_elems, size_t parity_bytes,
+                      int parity, uint32_t epoch, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                      double* __restrict__ out_scores64) {
+    extern __shared__ __align__(16) uint8_t x_smem[];
+    // wait until every source rank has published this epoch
+    if (threadIdx.x < G) {
+        volatile uint32_t* f = x_flags(self, parity) + threadIdx.x;
+        while (*f != epoch) {
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    const int b = blockIdx.x;
+    const int n = G * k;
+    const int m = next_pow2(n < 2 ? 2 : n);
+    uint64_t* hi = reinterpret_cast<uint64_t*>(x_smem);
+    uint64_t* lo = hi + m;
+    const uint8_t* base = self + kXHeaderBytes + (size_t)parity * parity_bytes;
+    const double* gs = reinterpret_cast<const double*>(base);
+    const int64_t* gi = reinterpret_cast<const int64_t*>(base + (size_t)G * slot_elems * sizeof(double));
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        uint64_t h = ~0ull, l = ~0ull;
+        if (i < n) {
+            const int g = i / k, j = i - g * k;
+            const size_t src = (size_t)g * slot_elems + (size_t)b * k + j;
+            // peers wrote these through NVLink: bypass L1 (volatile) -- they are fresh in L2 / HBM
+            const int64_t id = *reinterpret_cast<const volatile int64_t*>(gi + src);
+            const double s = *reinterpret_cast<const volatile double*>(gs + src);
+            if (id >= 0 && s == s) {
+                h = ~f64_orderable(s);
+                l = (uint64_t)id;
+            }
+        }
+        hi[i] = h;
+        lo[i] = l;
+    }
+    bitonic_sort_u128(hi, lo, m);
+    for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
+        double s = -INFINITY;
+        int64_t id = -1;
+        if (j < n && !(hi[j] == ~0ull && lo[j] == ~0ull)) {
+            s = f64_from_orderable(~hi[j]);
+            id = (int64_t)lo[j];
+        }
+        out_scores[(size_t)b * k_out + j] = (float)s;
+        out_ids[(size_t)b * k_out + j] = id;
+        if (out_scores64 != nullptr) out_scores64[(size_t)b * k_out + j] = s;
+    }
+}
+
+}  // namespace cmw
+
+using namespace cmw;
+
+extern "C" {
+
+size_t cmw_peer_buffer_bytes(int G, int max_batch, int max_k) {
+    if (G < 1 || G > kXMaxRanks || max_batch < 1 || max_k < 1) return 0;
+    return kXHeaderBytes + 2 * (size_t)G * max_batch * max_k * 16;
+}
+
+int cmw_peer_alloc(int device, size_t bytes, void** dev_ptr, void* ipc_handle_out) {
+    CMW_REQUIRE(dev_ptr != nullptr && ipc_handle_out != nullptr && bytes >= kXHeaderBytes, "cmw_peer_alloc: bad arguments");
+    CMW_CUDA_OK(cudaSetDevice(device));
+    void* p = nullptr;
+    CMW_CUDA_OK(cudaMalloc(&p, bytes));
+    CMW_CUDA_OK(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("cmw_peer_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return -2;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    CMW_CUDA_OK(cudaDeviceSynchronize());
+    *dev_ptr = p;
+    return 0;
+}
+
+int cmw_peer_open(int device, const void* ipc_handle, void** dev_ptr) {
+    CMW_REQUIRE(dev_ptr != nullptr && ipc_handle != nullptr, "cmw_peer_open: bad arguments");
+    CMW_CUDA_OK(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    void* p = nullptr;
+    CMW_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr = p;
+    return 0;
+}
+
+int cmw_peer_close(void* dev_ptr) {
+    if (dev_ptr) CMW_CUDA_OK(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
+int cmw_peer_free(void* dev_ptr) {
+    if (dev_ptr) CMW_CUDA_OK(cudaFree(dev_ptr));
+    return 0;
+}
+
+int cmw_exchange_merge(void* const* peer_bufs_host, int G, int rank, int max_batch, int max_k, int B, int k,
+                       int k_out, uint32_t epoch, const double* scores64_local_dev, const int64_t* ids_local_dev,
+                       float* out_scores_dev, int64_t* out_ids_dev, double* out_scores64_dev, void* stream_v) {
+    CMW_REQUIRE(peer_bufs_host && scores64_local_dev && ids_local_dev && out_scores_dev && out_ids_dev,
+                "cmw_exchange_merge: NULL argument");
+    CMW_REQUIRE(G >= 1 && G <= kXMaxRanks && rank >= 0 && rank < G, "cmw_exchange_merge: bad rank/world");
+    CMW_REQUIRE(B >= 1 && B <= max_batch && k >= 1 && k <= max_k && k_out >= 1, "cmw_exchange_merge: bad sizes");
+    CMW_REQUIRE(epoch != 0, "cmw_exchange_merge: epoch must be non-zero");
+    const int n = G * k;
+    CMW_REQUIRE(n <= 8192, "cmw_exchange_merge: G*k = %d exceeds 8192", n);
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    XPeers peers;
+    for (int g = 0; g < G; ++g) {
+        CMW_REQUIRE(peer_bufs_host[g] != nullptr, "cmw_exchange_merge: peer buffer %d is NULL", g);
+        peers.buf[g] = reinterpret_cast<uint8_t*>(peer_bufs_host[g]);
+    }
+    const size_t slot_elems = (size_t)max_batch * max_k;
+    const size_t parity_bytes = (size_t)G * slot_elems * 16;
+    const int parity = (int)(epoch & 1u);
+    const size_t total = (size_t)B * k;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 296) blocks = 296;
+    exchange_send_kernel<<<blocks, 256, 0, stream>>>(peers, G, rank, B, k, slot_elems, parity_bytes, parity, epoch,
+                                                     scores64_local_dev, ids_local_dev);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    const size_t smem = (size_t)next_pow2_host(n < 2 ? 2 : n) * 16;
+    static SmemAttrCache smem_set;
+    if (smem > 48 * 1024 && smem_set.needs(smem)) {
+        CMW_CUDA_OK(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set.done(smem);
+    }
+    exchange_merge_kernel<<<B, 256, smem, stream>>>(peers.buf[rank], G, B, k, k_out, slot_elems, parity_bytes, parity,
+                                                    epoch, out_scores_dev, out_ids_dev, out_scores64_dev);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -250,11 +250,11 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     int rc = encode_2d(&tmap_b, a.q_bf16, a.bpad, s->dim, p.nt);
     if (rc) return rc;
     const size_t smem = (size_t)nst * p.stage_bytes + tail + 1024;  // + slack for 1024-byte alignment
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    static SmemAttrCache smem_set;
+    if (smem_set.needs(smem)) {
         CMW_CUDA_OK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-        smem_set = smem;
+        smem_set.done(smem);
     }
     const int n_items = p.n_tiles * p.n_groups;
     const int grid = n_items < s->sm_count ? n_items : s->sm_count;

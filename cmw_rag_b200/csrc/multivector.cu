@@ -280,11 +280,11 @@ extern "C" int cmw_multivector(const int32_t* kb_gid_dev, int64_t kb_rows, int64
     p.grp_n = grp_n;
     const int n2 = next_pow2_host(n < 2 ? 2 : n);
     const size_t smem = (size_t)n2 * (3 * 8 + 5 * 4 + 5 * 4) + 32 * sizeof(int) + 16;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
+    static SmemAttrCache smem_set;
+    if (smem > 48 * 1024 && smem_set.needs(smem)) {
         CMW_CUDA_OK(cudaFuncSetAttribute(multivector_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+        smem_set.done(smem);
     }
     multivector_kernel<<<Q, kMvThreads, smem, (cudaStream_t)stream>>>(p);
     CMW_LAUNCHED();

@@ -467,11 +467,11 @@ extern "C" int cmw_merge_topk(const double* scores_dev, const int64_t* ids_dev, 
     const int n = G * k_in;
     CMW_REQUIRE(n <= 8192, "cmw_merge_topk: G*k_in = %d exceeds 8192", n);
     const size_t smem = (size_t)next_pow2_host(n) * 16;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
+    static SmemAttrCache smem_set;
+    if (smem > 48 * 1024 && smem_set.needs(smem)) {
         CMW_CUDA_OK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-        smem_set = smem;
+        smem_set.done(smem);
     }
     merge_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(scores_dev, ids_dev, G, B, k_in, k_out,
                                                         out_scores_dev, out_ids_dev, out_scores64_dev);

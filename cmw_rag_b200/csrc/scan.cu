@@ -245,10 +245,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
 template <typename ELT, int NQ, int CHUNKS>
 static int launch_one(const ScanParams& p, int grid, size_t smem, cudaStream_t stream) {
     auto kern = scan_kernel<ELT, NQ, CHUNKS>;
-    static size_t smem_set = 0;  // per instantiation; one device per process
-    if (smem > smem_set) {
+    static SmemAttrCache smem_set;  // per instantiation
+    if (smem_set.needs(smem)) {
         CMW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+        smem_set.done(smem);
     }
     kern<<<grid, kScanThreads, smem, stream>>>(p);
     CMW_LAUNCHED();

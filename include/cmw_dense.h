@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CMW_ABI_VERSION 2
+#define CMW_ABI_VERSION 3
 
 /* metric -- rag_engine/storage/vector_store.py:48-51 fixes the collection to cosine
  * ({"hnsw:space": "cosine"}); inner product is the north star's second metric. */
@@ -132,6 +132,24 @@ int cmw_multivector(const int32_t* kb_gid_dev, int64_t kb_rows, int64_t id_offse
 int cmw_merge_topk(const double* scores_dev, const int64_t* ids_dev, int G, int B, int k_in,
                    int k_out, float* out_scores_dev, int64_t* out_ids_dev,
                    double* out_scores64_dev, void* stream);
+
+/* ---- fused exchange + merge over NVLink peer memory (alternative to all-gather + cmw_merge_topk).
+ * Every rank allocates one peer buffer (cmw_peer_alloc: cudaMalloc + cudaIpc handle, zero-initialised,
+ * cmw_peer_buffer_bytes bytes), exchanges the 64-byte handles out of band (torch.distributed, MPI, a
+ * file...), opens the others (cmw_peer_open) and passes the G device pointers (its own at index `rank`)
+ * to cmw_exchange_merge.  That call launches, stream-ordered and without host synchronisation: a send
+ * kernel that stores this rank's [B,k] (f64 score, i64 id) candidates into every peer's buffer over
+ * NVLink and publishes an epoch flag, and a merge kernel that waits for the G flags and reduces
+ * G*k -> k_out per query by (score desc, id asc).  `epoch` must be non-zero and increase by 1 per call
+ * on every rank (buffers are double-buffered by its parity); B <= max_batch, k <= max_k as allocated. */
+size_t cmw_peer_buffer_bytes(int G, int max_batch, int max_k);
+int cmw_peer_alloc(int device, size_t bytes, void** dev_ptr, void* ipc_handle_out /* 64 bytes */);
+int cmw_peer_open(int device, const void* ipc_handle /* 64 bytes */, void** dev_ptr);
+int cmw_peer_close(void* dev_ptr);
+int cmw_peer_free(void* dev_ptr);
+int cmw_exchange_merge(void* const* peer_bufs_host, int G, int rank, int max_batch, int max_k, int B, int k,
+                       int k_out, uint32_t epoch, const double* scores64_local_dev, const int64_t* ids_local_dev,
+                       float* out_scores_dev, int64_t* out_ids_dev, double* out_scores64_dev, void* stream);
 
 /* ---- instrumentation ---- */
 /* number of kernels this library has launched since load (all stores, all streams) */

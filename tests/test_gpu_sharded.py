@@ -18,7 +18,7 @@ import numpy as np, torch, torch.distributed as dist
 import synth
 from oracle.cport import exact_topk_c
 from cmw_rag_b200 import DenseStore
-from cmw_rag_b200.sharded import ShardedSearcher, shard_bounds
+from cmw_rag_b200.sharded import PeerExchange, ShardedSearcher, shard_bounds
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 dev = torch.device(f"cuda:{{local}}"); torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
@@ -41,6 +41,17 @@ for mode in ("f32", "bf16"):
     else:
         rec = np.mean([len(set(mi[b].tolist()) & set(ref_ids[b])) / k for b in range(37)])
         assert rec >= 0.95, rec
+# the fused NVLink peer-memory exchange must give the same answer as all-gather + merge, call after call
+ex = PeerExchange(device=local, max_batch=64, max_k=64)
+fused = ShardedSearcher(st, exchange=ex)
+for it in range(5):
+    qi = torch.from_numpy(np.roll(q, it, axis=0).copy()).to(dev)
+    a_s, a_i, _ = s.search(qi, k, mode="f32")
+    b_s, b_i, _ = fused.search(qi, k, mode="f32")
+    torch.cuda.synchronize()
+    assert torch.equal(a_i, b_i) and torch.equal(a_s, b_s), (rank, it)
+assert (b_i.cpu().numpy() == np.roll(ref_ids, 4, axis=0)).all()
+ex.close()
 dist.barrier(); dist.destroy_process_group()
 print("sharded ok", rank, world)
 """
