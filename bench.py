@@ -52,7 +52,9 @@ def parse_args():
                     help="--shard rows: NCCL all-gather + merge kernel, or the fused NVLink peer-memory exchange")
     ap.add_argument("--no-f32", action="store_true", help="bf16 tiles only (rows-sharded 200M config)")
     ap.add_argument("--cpu-queries", type=int, default=16, help="queries in the bounded CPU sample")
-    ap.add_argument("--hnsw-rows", type=int, default=50_000, help="rows in the CPU HNSW index (bounded sample)")
+    ap.add_argument("--hnsw-rows", type=int, default=0,
+                    help="rows in the CPU HNSW index (bounded sample); 0 = 50k for the cpu_baseline leg of the "
+                         "GPU arm (~10 s build), 250k for --impl reference (~1 min build on 16 cores)")
     ap.add_argument("--hnsw-queries", type=int, default=512)
     ap.add_argument("--skip-cpu-exact", action="store_true")
     ap.add_argument("--skip-b1", action="store_true")
@@ -186,7 +188,7 @@ def run_reference(args):
     import synth
     from oracle.hnsw import HnswIndex, num_threads
 
-    index_rows = min(args.rows, args.hnsw_rows)
+    index_rows = min(args.rows, args.hnsw_rows or 250_000)
     corpus = host_corpus(index_rows, args.dim)
     nq = max(16, args.hnsw_queries)
     q, _ = synth.make_queries(corpus, nq, seed=7, tie_probe=False)
@@ -476,7 +478,7 @@ def run_ours(args):
         import synth
 
         # an equally shaped, equally seeded corpus on the host (same workload, bounded sample)
-        index_rows = min(args.rows, args.hnsw_rows)
+        index_rows = min(args.rows, args.hnsw_rows or 50_000)
         corpus = host_corpus(args.rows if not args.skip_cpu_exact else index_rows, args.dim)
         cq, _ = synth.make_queries(corpus[:index_rows], max(16, args.hnsw_queries), seed=7, tie_probe=False)
         qps, recall, build_s, threads = cpu_hnsw_sample(corpus, cq, k, index_rows)

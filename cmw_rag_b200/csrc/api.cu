@@ -370,6 +370,7 @@ int cmw_search_host(cmw_store* h, const float* queries_host, int batch, int k, i
     CMW_REQUIRE(batch > 0 && queries_host && out_scores_host && out_ids_host,
                 "cmw_search_host: bad arguments");
     CMW_REQUIRE(k >= 1 && k <= kMaxKPrime, "cmw_search_host: k must be in [1, %d], got %d", kMaxKPrime, k);
+    std::lock_guard<std::mutex> host_lock(s->host_mu);
     CMW_CUDA_OK(cudaSetDevice(s->device));
     cudaStream_t stream;
     int rc = get_stream(s, &stream);
@@ -446,14 +447,16 @@ int cmw_search_host(cmw_store* h, const float* queries_host, int batch, int k, i
     // A query whose certificate failed (bf16 filter too coarse near the k-th score) or whose pool
     // overflowed (adversarial row order) is repeated through the fp32 scan filter -- certificate
     // bound three orders of magnitude tighter -- on the overflow-proof slab schedule.
+    // bf16 mode can only be flagged by a pool overflow: repeated as is on the overflow-proof schedule.
     const bool was_safe_scan = (mode & CMW_SLABS_SAFE) && !use_gemm(s, batch, mode);
-    if (!redo.empty() && (mode & 0xff) == CMW_MODE_F32_EXACT && !was_safe_scan) {
+    const bool exact = (mode & 0xff) == CMW_MODE_F32_EXACT;
+    if (!redo.empty() && ((exact && !was_safe_scan) || (!exact && !(mode & CMW_SLABS_SAFE)))) {
         std::vector<float> q2((size_t)redo.size() * s->dim);
         for (size_t i = 0; i < redo.size(); ++i)
             memcpy(q2.data() + i * s->dim, queries_host + (size_t)redo[i] * s->dim,
                    (size_t)s->dim * sizeof(float));
-        if ((rc = run(q2.data(), (int)redo.size(), CMW_MODE_F32_EXACT | CMW_ALGO_SCAN | CMW_SLABS_SAFE, false)))
-            return rc;
+        const int redo_mode = exact ? (CMW_MODE_F32_EXACT | CMW_ALGO_SCAN | CMW_SLABS_SAFE) : (mode | CMW_SLABS_SAFE);
+        if ((rc = run(q2.data(), (int)redo.size(), redo_mode, false))) return rc;
         for (size_t i = 0; i < redo.size(); ++i) {
             const int b = redo[i];
             memcpy(out_scores_host + (size_t)b * k, sc + i * k, (size_t)k * sizeof(float));

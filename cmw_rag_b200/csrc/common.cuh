@@ -11,6 +11,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 
 #include "../../include/cmw_dense.h"
@@ -93,6 +94,7 @@ struct Store {
     // TMA descriptor of the bf16 tiles (K2), encoded at create time
     alignas(64) CUtensorMap tmap_bf16;
     bool tmap_ok = false;
+    std::mutex host_mu;  // serialises the *_host entry points, which share the staging resources above
 };
 
 // options (cmw_set_option)

@@ -329,6 +329,7 @@ int cmw_store_append_host_f32(cmw_store* h, const float* rows_host, const int32_
     CMW_REQUIRE(s->rows + n <= s->capacity,
                 "cmw_store_append_host_f32: %lld rows + %lld exceed the capacity %lld",
                 (long long)s->rows, (long long)n, (long long)s->capacity);
+    std::lock_guard<std::mutex> host_lock(s->host_mu);
     CMW_CUDA_OK(cudaSetDevice(s->device));
     int rc = ensure_stream(s);
     if (rc) return rc;
@@ -384,6 +385,7 @@ int cmw_store_tombstone_host(cmw_store* h, const int64_t* rows_host, int64_t n) 
     Store* s = reinterpret_cast<Store*>(h);
     if (n == 0) return 0;
     CMW_REQUIRE(n > 0 && rows_host != nullptr, "cmw_store_tombstone_host: bad arguments");
+    std::lock_guard<std::mutex> host_lock(s->host_mu);
     CMW_CUDA_OK(cudaSetDevice(s->device));
     int rc = ensure_stream(s);
     if (rc) return rc;
@@ -406,6 +408,7 @@ int cmw_store_read_rows_f32(cmw_store* h, int64_t row0, int64_t n, float* rows_h
     if (n == 0) return 0;
     CMW_REQUIRE(row0 >= 0 && n > 0 && row0 + n <= s->rows, "cmw_store_read_rows_f32: rows [%lld, %lld) out of range",
                 (long long)row0, (long long)(row0 + n));
+    std::lock_guard<std::mutex> host_lock(s->host_mu);
     CMW_CUDA_OK(cudaSetDevice(s->device));
     cudaStream_t st;
     int rc = get_stream(s, &st);

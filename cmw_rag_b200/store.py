@@ -282,12 +282,13 @@ class B200Store:
 
     def _docs_for(self, ids_row: np.ndarray) -> list[RetrievedDoc]:
         out = []
-        for gid in ids_row.tolist():
-            if gid < 0:
-                continue
-            r = gid - self._id_offset
-            if 0 <= r < len(self._ids) and self._alive[r]:
-                out.append(RetrievedDoc(page_content=self._docs[r], metadata=dict(self._metas[r] or {})))
+        with self._lock:
+            for gid in ids_row.tolist():
+                if gid < 0:
+                    continue
+                r = gid - self._id_offset
+                if 0 <= r < len(self._ids) and self._alive[r]:
+                    out.append(RetrievedDoc(page_content=self._docs[r], metadata=dict(self._metas[r] or {})))
         return out
 
     def query(self, query_embeddings, n_results: int = 10, include=("documents", "metadatas", "distances")):

@@ -13,6 +13,10 @@
  *   - return value: 0 = ok, negative = error; the message is in cmw_last_error() (thread-local).
  *   - row ids are int64 = row number in append order + the store's id offset (row shards).
  *   - unused output slots (k larger than the number of live rows): id = -1, score = -inf.
+ *   - threading: the *_host entry points of one store are serialised internally (they share its pinned
+ *     staging buffers and stream); device-pointer entry points may run concurrently on different
+ *     streams when each call has its own workspace; append / tombstone are exclusive with searches
+ *     of the same store.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
  */
 #ifndef CMW_DENSE_H_
