@@ -70,6 +70,8 @@ static int pick_kprime(int k, int mode, bool gemm) {
         kp = (int)g_opt.kprime;
     } else if ((mode & 0xff) == CMW_MODE_BF16) {
         kp = k;
+    } else if (gemm && g_opt.strict_certificate != 0) {
+        kp = (4 * k > 512) ? 4 * k : 512;  // rigorous bound: ~3.3x the candidates at 1M iid rows
     } else if (gemm) {
         kp = (k + 64 > 2 * k) ? k + 64 : 2 * k;  // bf16 filter: room for the certificate
     } else {
@@ -353,7 +355,7 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
 
     PhaseTimer tfin(2, stream);
     if (base_mode == CMW_MODE_F32_EXACT) {
-        const double eps = gemm ? g_opt.bf16_eps : g_opt.f32_eps;
+        const double eps = gemm ? (g_opt.strict_certificate != 0 ? 4.1e-3 : g_opt.bf16_eps) : g_opt.f32_eps;
         return launch_rescore_select(s, pool, batch, k, kprime, metric, queries_dev, qn64, eps, exact,
                                      out_scores_dev, out_ids_dev, out_scores64_dev, out_flags_dev,
                                      stream);

@@ -110,6 +110,9 @@ struct Options {
     double gemm_enabled = 1;
     double gemm_2cta = 1;            // CTA-pair (cta_group::2) K2 kernel for large batches
     double gemm_2cta_min_batch = 256;
+    // 1 = rigorous certificate behind the bf16 filter: eps = 2u(1+u) + fp32 accumulation slack = 4.1e-3
+    // (Cauchy-Schwarz over unit vectors, u = 2^-9) and K' = max(512, 4k); ~17 % slower at B=4096
+    double strict_certificate = 0;
     double slab_growth = 0;   // 0 = automatic ((cap - K') / (3 K'), at most 8); else the fixed growth factor
 };
 extern Options g_opt;

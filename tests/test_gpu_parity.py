@@ -518,3 +518,17 @@ def test_batch_larger_than_4096_and_store_growth(torch_cuda):
     ref_ids, ref_sc, _ = exact_topk_c(c, q, 10)
     sc, ids, fl = store.search(q, 10)
     _check_exact(ids, sc, ref_ids, ref_sc)
+
+
+def test_strict_certificate_mode(cfg1):
+    """cmw_set_option("strict_certificate", 1): the rigorous (Cauchy-Schwarz) bound behind the bf16
+    filter -- same ids, every query certified without the fallback at this size."""
+    from cmw_rag_b200 import _native as N
+
+    N.set_option("strict_certificate", 1)
+    try:
+        sc, ids, fl = cfg1["store"].search_host(cfg1["q"], 20, mode="f32", algo="gemm")
+    finally:
+        N.set_option("strict_certificate", 0)
+    _check_exact(ids, sc, cfg1["ref_ids"], cfg1["ref_sc"])
+    assert (fl == 0).all()
