@@ -21,6 +21,7 @@ ALGO_AUTO = 0 << 8
 ALGO_SCAN = 1 << 8
 ALGO_GEMM = 2 << 8
 SLABS_SAFE = 1 << 16
+KPRIME_MAX = 1 << 17
 STORE_F32 = 1
 STORE_BF16 = 2
 FLAG_UNCERTIFIED = 1

@@ -66,7 +66,9 @@ static bool use_gemm(const Store* s, int batch, int mode) {
 
 static int pick_kprime(int k, int mode, bool gemm) {
     int kp;
-    if (g_opt.kprime > 0) {
+    if (mode & CMW_KPRIME_MAX) {
+        kp = kMaxKPrime;
+    } else if (g_opt.kprime > 0) {
         kp = (int)g_opt.kprime;
     } else if ((mode & 0xff) == CMW_MODE_BF16) {
         kp = k;
@@ -446,25 +448,35 @@ int cmw_search_host(cmw_store* h, const float* queries_host, int batch, int k, i
         if (out_flags_host) out_flags_host[b] = fl[b];
         if (fl[b] & CMW_FLAG_UNCERTIFIED) redo.push_back(b);
     }
-    // A query whose certificate failed (bf16 filter too coarse near the k-th score) or whose pool
-    // overflowed (adversarial row order) is repeated through the fp32 scan filter -- certificate
-    // bound three orders of magnitude tighter -- on the overflow-proof slab schedule.
-    // bf16 mode can only be flagged by a pool overflow: repeated as is on the overflow-proof schedule.
-    const bool was_safe_scan = (mode & CMW_SLABS_SAFE) && !use_gemm(s, batch, mode);
+    // Repair chain for flagged queries (a failed certificate: many scores within eps of the k-th; or a
+    // pool overflow: adversarial row order).  Each stage re-runs only the queries still flagged, batched:
+    //   1. the same filter with the largest K' (1024) on the overflow-proof slab schedule -- a handful
+    //      of milliseconds whatever the number of queries when the filter is K2;
+    //   2. (exact mode) the fp32 scan filter, certificate bound three orders of magnitude tighter, also
+    //      with the largest K' and the overflow-proof schedule.
+    // bf16 mode can only be flagged by an overflow: stage 1 settles it.
     const bool exact = (mode & 0xff) == CMW_MODE_F32_EXACT;
-    if (!redo.empty() && ((exact && !was_safe_scan) || (!exact && !(mode & CMW_SLABS_SAFE)))) {
+    const bool first_was_gemm = use_gemm(s, batch, mode);
+    int stages[2];
+    int nstage = 0;
+    if (!((mode & CMW_SLABS_SAFE) && (mode & CMW_KPRIME_MAX))) stages[nstage++] = mode | CMW_SLABS_SAFE | CMW_KPRIME_MAX;
+    if (exact && first_was_gemm)
+        stages[nstage++] = CMW_MODE_F32_EXACT | CMW_ALGO_SCAN | CMW_SLABS_SAFE | CMW_KPRIME_MAX;
+    for (int st = 0; st < nstage && !redo.empty(); ++st) {
         std::vector<float> q2((size_t)redo.size() * s->dim);
         for (size_t i = 0; i < redo.size(); ++i)
             memcpy(q2.data() + i * s->dim, queries_host + (size_t)redo[i] * s->dim,
                    (size_t)s->dim * sizeof(float));
-        const int redo_mode = exact ? (CMW_MODE_F32_EXACT | CMW_ALGO_SCAN | CMW_SLABS_SAFE) : (mode | CMW_SLABS_SAFE);
-        if ((rc = run(q2.data(), (int)redo.size(), redo_mode, false))) return rc;
+        if ((rc = run(q2.data(), (int)redo.size(), stages[st], false))) return rc;
+        std::vector<int> still;
         for (size_t i = 0; i < redo.size(); ++i) {
             const int b = redo[i];
             memcpy(out_scores_host + (size_t)b * k, sc + i * k, (size_t)k * sizeof(float));
             memcpy(out_ids_host + (size_t)b * k, id + i * k, (size_t)k * sizeof(int64_t));
             if (out_flags_host) out_flags_host[b] = fl[i];
+            if (fl[i] & CMW_FLAG_UNCERTIFIED) still.push_back(b);
         }
+        redo.swap(still);
     }
     return 0;
 }

@@ -47,6 +47,8 @@ extern "C" {
 /* slab schedule override, OR-ed into `mode`: fixed slabs small enough that the candidate pool can
  * never overflow, whatever the row order (slower; cmw_search_host falls back to it by itself) */
 #define CMW_SLABS_SAFE (1 << 16)
+/* keep the largest candidate set (K' = 1024) per query: the most head-room for the certificate */
+#define CMW_KPRIME_MAX (1 << 17)
 
 /* store flags */
 #define CMW_STORE_F32 1u  /* keep row-major fp32 tiles (needed by CMW_MODE_F32_EXACT) */

@@ -532,3 +532,32 @@ def test_strict_certificate_mode(cfg1):
         N.set_option("strict_certificate", 0)
     _check_exact(ids, sc, cfg1["ref_ids"], cfg1["ref_sc"])
     assert (fl == 0).all()
+
+
+def test_repair_chain_on_near_duplicates(torch_cuda):
+    """600 near-duplicates of the best match (scores within 1e-6..1e-4 of each other): the bf16 filter
+    cannot separate them, so the certificate behind K2 must fail on the device API -- and the host API's
+    repair chain (stage 1: K' = 1024 on the overflow-proof schedule) must still return the oracle's ids."""
+    torch = torch_cuda
+    from cmw_rag_b200 import DenseStore
+
+    n, d, k = 20000, 256, 20
+    c = synth.make_corpus(n, d, seed=31, ties=False)
+    rng = np.random.default_rng(2)
+    base = c[7].copy()
+    noise = rng.standard_normal((600, d)).astype(np.float32)
+    c[1000:1600] = base[None, :] + 2e-4 * noise / np.sqrt(d)
+    c[1000:1600] /= np.linalg.norm(c[1000:1600].astype(np.float64), axis=1, keepdims=True).astype(np.float32)
+    q = np.stack([base + 0.05 * rng.standard_normal(d).astype(np.float32) / np.sqrt(d) for _ in range(8)])
+    q2, _ = synth.make_queries(c, 8, seed=4, tie_probe=False)
+    q = np.concatenate([q, q2]).astype(np.float32)
+    st = DenseStore(d, n)
+    st.append(c)
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, k)
+    _, _, fl_dev = st.search(torch.from_numpy(q).cuda(), k, mode="f32", algo="gemm")
+    torch.cuda.synchronize()
+    assert int(fl_dev[:8].sum()) >= 1, "the near-duplicate queries should not be certifiable at K' = 96"
+    sc, ids, fl = st.search_host(q, k, mode="f32", algo="gemm")
+    _check_exact(ids, sc, ref_ids, ref_sc)
+    assert (fl == 0).all()
+    st.close()
