@@ -24,7 +24,7 @@ namespace cmw {
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-    size_t qn64, q_f32, q_bf16, pool_scores, pool_ids, pool_cnt, pool_thr, pool_ovf, exact, total;
+    size_t qn64, q4, q_f32, q_bf16, pool_scores, pool_ids, pool_cnt, pool_thr, pool_ovf, exact, total;
     int bpad;
 };
 
@@ -44,6 +44,7 @@ static WsLayout ws_layout(int dim, int batch, int kprime) {
     };
     w.bpad = pad_batch(batch);
     w.qn64 = take((size_t)batch * sizeof(double));
+    w.q4 = take((size_t)batch * sizeof(double));
     w.q_f32 = take((size_t)batch * dim * sizeof(float));
     w.q_bf16 = take((size_t)w.bpad * dim * sizeof(__nv_bfloat16));
     w.pool_scores = take((size_t)batch * kPoolCap * sizeof(float));
@@ -256,6 +257,7 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
     CMW_REQUIRE((reinterpret_cast<uintptr_t>(ws_dev) & 255) == 0, "cmw_search: workspace must be 256-byte aligned");
     uint8_t* ws = reinterpret_cast<uint8_t*>(ws_dev);
     double* qn64 = reinterpret_cast<double*>(ws + w.qn64);
+    double* q4 = reinterpret_cast<double*>(ws + w.q4);
     float* q_f32 = reinterpret_cast<float*>(ws + w.q_f32);
     __nv_bfloat16* q_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + w.q_bf16);
     Pool pool;
@@ -271,7 +273,7 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
     const int64_t slab0 = rows < kDenseSlabRows ? rows : kDenseSlabRows;
     {
         PhaseTimer t(3, stream);
-        if ((rc = launch_prep_queries(queries_dev, batch, w.bpad, s->dim, metric, qn64, q_f32,
+        if ((rc = launch_prep_queries(queries_dev, batch, w.bpad, s->dim, metric, qn64, q4, q_f32,
                                       gemm ? q_bf16 : nullptr, pool, (int)slab0, stream)))
             return rc;
     }
@@ -357,8 +359,19 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
 
     PhaseTimer tfin(2, stream);
     if (base_mode == CMW_MODE_F32_EXACT) {
-        const double eps = gemm ? (g_opt.strict_certificate != 0 ? 4.1e-3 : g_opt.bf16_eps) : g_opt.f32_eps;
-        return launch_rescore_select(s, pool, batch, k, kprime, metric, queries_dev, qn64, eps, exact,
+        CertParams cert;
+        cert.eps_fixed = g_opt.f32_eps;
+        cert.sigmas = 0.0;
+        if (gemm) {
+            if (g_opt.strict_certificate != 0) cert.eps_fixed = 4.1e-3;
+            else if (g_opt.bf16_eps > 0) cert.eps_fixed = g_opt.bf16_eps;
+            else cert.sigmas = g_opt.bf16_sigmas;
+        }
+        cert.q4 = q4;
+        cert.qn64 = qn64;
+        cert.norms = s->maxnorm_bits;
+        cert.metric = metric;
+        return launch_rescore_select(s, pool, batch, k, kprime, metric, queries_dev, cert, exact,
                                      out_scores_dev, out_ids_dev, out_scores64_dev, out_flags_dev,
                                      stream);
     }

@@ -82,7 +82,7 @@ struct Store {
     float* live = nullptr;           // [cap4] 1.0   (NaN when tombstoned)
     double* norm64 = nullptr;        // [capacity] |c| in fp64
     int32_t* kb_gid = nullptr;       // [capacity]
-    uint32_t* maxnorm_bits = nullptr;  // device scalar: max |c| as float bits
+    uint32_t* maxnorm_bits = nullptr;  // device scalars: [0] max |c| as float bits, [1] max |c/|c||_4
     // host-API resources (cmw_search_host / *_host variants)
     cudaStream_t stream = nullptr;
     void* pinned = nullptr;
@@ -99,7 +99,14 @@ struct Store {
 
 // options (cmw_set_option)
 struct Options {
-    double bf16_eps = 5e-4;   // certificate bound on |bf16 filter score - exact score| (cosine units)
+    // Certificate bound on |bf16 filter score - exact score| (cosine units).  0 = automatic: the rounding
+    // errors of the two bf16 operands are independent with relative size <= u = 2^-9, so the error of a
+    // dot product has sigma <= u * sqrt(2/3) * |q|_4 * |c|_4 (Cauchy-Schwarz on the squared products);
+    // eps = bf16_sigmas * that bound with |c|_4 the maximum over the stored rows, capped by the rigorous
+    // 4.1e-3.  For dense 1536-d unit vectors this is ~6e-4; it grows as 1/sqrt(D) for smaller D and for
+    // concentrated (sparse-ish) vectors.  > 0 = fixed override.
+    double bf16_eps = 0;
+    double bf16_sigmas = 8;
     double f32_eps = 4e-6;    // same for the fp32 FMA filter
     double kprime = 0;        // 0 = automatic
     // Batches up to this use K1 (scan), larger ones K2 (GEMM).  0 = K2 for every batch size: even at
@@ -147,14 +154,24 @@ struct GemmArgs {
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 bool gemm_supported(const Store* s);
 
-int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64,
+int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64, double* q4,
                         float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count,
                         cudaStream_t stream);
+
+// how the certificate / rescoring cut bound is obtained (see Options::bf16_eps)
+struct CertParams {
+    double eps_fixed;       // used when sigmas == 0
+    double sigmas;          // > 0: statistical bf16 bound from q4 and the store's max row 4-norm
+    const double* q4;       // [B] |q/|q||_4
+    const double* qn64;     // [B] |q|
+    const uint32_t* norms;  // store scalars: [0] max |c| bits, [1] max 4-norm bits
+    int metric;
+};
 int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_t stream);
 // exact fp64 rescoring of the pool's first min(cnt, kprime) entries + final (score desc, id asc)
 // selection with the exactness certificate
 int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprime, int metric,
-                          const float* q_raw, const double* qn64, double eps, double* exact_ws,
+                          const float* q_raw, const CertParams& cert, double* exact_ws,
                           float* out_scores, int64_t* out_ids, double* out_scores64,
                           int32_t* out_flags, cudaStream_t stream);
 // bf16 mode: emit the pool's best k as they are
@@ -206,6 +223,16 @@ __device__ __forceinline__ uint64_t f64_orderable(double d) {
 }
 __device__ __forceinline__ double f64_from_orderable(uint64_t u) {
     return __longlong_as_double((long long)((u >> 63) ? (u & 0x7fffffffffffffffull) : ~u));
+}
+__device__ __forceinline__ double cert_eps(const CertParams& c, int b) {
+    double e = c.eps_fixed;
+    if (c.sigmas > 0.0) {
+        const double bound = c.sigmas * (1.0 / 512.0) * 0.816496580927726 * c.q4[b] *
+                             (double)__uint_as_float(c.norms[1]);
+        e = (bound < 4.1e-3 ? bound : 4.1e-3) + 2e-5;  // + fp32 accumulation slack of the tensor pipe
+    }
+    if (c.metric == CMW_METRIC_IP) e *= c.qn64[b] * (double)__uint_as_float(c.norms[0]);
+    return e;
 }
 // key whose ASCENDING order is (score descending, id ascending)
 __device__ __forceinline__ uint64_t desc_key(float score, uint32_t id) {

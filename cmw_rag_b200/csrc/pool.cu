@@ -13,7 +13,7 @@ namespace cmw {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, int metric,
-                    double* __restrict__ qn64, float* __restrict__ q_f32,
+                    double* __restrict__ qn64, double* __restrict__ q4, float* __restrict__ q_f32,
                     __nv_bfloat16* __restrict__ q_bf16, Pool pool, int dense_count) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -48,6 +48,19 @@ prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, i
     const double nrm = sqrt(acc);
     const double scale = (metric == CMW_METRIC_COSINE) ? (nrm > 0.0 ? 1.0 / nrm : 0.0) : 1.0;
     if (lane == 0) qn64[b] = nrm;
+    {
+        // |q/|q||_4 for the certificate bound
+        const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+        double s4 = 0.0;
+        for (int c = lane; c < nvec; c += 32) {
+            float4 v = __ldg(in + c);
+            const double x = (double)v.x * inv, y = (double)v.y * inv, z = (double)v.z * inv, w = (double)v.w * inv;
+            s4 += x * x * x * x + y * y * y * y + z * z * z * z + w * w * w * w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s4 += __shfl_xor_sync(0xffffffffu, s4, o);
+        if (lane == 0) q4[b] = sqrt(sqrt(s4));
+    }
     float4* of = reinterpret_cast<float4*>(q_f32 + (size_t)b * dim);
     for (int c = lane; c < nvec; c += 32) {
         float4 v = __ldg(in + c);
@@ -62,12 +75,12 @@ prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, i
     }
 }
 
-int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64,
+int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64, double* q4,
                         float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count,
                         cudaStream_t stream) {
     const int wpb = 8;
     prep_queries_kernel<<<(bpad + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, batch, bpad, dim, metric,
-                                                                        qn64, q_f32, q_bf16, pool, dense_count);
+                                                                        qn64, q4, q_f32, q_bf16, pool, dense_count);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
@@ -229,8 +242,8 @@ int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_
 __global__ void __launch_bounds__(256)
 rescore_kernel(const float* __restrict__ f32, const double* __restrict__ norm64,
                const float* __restrict__ live, int dim, Pool pool, int kprime, int metric,
-               const float* __restrict__ q_raw, const double* __restrict__ qn64,
-               const uint32_t* __restrict__ maxnorm_bits, int k, double eps, double* __restrict__ exact) {
+               const float* __restrict__ q_raw, const CertParams cert, int k, double* __restrict__ exact) {
+    const double* __restrict__ qn64 = cert.qn64;
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
@@ -239,11 +252,7 @@ rescore_kernel(const float* __restrict__ f32, const double* __restrict__ norm64,
     // is below a_k - 2*eps has an exact score below a_k - eps <= (k-th exact score): it cannot be in the
     // exact top-k, so it is not rescored (its slot gets -inf and sorts last).
     double cut = -INFINITY;
-    if (n > k) {
-        double e = eps;
-        if (metric == CMW_METRIC_IP) e *= qn64[b] * (double)__uint_as_float(*maxnorm_bits);
-        cut = (double)pool.scores[(size_t)b * kPoolCap + (k - 1)] - 2.0 * e;
-    }
+    if (n > k) cut = (double)pool.scores[(size_t)b * kPoolCap + (k - 1)] - 2.0 * cert_eps(cert, b);
     const float4* qv = reinterpret_cast<const float4*>(q_raw + (size_t)b * dim);
     const int nvec = dim >> 2;
     // gridDim.x blocks share a query (many for small batches, one for large ones); a warp walks its
@@ -301,8 +310,7 @@ rescore_kernel(const float* __restrict__ f32, const double* __restrict__ norm64,
 
 // K3b: per query, sort the rescored candidates by (exact desc, id asc), emit k, certify.
 __global__ void __launch_bounds__(256)
-select_kernel(Pool pool, int k, int kprime, int metric, const double* __restrict__ exact,
-              const double* __restrict__ qn64, const uint32_t* __restrict__ maxnorm_bits, double eps,
+select_kernel(Pool pool, int k, int kprime, const double* __restrict__ exact, const CertParams cert,
               int64_t id_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
               double* __restrict__ out_scores64, int32_t* __restrict__ out_flags) {
     extern __shared__ __align__(16) uint8_t sel_smem[];
@@ -340,9 +348,7 @@ select_kernel(Pool pool, int k, int kprime, int metric, const double* __restrict
         if (n >= kprime) {
             // rows outside the pool have filter score <= t, hence exact score <= t + eps
             const double t = (double)pool.thr[b];
-            double e = eps;
-            if (metric == CMW_METRIC_IP)
-                e *= qn64[b] * (double)__uint_as_float(*maxnorm_bits);
+            const double e = cert_eps(cert, b);
             const int kk = (k <= n) ? k : n;
             double kth = -INFINITY;
             if (kk >= 1 && hi[kk - 1] < neg_inf_key) {
@@ -355,7 +361,7 @@ select_kernel(Pool pool, int k, int kprime, int metric, const double* __restrict
 }
 
 int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprime, int metric,
-                          const float* q_raw, const double* qn64, double eps, double* exact_ws,
+                          const float* q_raw, const CertParams& cert, double* exact_ws,
                           float* out_scores, int64_t* out_ids, double* out_scores64,
                           int32_t* out_flags, cudaStream_t stream) {
     CMW_REQUIRE(s->f32 != nullptr, "CMW_MODE_F32_EXACT needs a store created with CMW_STORE_F32");
@@ -367,12 +373,11 @@ int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprim
     if (per_query < 1) per_query = 1;
     dim3 grid(per_query, batch);
     rescore_kernel<<<grid, wpb * 32, 0, stream>>>(s->f32, s->norm64, s->live, s->dim, pool, kprime,
-                                                 metric, q_raw, qn64, s->maxnorm_bits, k, eps, exact_ws);
+                                                 metric, q_raw, cert, k, exact_ws);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     const size_t smem = (size_t)next_pow2_host(kprime) * 16;
-    select_kernel<<<batch, 256, smem, stream>>>(pool, k, kprime, metric, exact_ws, qn64,
-                                               s->maxnorm_bits, eps, s->id_offset, out_scores,
+    select_kernel<<<batch, 256, smem, stream>>>(pool, k, kprime, exact_ws, cert, s->id_offset, out_scores,
                                                out_ids, out_scores64, out_flags);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());

@@ -74,7 +74,17 @@ ingest_kernel(const float* __restrict__ src, const int32_t* __restrict__ gid_src
                     __floats2bfloat162_rn((float)((double)v.z * inv), (float)((double)v.w * inv));
             }
         }
+        // 4-norm of the normalised row (certificate bound of the bf16 filter, Options::bf16_eps)
+        double s4 = 0.0;
+        for (int c = lane; c < nvec; c += 32) {
+            float4 v = __ldg(in + c);
+            const double x = (double)v.x * inv, y = (double)v.y * inv, z = (double)v.z * inv, w = (double)v.w * inv;
+            s4 += x * x * x * x + y * y * y * y + z * z * z * z + w * w * w * w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s4 += __shfl_xor_sync(0xffffffffu, s4, o);
         if (lane == 0) {
+            atomicMax(maxnorm_bits + 1, __float_as_uint((float)sqrt(sqrt(s4))) + 1u);
             inv_norm[dst] = (float)inv;
             norm[dst] = (float)nrm;
             live[dst] = 1.0f;
@@ -160,6 +170,7 @@ int cmw_set_option(const char* name, double value) {
     if (!name) return -1;
     if (!strcmp(name, "bf16_eps")) g_opt.bf16_eps = value;
     else if (!strcmp(name, "f32_eps")) g_opt.f32_eps = value;
+    else if (!strcmp(name, "bf16_sigmas")) g_opt.bf16_sigmas = value;
     else if (!strcmp(name, "kprime")) g_opt.kprime = value;
     else if (!strcmp(name, "scan_max_batch")) g_opt.scan_max_batch = value;
     else if (!strcmp(name, "gemm_enabled")) g_opt.gemm_enabled = value;
@@ -178,6 +189,7 @@ double cmw_get_option(const char* name) {
     if (!name) return 0.0;
     if (!strcmp(name, "bf16_eps")) return g_opt.bf16_eps;
     if (!strcmp(name, "f32_eps")) return g_opt.f32_eps;
+    if (!strcmp(name, "bf16_sigmas")) return g_opt.bf16_sigmas;
     if (!strcmp(name, "kprime")) return g_opt.kprime;
     if (!strcmp(name, "scan_max_batch")) return g_opt.scan_max_batch;
     if (!strcmp(name, "gemm_enabled")) return g_opt.gemm_enabled;
