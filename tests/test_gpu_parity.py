@@ -561,3 +561,17 @@ def test_repair_chain_on_near_duplicates(torch_cuda):
     _check_exact(ids, sc, ref_ids, ref_sc)
     assert (fl == 0).all()
     st.close()
+
+
+def test_pure_c_client(tmp_path):
+    """The C-ABI boundary used from plain C (examples/c_client.c): no CUDA headers, no Python objects."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "cmw_rag_b200", "csrc")
+    exe = str(tmp_path / "c_client")
+    subprocess.run(["gcc", "-O2", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "c_client.c"),
+                    "-o", exe, "-L" + lib_dir, "-lcmwdense", "-Wl,-rpath," + lib_dir, "-lm"], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "c_client ok" in res.stdout
