@@ -12,11 +12,15 @@
 //   MMAs of item i+1.
 // Warp roles (192 threads, one persistent CTA per SM):
 //   warp 0   TMA producer (one elected lane): ring of [A 16 KB | B NT*128 B] stages, mbarrier tx
-//   warp 1   TMEM allocator + MMA issuer (one lane): tcgen05.mma.cta_group::1.kind::f16, K = 16,
-//            tcgen05.commit releases shared-memory stages and publishes finished accumulators
-//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns), multiply by the per-row multiplier
-//            (NaN for tombstoned rows), compare with the per-query admission threshold and append the
-//            rare survivors to the query's candidate pool (one global atomic each).  In the first
+//   warp 1   TMEM allocator + MMA issuer: the whole warp walks the pipeline warp-uniformly (operand
+//            descriptors stay in uniform registers), one elect.sync lane issues 4 back-to-back
+//            tcgen05.mma.cta_group::1.kind::f16 (K = 16) per k-block; tcgen05.commit releases
+//            shared-memory stages and publishes finished accumulators
+//   warps 2-5 epilogue (gemm_common.cuh): tcgen05.ld (32 lanes x 32 columns), multiply by the per-row
+//            multiplier (NaN for tombstoned rows), compare with the per-query admission thresholds
+//            (fetched as one batch while the TMEM load is in flight), stage the rare survivors in
+//            shared memory (ballot + popc), hand the accumulator back, then flush the staged entries
+//            to the queries' candidate pools with 32-64 global atomics in flight.  In the first
 //            ("dense") slab every score is written to its own slot instead.
 // The B x N score matrix is never written to memory.
 //
