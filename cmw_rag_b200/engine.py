@@ -70,14 +70,14 @@ class DenseStore:
         self.device = int(device)
         self.capacity = int(capacity)
         self.id_offset = int(id_offset)
-        self._ws = None
+        self._ws = {}
 
     # -- lifecycle ---------------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_h", None):
             N.lib().cmw_store_destroy(self._h)
             self._h = None
-            self._ws = None
+            self._ws = {}
 
     def __del__(self):  # pragma: no cover - best effort
         try:
@@ -153,14 +153,17 @@ class DenseStore:
     def _mode(mode, algo) -> int:
         return N.MODES[mode] | N.ALGOS[algo]
 
-    def _workspace(self, batch: int, k: int, mode: int):
+    def _workspace(self, batch: int, k: int, mode: int, slot: int = 0):
+        """One workspace per slot: searches that may overlap (different streams) need different slots."""
         torch = _torch()
         need = int(N.lib().cmw_search_workspace_bytes(self._h, batch, k, mode))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
-        return self._ws
+        ws = self._ws.get(slot)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
+            self._ws[slot] = ws
+        return ws
 
-    def search(self, queries, k: int, metric="cosine", mode="f32", algo=None, return_scores64=False):
+    def search(self, queries, k: int, metric="cosine", mode="f32", algo=None, return_scores64=False, ws_slot: int = 0):
         """Batched top-k on the device.  ``queries``: CUDA fp32 tensor [B, dim].
 
         Returns (scores f32[B,k], ids i64[B,k], flags i32[B]) as CUDA tensors, stream-ordered on
@@ -179,7 +182,7 @@ class DenseStore:
         s64 = torch.empty((b, k), dtype=torch.float64, device=dev) if return_scores64 else None
         if b == 0:
             return (scores, ids, flags, s64) if return_scores64 else (scores, ids, flags)
-        ws = self._workspace(b, k, m)
+        ws = self._workspace(b, k, m, ws_slot)
         stream = torch.cuda.current_stream(dev).cuda_stream
         N.check(
             N.lib().cmw_search(self._h, q.data_ptr(), b, k, N.METRICS[metric], m, scores.data_ptr(),
