@@ -70,3 +70,35 @@ def test_sharded_searcher_nccl(tmp_path):
         capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert res.stdout.count("sharded ok") == world
+
+
+def test_two_devices_in_one_process():
+    """One process driving two GPUs (the C ABI selects the store's device per call; shared-memory
+    attributes and TMA descriptors are per device)."""
+    import numpy as np
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    from cmw_rag_b200 import DenseStore
+    from oracle.cport import exact_topk_c
+
+    c = synth.make_corpus(12000, 256, seed=2)
+    q, _ = synth.make_queries(c, 40, seed=3)
+    ref, ref_sc, _ = exact_topk_c(c, q, 10)
+    stores = [DenseStore(256, 12000, device=dv) for dv in (0, 1)]
+    for st in stores:
+        st.append(c)
+    for rep in range(2):
+        for dv, st in enumerate(stores):
+            sc, ids, fl = st.search_host(q, 10)
+            assert (ids == ref).all() and (fl == 0).all(), dv
+            qd = torch.from_numpy(q[:3]).to(f"cuda:{dv}")
+            with torch.cuda.device(dv):
+                sc2, ids2, _ = st.search(qd, 10, algo="scan")
+                torch.cuda.synchronize(dv)
+            assert (ids2.cpu().numpy() == ref[:3]).all()
+    for st in stores:
+        st.close()
