@@ -76,7 +76,7 @@ class B200Store:
         port: int | None = None,
         *,
         dim: int | None = None,
-        capacity: int = 1 << 20,
+        capacity: int = 1 << 17,  # rows reserved in HBM up front; the collection doubles when it fills up
         device: int = 0,
         metric: str = "cosine",  # vector_store.py:48-51 pins {"hnsw:space": "cosine"}
         mode: str = "f32",
