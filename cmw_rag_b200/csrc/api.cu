@@ -472,8 +472,9 @@ int cmw_search_host(cmw_store* h, const float* queries_host, int batch, int k, i
     const bool first_was_gemm = use_gemm(s, batch, mode);
     int stages[2];
     int nstage = 0;
-    if (!((mode & CMW_SLABS_SAFE) && (mode & CMW_KPRIME_MAX))) stages[nstage++] = mode | CMW_SLABS_SAFE | CMW_KPRIME_MAX;
-    if (exact && first_was_gemm)
+    if (g_opt.repair >= 1 && !((mode & CMW_SLABS_SAFE) && (mode & CMW_KPRIME_MAX)))
+        stages[nstage++] = mode | CMW_SLABS_SAFE | CMW_KPRIME_MAX;
+    if (g_opt.repair >= 2 && exact && first_was_gemm)
         stages[nstage++] = CMW_MODE_F32_EXACT | CMW_ALGO_SCAN | CMW_SLABS_SAFE | CMW_KPRIME_MAX;
     for (int st = 0; st < nstage && !redo.empty(); ++st) {
         std::vector<float> q2((size_t)redo.size() * s->dim);

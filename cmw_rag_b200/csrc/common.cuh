@@ -120,6 +120,11 @@ struct Options {
     // 1 = rigorous certificate behind the bf16 filter: eps = 2u(1+u) + fp32 accumulation slack = 4.1e-3
     // (Cauchy-Schwarz over unit vectors, u = 2^-9) and K' = max(512, 4k); ~17 % slower at B=4096
     double strict_certificate = 0;
+    // host API repair chain for flagged queries: 0 = off (flags are only reported), 1 = stage 1 only (same
+    // filter, K' = 1024, overflow-proof slabs), 2 = also stage 2 (fp32 scan filter).  Exact ties larger than
+    // K' - k straddling the k-th place stay flagged whatever the stage -- the ids are still the lowest of
+    // the tie by construction -- so tie-heavy corpora may prefer 1.
+    double repair = 2;
     double slab_growth = 0;   // 0 = automatic ((cap - K') / (3 K'), at most 8); else the fixed growth factor
 };
 extern Options g_opt;

@@ -176,6 +176,7 @@ int cmw_set_option(const char* name, double value) {
     else if (!strcmp(name, "gemm_enabled")) g_opt.gemm_enabled = value;
     else if (!strcmp(name, "slab_growth")) g_opt.slab_growth = value;
     else if (!strcmp(name, "strict_certificate")) g_opt.strict_certificate = value;
+    else if (!strcmp(name, "repair")) g_opt.repair = value;
     else if (!strcmp(name, "gemm_2cta")) g_opt.gemm_2cta = value;
     else if (!strcmp(name, "gemm_2cta_min_batch")) g_opt.gemm_2cta_min_batch = value;
     else {
@@ -195,6 +196,7 @@ double cmw_get_option(const char* name) {
     if (!strcmp(name, "gemm_enabled")) return g_opt.gemm_enabled;
     if (!strcmp(name, "slab_growth")) return g_opt.slab_growth;
     if (!strcmp(name, "strict_certificate")) return g_opt.strict_certificate;
+    if (!strcmp(name, "repair")) return g_opt.repair;
     if (!strcmp(name, "gemm_2cta")) return g_opt.gemm_2cta;
     if (!strcmp(name, "gemm_2cta_min_batch")) return g_opt.gemm_2cta_min_batch;
     if (!strcmp(name, "pool_cap")) return (double)kPoolCap;
