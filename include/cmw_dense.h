@@ -167,7 +167,15 @@ int64_t cmw_kernel_launches(void);
  * preparation; counts[i] = kernels launched in that phase.  n = array length (<= 4). */
 int cmw_profile_enable(int on);
 int cmw_profile_read(double* ms, int64_t* counts, int n);
-/* tunables: "bf16_eps" (certificate bound for the bf16 filter), "scan_max_batch", ... */
+/* Process-wide tunables (defaults in parentheses):
+ *   "scan_max_batch" (0)      batches up to this size use K1 (scan), larger ones K2 (GEMM)
+ *   "gemm_enabled" (1), "gemm_2cta" (1), "gemm_2cta_min_batch" (256)   K2 kernel selection
+ *   "kprime" (0 = automatic)  candidates kept per query between slabs and handed to K3
+ *   "bf16_eps" (0 = automatic, dimension-aware), "bf16_sigmas" (8), "f32_eps" (4e-6)   certificate bounds
+ *   "strict_certificate" (0)  1 = rigorous Cauchy-Schwarz bound behind the bf16 filter (K' = max(512, 4k))
+ *   "repair" (2)              cmw_search_host repair chain for flagged queries: 0 off, 1 stage 1, 2 both stages
+ *   "slab_growth" (0 = automatic)   cap on the geometric growth of the slabs
+ *   "pool_cap" (read-only)    candidate-pool slots per query */
 int cmw_set_option(const char* name, double value);
 double cmw_get_option(const char* name);
 
