@@ -54,8 +54,12 @@ def parse_args():
     ap.add_argument("--cpu-queries", type=int, default=16, help="queries in the bounded CPU sample")
     ap.add_argument("--hnsw-rows", type=int, default=0,
                     help="rows in the CPU HNSW index (bounded sample); 0 = 50k for the cpu_baseline leg of the "
-                         "GPU arm (~10 s build), 250k for --impl reference (~1 min build on 16 cores)")
+                         "GPU arm (~10 s build), and for --impl reference as many rows as --hnsw-build-budget allows")
+    ap.add_argument("--hnsw-build-budget", type=float, default=150.0,
+                    help="--impl reference: seconds of index construction before the index is frozen")
     ap.add_argument("--hnsw-queries", type=int, default=512)
+    ap.add_argument("--in-flight", type=int, default=2, help="requests outstanding in the pipelined end-to-end leg")
+    ap.add_argument("--leg-gap", type=float, default=1.0, help="idle seconds before each timed leg")
     ap.add_argument("--skip-cpu-exact", action="store_true")
     ap.add_argument("--skip-b1", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -180,22 +184,36 @@ HNSW_LABEL = ("hnswlib-equivalent HNSW re-implementation (oracle/hnsw/hnsw_basel
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  The
-    reference delegates the arithmetic to chromadb/hnswlib (not installable here); the timed code is
-    the oracle's exact C port (all host threads), on a bounded sample of queries per step."""
+    reference delegates the arithmetic to chromadb/hnswlib (not installable here); what is timed is the
+    hnswlib-equivalent HNSW index of oracle/hnsw (Chroma's defaults, all host threads, one query per
+    thread) answering a bounded sample of queries per step.  The index covers as much of the corpus as
+    can be inserted within --hnsw-build-budget seconds (a full 1M x 1536 build takes ~250 s on 16
+    cores; HNSW query cost grows ~log N, so a partial index flatters the CPU), or exactly --hnsw-rows."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import synth
+    from oracle.cport import exact_topk_c
     from oracle.hnsw import HnswIndex, num_threads
 
-    index_rows = min(args.rows, args.hnsw_rows or 250_000)
-    corpus = host_corpus(index_rows, args.dim)
+    max_rows = min(args.rows, args.hnsw_rows) if args.hnsw_rows else args.rows
+    budget = float("inf") if args.hnsw_rows else args.hnsw_build_budget
+    block = 25_000
+    corpus = np.empty((max_rows, args.dim), np.float32)
+    ix = HnswIndex(args.dim, max_rows)
+    index_rows, build_s, blk = 0, 0.0, 0
+    while index_rows < max_rows and build_s < budget:
+        m = min(block, max_rows - index_rows)
+        # iid rows: one seeded block at a time, so that generation stays out of the build clock
+        corpus[index_rows:index_rows + m] = synth.make_corpus(m, args.dim, seed=SEED + blk, ties=False)
+        t0 = time.perf_counter()
+        ix.add(corpus[index_rows:index_rows + m])
+        build_s += time.perf_counter() - t0
+        index_rows += m
+        blk += 1
+    corpus = corpus[:index_rows]
     nq = max(16, args.hnsw_queries)
-    q, _ = synth.make_queries(corpus, nq, seed=7, tie_probe=False)
-    ix = HnswIndex(args.dim, index_rows)
-    t0 = time.perf_counter()
-    ix.add(corpus)
-    build_s = time.perf_counter() - t0
+    q, _ = synth.make_queries(corpus[:block], nq, seed=7, tie_probe=False)
     for _ in range(max(1, args.warmup)):
         ix.search(q[:16], args.k)
     t0 = time.perf_counter()
@@ -203,20 +221,23 @@ def run_reference(args):
         ids, _ = ix.search(q, args.k)
     dt = time.perf_counter() - t0
     qps = nq * args.steps / dt
-    from oracle.cport import exact_topk_c
-
     nref = min(64, nq)
     ref, _, _ = exact_topk_c(corpus, q[:nref], args.k)
     recall = float(np.mean([len(set(ids[b]) & set(ref[b])) / args.k for b in range(nref)]))
-    sample = (f"{nq} queries per step against an HNSW index over {index_rows} rows "
-              f"({'the full corpus' if index_rows == args.rows else 'a subsample of the ' + str(args.rows) + '-row corpus; HNSW cost grows ~log N, so this flatters the CPU'}), "
+    ix.close()
+    cover = ("the full corpus" if index_rows == args.rows else
+             f"the part of the {args.rows}-row corpus that could be inserted within the build budget "
+             f"({args.hnsw_build_budget:.0f} s); HNSW cost grows ~log N, so this flatters the CPU"
+             if not args.hnsw_rows else f"a subsample of the {args.rows}-row corpus; this flatters the CPU")
+    sample = (f"{nq} queries per step against an HNSW index over {index_rows} rows ({cover}), "
               f"index build {build_s:.1f} s (not timed), recall@{args.k} {recall:.3f} vs exact; {HNSW_LABEL}")
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.rows}x{args.dim} fp32 corpus, top-{args.k} cosine, "
-                               f"query batch {args.batch} per GPU (CPU arm: {nq}-query sample per step)"},
+                               f"query batch {args.batch} per GPU (CPU arm: {nq}-query sample per step, "
+                               f"index over {index_rows} rows)"},
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": num_threads(), "kind": "port", "sample": sample,
                          "recall_at_k": recall, "index_rows": index_rows, "build_s": build_s},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -337,6 +358,7 @@ def run_ours(args):
     # ---- timed region: device-resident ------------------------------------------------------
     sampler = ClockSampler(local_rank)
     barrier()
+    time.sleep(args.leg_gap)
     if rank == 0:
         sampler.start()
     N.profile_enable(True)
@@ -353,20 +375,53 @@ def run_ours(args):
     N.profile_enable(False)
 
     # ---- timed region: end to end through the host-buffer C ABI ------------------------------
+    # (a) blocking calls, one after the other (cmw_search_host): H2D, kernels, D2H, sync -- per-call latency
+    # (every leg starts from an idle GPU: the step is power-capped, so a leg that runs right behind another
+    # one inherits its heat and reads ~5 % lower)
     barrier()
+    time.sleep(args.leg_gap)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         st.search_host(q_host, k, mode=args.mode, algo=args.algo, out=out_host)
     torch.cuda.synchronize(device)
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_serial_ms = (time.perf_counter() - t0) * 1e3
     if not row_shard:
         assert (out_host[1] == ids0_h).all(), "host-buffer path and device path disagree"
+    # (b) the pipelined form (cmw_search_host_submit / _wait), `--in-flight` requests outstanding, as the
+    # reference's callers are (S concurrent awaits per request, concurrent requests): every step still
+    # copies its own inputs from pinned host memory and reads its own results back, inside the timed
+    # region; the copies of one step overlap the kernels of its neighbours
+    depth = max(1, min(args.in_flight, N.HOST_SLOTS))
+    outs = [out_host] + [(pinned_empty((B, k), np.float32), pinned_empty((B, k), np.int64), np.zeros((B,), np.int32))
+                         for _ in range(depth - 1)]
+    for o in outs:
+        o[1][:] = -7
+    # first use of a slot allocates its staging buffers and workspace: keep that out of the clock
+    for t in [st.search_host_submit(q_host, k, mode=args.mode, algo=args.algo, out=outs[i]) for i in range(depth)]:
+        st.search_host_wait(t)
+    from collections import deque
+
+    pending = deque()
+    barrier()
+    time.sleep(args.leg_gap)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        if len(pending) == depth:
+            st.search_host_wait(pending.popleft())
+        pending.append(st.search_host_submit(q_host, k, mode=args.mode, algo=args.algo, out=outs[i % depth]))
+    while pending:
+        st.search_host_wait(pending.popleft())
+    torch.cuda.synchronize(device)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if not row_shard:
+        for o in outs[: min(depth, args.steps)]:
+            assert (o[1] == ids0_h).all(), "pipelined host-buffer path and device path disagree"
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=device)
+        t = torch.tensor([dev_ms, e2e_ms, e2e_serial_ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        dev_ms, e2e_ms, e2e_serial_ms = float(t[0]), float(t[1]), float(t[2])
 
     # ---- batch-1 legs (HBM-bound regime) ------------------------------------------------------
     # "auto": the default exact path (K2 tensor-core filter over the bf16 tiles + fp64 rescoring);
@@ -443,11 +498,16 @@ def run_ours(args):
     if used_gemm:
         flops = 2.0 * B * args.rows * args.dim * args.steps
         ach = flops / (filt_ms * 1e-3) / 1e12
+        # B200_PROFILING.md: burst cuBLAS figure for a kernel timed in a short region, the sustained
+        # (power-capped, seconds-long) one for a long step
+        long_region = dev_ms > 2000.0
+        pk = peaks["bf16_tflops_sustained"] if long_region else peaks["bf16_tflops"]
         roof = {"bound": "tensor", "kernel": "gemm_topk_kernel (K2)", "achieved": ach,
-                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
-                "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
-                "frac_of_burst": ach / peaks["bf16_tflops"]}
+                "peak": pk, "unit": "TFLOP/s", "frac": ach / pk, "traffic": None,
+                "peak_source": peaks["source"] + (" (sustained cuBLAS bf16: timed region > 2 s)" if long_region else
+                                                  f" (burst cuBLAS bf16: timed region {dev_ms:.0f} ms)"),
+                "frac_of_burst": ach / peaks["bf16_tflops"],
+                "frac_of_sustained": ach / peaks["bf16_tflops_sustained"]}
     else:
         elt = 2 if args.mode == "bf16" else 4
         passes = (B + 1) // 2
@@ -473,25 +533,61 @@ def run_ours(args):
     phases = {name: {"ms_per_step": ms / args.steps, "launches_per_step": n / args.steps}
               for name, (ms, n) in prof.items()}
 
-    cpu = None
-    if world == 1 and not args.skip_cpu:
-        import synth
+    # bf16 mode (approximate) on the same batch: throughput and recall@k against the exact mode's ids
+    bf16_leg = None
+    if args.mode == "f32" and not row_shard:
+        for _ in range(2):
+            st.search(q, k, mode="bf16", algo=args.algo)
+        torch.cuda.synchronize(device)
+        time.sleep(args.leg_gap)
+        b0, b1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(args.steps):
+            sc_b, ids_b, _ = st.search(q, k, mode="bf16", algo=args.algo)
+        b1e.record()
+        torch.cuda.synchronize(device)
+        ids_bh = ids_b.cpu().numpy()
+        rec = float(np.mean([len(np.intersect1d(ids_bh[i], ids0_h[i])) / k for i in range(B)]))
+        err = float((sc_b - sc0).abs().max().item())
+        bf16_leg = {"qps": B * args.steps / (b0.elapsed_time(b1e) * 1e-3), "recall_at_k": rec,
+                    "max_abs_score_err_vs_exact": err, "tolerance": 2e-3}
 
-        # an equally shaped, equally seeded corpus on the host (same workload, bounded sample)
+    cpu = None
+    parity = None
+    if world == 1 and not args.skip_cpu:
+        # the CPU legs run on the SAME corpus bits (read back from the HBM store) and the same queries
         index_rows = min(args.rows, args.hnsw_rows or 50_000)
-        corpus = host_corpus(args.rows if not args.skip_cpu_exact else index_rows, args.dim)
-        cq, _ = synth.make_queries(corpus[:index_rows], max(16, args.hnsw_queries), seed=7, tie_probe=False)
+        if args.no_f32 or args.skip_cpu_exact:
+            corpus = host_corpus(index_rows, args.dim)
+            import synth
+
+            cq, _ = synth.make_queries(corpus, max(16, args.hnsw_queries), seed=7, tie_probe=False)
+        else:
+            corpus = st.read_rows(0, args.rows)[0]
+            cq = np.ascontiguousarray(q_host[: max(16, args.hnsw_queries)])
         qps, recall, build_s, threads = cpu_hnsw_sample(corpus, cq, k, index_rows)
         cpu = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{cq.shape[0]} queries against an HNSW index over a {index_rows}-row subsample "
                          f"(build {build_s:.1f} s, not timed; HNSW cost grows ~log N, so the subsample flatters "
                          f"the CPU), recall@{k} {recall:.3f} vs exact; {HNSW_LABEL}",
                "recall_at_k": recall, "index_rows": index_rows, "build_s": build_s}
-        if not args.skip_cpu_exact:
-            xq, dt, xthreads = cpu_exact_sample(corpus, cq[: args.cpu_queries], k)
+        if not (args.no_f32 or args.skip_cpu_exact):
+            from oracle.cport import exact_topk_c
+
+            nchk = min(args.cpu_queries, B)
+            xq, dt, xthreads = cpu_exact_sample(corpus, cq[:nchk], k)
             cpu["exact_port"] = {"value": xq, "unit": UNIT, "cores": xthreads,
-                                 "sample": f"{args.cpu_queries} queries x {args.rows} rows, exact fp64 brute force "
+                                 "sample": f"{nchk} queries x {args.rows} rows, exact fp64 brute force "
                                            f"(oracle/c/oracle_topk.c, OpenMP, {dt:.1f} s)"}
+        if not (args.no_f32 or args.skip_cpu_exact) and args.mode == "f32":
+            # parity of the timed workload itself: the first queries of the batch against the oracle
+            ref_ids, ref_sc, _ = exact_topk_c(corpus, cq[:nchk], k)
+            sc0_h = sc0.cpu().numpy()
+            parity = {"queries_checked": nchk, "rows": args.rows, "k": k,
+                      "ids_identical_to_fp64_oracle": bool((ids0_h[:nchk] == ref_ids).all()),
+                      "max_abs_score_err": float(np.abs(sc0_h[:nchk] - ref_sc).max()), "tolerance": 1e-5}
+            assert parity["ids_identical_to_fp64_oracle"], "top-k ids differ from the fp64 oracle"
+            assert parity["max_abs_score_err"] <= 1e-5, parity
         del corpus
 
     line = {
@@ -512,11 +608,16 @@ def run_ours(args):
         },
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * args.dim * 4,
-                "d2h_bytes_per_step": B * k * 12 + B * 4, "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": B * k * 12 + B * 4, "ms_per_step": e2e_ms / args.steps,
+                "in_flight": depth, "api": "cmw_search_host_submit/_wait (pinned host buffers)",
+                "blocking": {"value": units / (e2e_serial_ms * 1e-3), "unit": UNIT,
+                             "ms_per_step": e2e_serial_ms / args.steps, "api": "cmw_search_host"}},
         "gpu_launches": int(launches),
         "roofline": roof,
         "phases": phases,
         "cpu_baseline": cpu,
+        "parity": parity,
+        "bf16_mode": bf16_leg,
         "batch1": b1,
         "batch1_fp32_scan": b1_scan,
         "store": {"rows": info["rows"], "hbm_bytes": info["hbm_bytes"], "gemm_ready": info["gemm_ready"]},

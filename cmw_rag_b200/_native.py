@@ -25,6 +25,7 @@ KPRIME_MAX = 1 << 17
 STORE_F32 = 1
 STORE_BF16 = 2
 FLAG_UNCERTIFIED = 1
+HOST_SLOTS = 4
 
 METRICS = {"cosine": METRIC_COSINE, "ip": METRIC_IP, METRIC_COSINE: METRIC_COSINE, METRIC_IP: METRIC_IP}
 MODES = {"f32": MODE_F32_EXACT, "exact": MODE_F32_EXACT, "bf16": MODE_BF16,
@@ -65,6 +66,9 @@ SIGNATURES = {
                            c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cmw_search_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p]),
+    "cmw_search_host_submit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p, POINTER(c_int)]),
+    "cmw_search_host_wait": (c_int, [c_void_p, c_int]),
     "cmw_multivector": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_int, c_int] + [c_void_p] * 11 + [c_void_p]),
     "cmw_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

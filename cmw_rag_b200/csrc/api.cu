@@ -122,6 +122,137 @@ static int stage_h2d(int device, uint8_t* pin, uint8_t* dev, const uint8_t* src,
     return 0;
 }
 
+// Layout of one host call's I/O block (the same offsets in the pinned staging buffer and in its device twin):
+// queries | scores | ids | flags.
+struct HostIo {
+    size_t q_bytes, sc_bytes, id_bytes, fl_bytes, total;
+};
+static HostIo host_io(const Store* s, int batch, int k) {
+    HostIo io;
+    io.q_bytes = align_up((size_t)batch * s->dim * sizeof(float), 256);
+    io.sc_bytes = align_up((size_t)batch * k * sizeof(float), 256);
+    io.id_bytes = align_up((size_t)batch * k * sizeof(int64_t), 256);
+    io.fl_bytes = align_up((size_t)batch * sizeof(int32_t), 256);
+    io.total = io.q_bytes + io.sc_bytes + io.id_bytes + io.fl_bytes;
+    return io;
+}
+
+// page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used for DMA
+// directly; pageable ones go through a pinned staging buffer
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+static int ensure_buffer(void** ptr, size_t* have, size_t bytes, bool host) {
+    if (*have >= bytes) return 0;
+    if (*ptr) {
+        if (host) cudaFreeHost(*ptr);
+        else cudaFree(*ptr);
+    }
+    *ptr = nullptr;
+    *have = 0;
+    if (host) CMW_CUDA_OK(cudaMallocHost(ptr, bytes));
+    else CMW_CUDA_OK(cudaMalloc(ptr, bytes));
+    *have = bytes;
+    return 0;
+}
+
+static int ensure_blocking_buffers(cmw_store* h, Store* s, const HostIo& io, int batch, int k, int mode) {
+    int rc;
+    if ((rc = ensure_pinned(s, io.total))) return rc;
+    if ((rc = ensure_dev_io(s, io.total))) return rc;
+    return ensure_ws(s, cmw_search_workspace_bytes(h, batch, k, mode));
+}
+
+// One blocking search of nb <= batch queries through the store's own staging buffers (offsets of `io`, which
+// was laid out for the whole batch): H2D, cmw_search, D2H, synchronise.  direct_* non-NULL = page-locked
+// caller buffers that receive scores / ids by DMA; flags always land in the pinned buffer.
+static int run_blocking(cmw_store* h, Store* s, cudaStream_t stream, const HostIo& io, const float* q_src, int nb,
+                        int k, int metric, int run_mode, float* direct_scores, int64_t* direct_ids) {
+    uint8_t* pin = reinterpret_cast<uint8_t*>(s->pinned);
+    uint8_t* dev = reinterpret_cast<uint8_t*>(s->dev_io);
+    const size_t qb = (size_t)nb * s->dim * sizeof(float);
+    if (is_pinned(q_src)) {
+        CMW_CUDA_OK(cudaMemcpyAsync(dev, q_src, qb, cudaMemcpyHostToDevice, stream));
+    } else if (stage_h2d(s->device, pin, dev, reinterpret_cast<const uint8_t*>(q_src), qb, stream)) {
+        // pageable -> pinned -> device, pipelined: a few host threads copy 1 MB pieces into the pinned
+        // staging buffer and enqueue each piece's H2D as soon as it is staged, so the DMA of one
+        // piece overlaps the memcpy of the next (all pieces precede the search on the same stream)
+        return -2;
+    }
+    const size_t sc_off = io.q_bytes, id_off = io.q_bytes + io.sc_bytes, fl_off = id_off + io.id_bytes;
+    int r = cmw_search(h, reinterpret_cast<const float*>(dev), nb, k, metric, run_mode,
+                       reinterpret_cast<float*>(dev + sc_off), reinterpret_cast<int64_t*>(dev + id_off), nullptr,
+                       reinterpret_cast<int32_t*>(dev + fl_off), s->ws, s->ws_bytes, stream);
+    if (r) return r;
+    if (direct_scores && direct_ids) {
+        CMW_CUDA_OK(cudaMemcpyAsync(direct_scores, dev + sc_off, (size_t)nb * k * sizeof(float),
+                                    cudaMemcpyDeviceToHost, stream));
+        CMW_CUDA_OK(cudaMemcpyAsync(direct_ids, dev + id_off, (size_t)nb * k * sizeof(int64_t),
+                                    cudaMemcpyDeviceToHost, stream));
+        CMW_CUDA_OK(cudaMemcpyAsync(pin + fl_off, dev + fl_off, io.fl_bytes, cudaMemcpyDeviceToHost, stream));
+    } else {
+        // one D2H for scores + ids + flags (contiguous in dev_io)
+        CMW_CUDA_OK(cudaMemcpyAsync(pin + sc_off, dev + sc_off, io.sc_bytes + io.id_bytes + io.fl_bytes,
+                                    cudaMemcpyDeviceToHost, stream));
+    }
+    CMW_CUDA_OK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+// Repair chain for flagged queries (a failed certificate: many scores within eps of the k-th; or a
+// pool overflow: adversarial row order).  `first_flags` = the flags of the first pass (copied out before
+// the staging buffers are reused).  Each stage re-runs only the queries still flagged, batched:
+//   1. the same filter with the largest K' (1024) on the overflow-proof slab schedule -- a handful
+//      of milliseconds whatever the number of queries when the filter is K2;
+//   2. (exact mode) the fp32 scan filter, certificate bound three orders of magnitude tighter, also
+//      with the largest K' and the overflow-proof schedule.
+// bf16 mode can only be flagged by an overflow: stage 1 settles it.
+static int repair_flagged(cmw_store* h, Store* s, cudaStream_t stream, const HostIo& io, const float* queries_host,
+                          int batch, int k, int metric, int mode, float* out_scores_host, int64_t* out_ids_host,
+                          int32_t* out_flags_host, const int32_t* first_flags) {
+    std::vector<int> redo;
+    for (int b = 0; b < batch; ++b) {
+        if (out_flags_host) out_flags_host[b] = first_flags[b];
+        if (first_flags[b] & CMW_FLAG_UNCERTIFIED) redo.push_back(b);
+    }
+    if (redo.empty()) return 0;
+    const uint8_t* pin = reinterpret_cast<const uint8_t*>(s->pinned);
+    const float* sc = reinterpret_cast<const float*>(pin + io.q_bytes);
+    const int64_t* id = reinterpret_cast<const int64_t*>(pin + io.q_bytes + io.sc_bytes);
+    const int32_t* fl = reinterpret_cast<const int32_t*>(pin + io.q_bytes + io.sc_bytes + io.id_bytes);
+    const bool exact = (mode & 0xff) == CMW_MODE_F32_EXACT;
+    const bool first_was_gemm = use_gemm(s, batch, mode);
+    int stages[2];
+    int nstage = 0;
+    if (g_opt.repair >= 1 && !((mode & CMW_SLABS_SAFE) && (mode & CMW_KPRIME_MAX)))
+        stages[nstage++] = mode | CMW_SLABS_SAFE | CMW_KPRIME_MAX;
+    if (g_opt.repair >= 2 && exact && first_was_gemm)
+        stages[nstage++] = CMW_MODE_F32_EXACT | CMW_ALGO_SCAN | CMW_SLABS_SAFE | CMW_KPRIME_MAX;
+    for (int st = 0; st < nstage && !redo.empty(); ++st) {
+        std::vector<float> q2((size_t)redo.size() * s->dim);
+        for (size_t i = 0; i < redo.size(); ++i)
+            memcpy(q2.data() + i * s->dim, queries_host + (size_t)redo[i] * s->dim, (size_t)s->dim * sizeof(float));
+        int rc = run_blocking(h, s, stream, io, q2.data(), (int)redo.size(), k, metric, stages[st], nullptr, nullptr);
+        if (rc) return rc;
+        std::vector<int> still;
+        for (size_t i = 0; i < redo.size(); ++i) {
+            const int b = redo[i];
+            memcpy(out_scores_host + (size_t)b * k, sc + i * k, (size_t)k * sizeof(float));
+            memcpy(out_ids_host + (size_t)b * k, id + i * k, (size_t)k * sizeof(int64_t));
+            if (out_flags_host) out_flags_host[b] = fl[i];
+            if (fl[i] & CMW_FLAG_UNCERTIFIED) still.push_back(b);
+        }
+        redo.swap(still);
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // optional per-phase timing (cmw_profile_enable / cmw_profile_read)
 // ---------------------------------------------------------------------------------------------
@@ -392,107 +523,158 @@ int cmw_search_host(cmw_store* h, const float* queries_host, int batch, int k, i
     cudaStream_t stream;
     int rc = get_stream(s, &stream);
     if (rc) return rc;
-    const size_t q_bytes = align_up((size_t)batch * s->dim * sizeof(float), 256);
-    const size_t sc_bytes = align_up((size_t)batch * k * sizeof(float), 256);
-    const size_t id_bytes = align_up((size_t)batch * k * sizeof(int64_t), 256);
-    const size_t fl_bytes = align_up((size_t)batch * sizeof(int32_t), 256);
-    const size_t io_bytes = q_bytes + sc_bytes + id_bytes + fl_bytes;
-    if ((rc = ensure_pinned(s, io_bytes))) return rc;
-    if ((rc = ensure_dev_io(s, io_bytes))) return rc;
-    const size_t ws_bytes = cmw_search_workspace_bytes(h, batch, k, mode);
-    if ((rc = ensure_ws(s, ws_bytes))) return rc;
-    uint8_t* pin = reinterpret_cast<uint8_t*>(s->pinned);
-    uint8_t* dev = reinterpret_cast<uint8_t*>(s->dev_io);
-
-    // page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used for
-    // DMA directly; pageable ones go through the store's pinned staging buffer
-    auto is_pinned = [](const void* p) -> bool {
-        cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        return attr.type == cudaMemoryTypeHost;
-    };
+    const HostIo io = host_io(s, batch, k);
+    if ((rc = ensure_blocking_buffers(h, s, io, batch, k, mode))) return rc;
     const bool out_pinned = is_pinned(out_scores_host) && is_pinned(out_ids_host);
+    if ((rc = run_blocking(h, s, stream, io, queries_host, batch, k, metric, mode,
+                           out_pinned ? out_scores_host : nullptr, out_pinned ? out_ids_host : nullptr)))
+        return rc;
+    uint8_t* pin = reinterpret_cast<uint8_t*>(s->pinned);
+    if (!out_pinned) {
+        memcpy(out_scores_host, pin + io.q_bytes, (size_t)batch * k * sizeof(float));
+        memcpy(out_ids_host, pin + io.q_bytes + io.sc_bytes, (size_t)batch * k * sizeof(int64_t));
+    }
+    return repair_flagged(h, s, stream, io, queries_host, batch, k, metric, mode, out_scores_host, out_ids_host,
+                          out_flags_host, reinterpret_cast<const int32_t*>(pin + io.q_bytes + io.sc_bytes + io.id_bytes));
+}
 
-    auto run = [&](const float* q_src, int nb, int run_mode, bool direct_out) -> int {
-        const size_t qb = (size_t)nb * s->dim * sizeof(float);
-        if (is_pinned(q_src)) {
-            CMW_CUDA_OK(cudaMemcpyAsync(dev, q_src, qb, cudaMemcpyHostToDevice, stream));
-        } else if (stage_h2d(s->device, pin, dev, reinterpret_cast<const uint8_t*>(q_src), qb, stream)) {
-            // pageable -> pinned -> device, pipelined: a few host threads copy 1 MB pieces into the pinned
-            // staging buffer and enqueue each piece's H2D as soon as it is staged, so the DMA of one
-            // piece overlaps the memcpy of the next (all pieces precede the search on the same stream)
+int cmw_search_host_submit(cmw_store* h, const float* queries_host, int batch, int k, int metric, int mode,
+                           float* out_scores_host, int64_t* out_ids_host, int32_t* out_flags_host,
+                           int* ticket_out) {
+    CMW_REQUIRE(h != nullptr, "cmw_search_host_submit: store is NULL");
+    Store* s = reinterpret_cast<Store*>(h);
+    CMW_REQUIRE(ticket_out != nullptr, "cmw_search_host_submit: ticket_out is NULL");
+    *ticket_out = -1;
+    CMW_REQUIRE(batch > 0 && queries_host && out_scores_host && out_ids_host,
+                "cmw_search_host_submit: bad arguments");
+    CMW_REQUIRE(k >= 1 && k <= kMaxKPrime, "cmw_search_host_submit: k must be in [1, %d], got %d", kMaxKPrime, k);
+    std::lock_guard<std::mutex> host_lock(s->host_mu);
+    CMW_CUDA_OK(cudaSetDevice(s->device));
+    int slot_no = -1;
+    for (int i = 0; i < kHostSlots; ++i)
+        if (!s->slots[i].busy) {
+            slot_no = i;
+            break;
+        }
+    if (slot_no < 0) {
+        set_error("cmw_search_host_submit: all %d slots are in flight; cmw_search_host_wait one first", kHostSlots);
+        return -4;
+    }
+    HostSlot& sl = s->slots[slot_no];
+    cudaStream_t compute;
+    int rc = get_stream(s, &compute);
+    if (rc) return rc;
+    if (s->copy_in == nullptr) CMW_CUDA_OK(cudaStreamCreateWithFlags(&s->copy_in, cudaStreamNonBlocking));
+    if (s->copy_out == nullptr) CMW_CUDA_OK(cudaStreamCreateWithFlags(&s->copy_out, cudaStreamNonBlocking));
+    if (sl.ev_in == nullptr) CMW_CUDA_OK(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+    if (sl.ev_compute == nullptr) CMW_CUDA_OK(cudaEventCreateWithFlags(&sl.ev_compute, cudaEventDisableTiming));
+    if (sl.ev_done == nullptr) CMW_CUDA_OK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    const HostIo io = host_io(s, batch, k);
+    const size_t ws_bytes = cmw_search_workspace_bytes(h, batch, k, mode);
+    if ((rc = ensure_buffer(&sl.dev_io, &sl.dev_io_bytes, io.total, false))) return rc;
+    if ((rc = ensure_buffer(&sl.ws, &sl.ws_bytes, ws_bytes, false))) return rc;
+    const bool in_pinned = is_pinned(queries_host);
+    const bool out_pinned = is_pinned(out_scores_host) && is_pinned(out_ids_host);
+    if ((rc = ensure_buffer(&sl.pinned, &sl.pinned_bytes, io.total, true))) return rc;
+    uint8_t* pin = reinterpret_cast<uint8_t*>(sl.pinned);
+    uint8_t* dev = reinterpret_cast<uint8_t*>(sl.dev_io);
+
+    auto enqueue = [&]() -> int {
+        // copy-in stream: H2D of the queries (overlaps whatever the compute stream is doing for earlier tickets)
+        const size_t qb = (size_t)batch * s->dim * sizeof(float);
+        if (in_pinned) {
+            CMW_CUDA_OK(cudaMemcpyAsync(dev, queries_host, qb, cudaMemcpyHostToDevice, s->copy_in));
+        } else if (stage_h2d(s->device, pin, dev, reinterpret_cast<const uint8_t*>(queries_host), qb, s->copy_in)) {
             return -2;
         }
-        int r = cmw_search(h, reinterpret_cast<const float*>(dev), nb, k, metric, run_mode,
-                           reinterpret_cast<float*>(dev + q_bytes),
-                           reinterpret_cast<int64_t*>(dev + q_bytes + sc_bytes), nullptr,
-                           reinterpret_cast<int32_t*>(dev + q_bytes + sc_bytes + id_bytes), s->ws,
-                           s->ws_bytes, stream);
-        if (r) return r;
-        if (direct_out) {
-            CMW_CUDA_OK(cudaMemcpyAsync(out_scores_host, dev + q_bytes, (size_t)nb * k * sizeof(float),
-                                        cudaMemcpyDeviceToHost, stream));
-            CMW_CUDA_OK(cudaMemcpyAsync(out_ids_host, dev + q_bytes + sc_bytes, (size_t)nb * k * sizeof(int64_t),
-                                        cudaMemcpyDeviceToHost, stream));
-            CMW_CUDA_OK(cudaMemcpyAsync(pin + q_bytes + sc_bytes + id_bytes, dev + q_bytes + sc_bytes + id_bytes,
-                                        fl_bytes, cudaMemcpyDeviceToHost, stream));
+        CMW_CUDA_OK(cudaEventRecord(sl.ev_in, s->copy_in));
+        // compute stream (in order over all tickets and blocking calls of this store)
+        CMW_CUDA_OK(cudaStreamWaitEvent(compute, sl.ev_in, 0));
+        rc = cmw_search(h, reinterpret_cast<const float*>(dev), batch, k, metric, mode,
+                        reinterpret_cast<float*>(dev + io.q_bytes), reinterpret_cast<int64_t*>(dev + io.q_bytes + io.sc_bytes),
+                        nullptr, reinterpret_cast<int32_t*>(dev + io.q_bytes + io.sc_bytes + io.id_bytes), sl.ws,
+                        sl.ws_bytes, compute);
+        if (rc) return rc;
+        CMW_CUDA_OK(cudaEventRecord(sl.ev_compute, compute));
+        // copy-out stream: D2H of the results
+        CMW_CUDA_OK(cudaStreamWaitEvent(s->copy_out, sl.ev_compute, 0));
+        if (out_pinned) {
+            CMW_CUDA_OK(cudaMemcpyAsync(out_scores_host, dev + io.q_bytes, (size_t)batch * k * sizeof(float),
+                                        cudaMemcpyDeviceToHost, s->copy_out));
+            CMW_CUDA_OK(cudaMemcpyAsync(out_ids_host, dev + io.q_bytes + io.sc_bytes, (size_t)batch * k * sizeof(int64_t),
+                                        cudaMemcpyDeviceToHost, s->copy_out));
+            CMW_CUDA_OK(cudaMemcpyAsync(pin + io.q_bytes + io.sc_bytes + io.id_bytes,
+                                        dev + io.q_bytes + io.sc_bytes + io.id_bytes, io.fl_bytes, cudaMemcpyDeviceToHost,
+                                        s->copy_out));
         } else {
-            // one D2H for scores + ids + flags (contiguous in dev_io)
-            CMW_CUDA_OK(cudaMemcpyAsync(pin + q_bytes, dev + q_bytes, sc_bytes + id_bytes + fl_bytes,
-                                        cudaMemcpyDeviceToHost, stream));
+            CMW_CUDA_OK(cudaMemcpyAsync(pin + io.q_bytes, dev + io.q_bytes, io.sc_bytes + io.id_bytes + io.fl_bytes,
+                                        cudaMemcpyDeviceToHost, s->copy_out));
         }
-        CMW_CUDA_OK(cudaStreamSynchronize(stream));
+        CMW_CUDA_OK(cudaEventRecord(sl.ev_done, s->copy_out));
         return 0;
     };
-
-    if ((rc = run(queries_host, batch, mode, out_pinned))) return rc;
-    const float* sc = reinterpret_cast<const float*>(pin + q_bytes);
-    const int64_t* id = reinterpret_cast<const int64_t*>(pin + q_bytes + sc_bytes);
-    const int32_t* fl = reinterpret_cast<const int32_t*>(pin + q_bytes + sc_bytes + id_bytes);
-    if (!out_pinned) {
-        memcpy(out_scores_host, sc, (size_t)batch * k * sizeof(float));
-        memcpy(out_ids_host, id, (size_t)batch * k * sizeof(int64_t));
+    if ((rc = enqueue())) {
+        // part of the chain may already be queued on buffers this slot will hand out again: drain it
+        cudaStreamSynchronize(s->copy_in);
+        cudaStreamSynchronize(compute);
+        cudaStreamSynchronize(s->copy_out);
+        return rc;
     }
-    std::vector<int> redo;
-    for (int b = 0; b < batch; ++b) {
-        if (out_flags_host) out_flags_host[b] = fl[b];
-        if (fl[b] & CMW_FLAG_UNCERTIFIED) redo.push_back(b);
-    }
-    // Repair chain for flagged queries (a failed certificate: many scores within eps of the k-th; or a
-    // pool overflow: adversarial row order).  Each stage re-runs only the queries still flagged, batched:
-    //   1. the same filter with the largest K' (1024) on the overflow-proof slab schedule -- a handful
-    //      of milliseconds whatever the number of queries when the filter is K2;
-    //   2. (exact mode) the fp32 scan filter, certificate bound three orders of magnitude tighter, also
-    //      with the largest K' and the overflow-proof schedule.
-    // bf16 mode can only be flagged by an overflow: stage 1 settles it.
-    const bool exact = (mode & 0xff) == CMW_MODE_F32_EXACT;
-    const bool first_was_gemm = use_gemm(s, batch, mode);
-    int stages[2];
-    int nstage = 0;
-    if (g_opt.repair >= 1 && !((mode & CMW_SLABS_SAFE) && (mode & CMW_KPRIME_MAX)))
-        stages[nstage++] = mode | CMW_SLABS_SAFE | CMW_KPRIME_MAX;
-    if (g_opt.repair >= 2 && exact && first_was_gemm)
-        stages[nstage++] = CMW_MODE_F32_EXACT | CMW_ALGO_SCAN | CMW_SLABS_SAFE | CMW_KPRIME_MAX;
-    for (int st = 0; st < nstage && !redo.empty(); ++st) {
-        std::vector<float> q2((size_t)redo.size() * s->dim);
-        for (size_t i = 0; i < redo.size(); ++i)
-            memcpy(q2.data() + i * s->dim, queries_host + (size_t)redo[i] * s->dim,
-                   (size_t)s->dim * sizeof(float));
-        if ((rc = run(q2.data(), (int)redo.size(), stages[st], false))) return rc;
-        std::vector<int> still;
-        for (size_t i = 0; i < redo.size(); ++i) {
-            const int b = redo[i];
-            memcpy(out_scores_host + (size_t)b * k, sc + i * k, (size_t)k * sizeof(float));
-            memcpy(out_ids_host + (size_t)b * k, id + i * k, (size_t)k * sizeof(int64_t));
-            if (out_flags_host) out_flags_host[b] = fl[i];
-            if (fl[i] & CMW_FLAG_UNCERTIFIED) still.push_back(b);
-        }
-        redo.swap(still);
-    }
+    sl.q_host = queries_host;
+    sl.batch = batch;
+    sl.k = k;
+    sl.metric = metric;
+    sl.mode = mode;
+    sl.out_scores = out_scores_host;
+    sl.out_ids = out_ids_host;
+    sl.out_flags = out_flags_host;
+    sl.out_pinned = out_pinned;
+    sl.busy = true;
+    *ticket_out = slot_no;
     return 0;
+}
+
+int cmw_search_host_wait(cmw_store* h, int ticket) {
+    CMW_REQUIRE(h != nullptr, "cmw_search_host_wait: store is NULL");
+    Store* s = reinterpret_cast<Store*>(h);
+    CMW_REQUIRE(ticket >= 0 && ticket < kHostSlots, "cmw_search_host_wait: bad ticket %d", ticket);
+    HostSlot& sl = s->slots[ticket];
+    cudaEvent_t done;
+    {
+        std::lock_guard<std::mutex> host_lock(s->host_mu);
+        CMW_REQUIRE(sl.busy, "cmw_search_host_wait: ticket %d is not in flight", ticket);
+        done = sl.ev_done;
+    }
+    // wait outside the lock: other threads may submit (or wait for other tickets) meanwhile
+    CMW_CUDA_OK(cudaSetDevice(s->device));
+    cudaError_t e = cudaEventSynchronize(done);
+    std::lock_guard<std::mutex> host_lock(s->host_mu);
+    sl.busy = false;
+    if (e != cudaSuccess) {
+        set_error("cmw_search_host_wait: %s", cudaGetErrorString(e));
+        return -2;
+    }
+    const HostIo io = host_io(s, sl.batch, sl.k);
+    const uint8_t* pin = reinterpret_cast<const uint8_t*>(sl.pinned);
+    if (!sl.out_pinned) {
+        memcpy(sl.out_scores, pin + io.q_bytes, (size_t)sl.batch * sl.k * sizeof(float));
+        memcpy(sl.out_ids, pin + io.q_bytes + io.sc_bytes, (size_t)sl.batch * sl.k * sizeof(int64_t));
+    }
+    const int32_t* fl = reinterpret_cast<const int32_t*>(pin + io.q_bytes + io.sc_bytes + io.id_bytes);
+    bool any = false;
+    for (int b = 0; b < sl.batch && !any; ++b) any = (fl[b] & CMW_FLAG_UNCERTIFIED) != 0;
+    if (!any || g_opt.repair < 1) {
+        if (sl.out_flags) memcpy(sl.out_flags, fl, (size_t)sl.batch * sizeof(int32_t));
+        return 0;
+    }
+    // rare: flagged queries go through the blocking repair chain on the compute stream (in order behind
+    // whatever has been submitted since)
+    cudaStream_t stream;
+    int rc = get_stream(s, &stream);
+    if (rc) return rc;
+    if ((rc = ensure_blocking_buffers(h, s, io, sl.batch, sl.k, sl.mode))) return rc;
+    return repair_flagged(h, s, stream, io, sl.q_host, sl.batch, sl.k, sl.metric, sl.mode, sl.out_scores, sl.out_ids,
+                          sl.out_flags, fl);
 }
 
 }  // extern "C"

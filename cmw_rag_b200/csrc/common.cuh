@@ -65,6 +65,27 @@ struct Pool {
 // per-row multiplier selector (see store.cu): which array turns a raw dot into the filter score
 enum RowMul : int { ROWMUL_INV_NORM = 0, ROWMUL_NORM = 1, ROWMUL_LIVE = 2 };
 
+// One in-flight ticket of the pipelined host API (cmw_search_host_submit / _wait): its own pinned staging
+// block, device I/O block and search workspace, plus the events that chain copy-in -> compute -> copy-out.
+constexpr int kHostSlots = 4;
+struct HostSlot {
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    void* dev_io = nullptr;
+    size_t dev_io_bytes = 0;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    cudaEvent_t ev_in = nullptr, ev_compute = nullptr, ev_done = nullptr;
+    bool busy = false;
+    // the request, kept for cmw_search_host_wait
+    const float* q_host = nullptr;
+    int batch = 0, k = 0, metric = 0, mode = 0;
+    float* out_scores = nullptr;
+    int64_t* out_ids = nullptr;
+    int32_t* out_flags = nullptr;
+    bool out_pinned = false;
+};
+
 struct Store {
     int device = 0;
     int dim = 0;
@@ -91,6 +112,9 @@ struct Store {
     size_t dev_io_bytes = 0;
     void* ws = nullptr;
     size_t ws_bytes = 0;
+    // pipelined host API: copy streams either side of `stream` (the compute stream) and the ticket slots
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    HostSlot slots[kHostSlots];
     // TMA descriptor of the bf16 tiles (K2), encoded at create time
     alignas(64) CUtensorMap tmap_bf16;
     bool tmap_ok = false;

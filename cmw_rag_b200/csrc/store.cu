@@ -280,6 +280,18 @@ int cmw_store_destroy(cmw_store* h) {
     Store* s = reinterpret_cast<Store*>(h);
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->copy_in) cudaStreamSynchronize(s->copy_in);
+    if (s->copy_out) cudaStreamSynchronize(s->copy_out);
+    for (HostSlot& sl : s->slots) {
+        cudaFree(sl.dev_io);
+        cudaFree(sl.ws);
+        if (sl.pinned) cudaFreeHost(sl.pinned);
+        if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+        if (sl.ev_compute) cudaEventDestroy(sl.ev_compute);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
+    if (s->copy_in) cudaStreamDestroy(s->copy_in);
+    if (s->copy_out) cudaStreamDestroy(s->copy_out);
     cudaFree(s->f32);
     cudaFree(s->bf16);
     cudaFree(s->inv_norm);

@@ -71,6 +71,7 @@ class DenseStore:
         self.capacity = int(capacity)
         self.id_offset = int(id_offset)
         self._ws = {}
+        self._tickets = {}
 
     # -- lifecycle ---------------------------------------------------------------------------
     def close(self) -> None:
@@ -216,6 +217,38 @@ class DenseStore:
                                         flags.ctypes.data),
                 "cmw_search_host",
             )
+        return scores, ids, flags
+
+    def search_host_submit(self, queries, k: int, metric="cosine", mode="f32", algo=None, out=None) -> int:
+        """Pipelined form of :meth:`search_host`: enqueue H2D -> search -> D2H and return a ticket at once.
+        Up to ``N.HOST_SLOTS`` tickets may be in flight; the copies of one overlap the kernels of the
+        others.  :meth:`search_host_wait` returns the (scores, ids, flags) arrays of a ticket."""
+        q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
+        assert q.shape[1] == self.dim and q.shape[0] > 0
+        b = q.shape[0]
+        if out is not None:
+            scores, ids, flags = out
+            assert scores.shape == (b, k) and scores.dtype == np.float32 and scores.flags.c_contiguous
+            assert ids.shape == (b, k) and ids.dtype == np.int64 and ids.flags.c_contiguous
+            assert flags.shape == (b,) and flags.dtype == np.int32
+        else:
+            scores = np.empty((b, k), np.float32)
+            ids = np.empty((b, k), np.int64)
+            flags = np.zeros((b,), np.int32)
+        ticket = ctypes.c_int(-1)
+        N.check(
+            N.lib().cmw_search_host_submit(self._h, q.ctypes.data, b, k, N.METRICS[metric], self._mode(mode, algo),
+                                           scores.ctypes.data, ids.ctypes.data, flags.ctypes.data,
+                                           ctypes.byref(ticket)),
+            "cmw_search_host_submit",
+        )
+        # the library reads `q` and writes the outputs until the wait: keep them alive with the ticket
+        self._tickets[ticket.value] = (q, scores, ids, flags)
+        return ticket.value
+
+    def search_host_wait(self, ticket: int):
+        q, scores, ids, flags = self._tickets.pop(ticket)
+        N.check(N.lib().cmw_search_host_wait(self._h, int(ticket)), "cmw_search_host_wait")
         return scores, ids, flags
 
     # -- multi-vector reduction (K4) -----------------------------------------------------------------

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CMW_ABI_VERSION 3
+#define CMW_ABI_VERSION 4
 
 /* metric -- rag_engine/storage/vector_store.py:48-51 fixes the collection to cosine
  * ({"hnsw:space": "cosine"}); inner product is the north star's second metric. */
@@ -114,6 +114,21 @@ int cmw_search(cmw_store* s, const float* queries_dev, int batch, int k, int met
  * H2D of the queries, search, D2H of the results, synchronises before returning. */
 int cmw_search_host(cmw_store* s, const float* queries_host, int batch, int k, int metric, int mode,
                     float* out_scores_host, int64_t* out_ids_host, int32_t* out_flags_host);
+
+/* Pipelined form of cmw_search_host for callers that keep several requests in flight -- the reference does
+ * (S concurrent awaits per request: rag_engine/retrieval/retriever.py:179-182; concurrent requests:
+ * rag_engine/config/settings.py:166).  submit enqueues H2D (copy-in stream) -> search (the store's compute
+ * stream, in order over all tickets) -> D2H (copy-out stream) and returns a ticket without waiting, so the
+ * copies of one ticket overlap the kernels of its neighbours; wait blocks until that ticket's results are in
+ * the caller's buffers (and runs the repair chain for flagged queries).  At most CMW_HOST_SLOTS tickets per
+ * store are in flight: a further submit fails with -4 until one is waited for.  The query and output buffers
+ * must stay valid and untouched from submit to wait.  Page-locked buffers are used for DMA directly, pageable
+ * ones are staged.  Thread-safe; tickets may be waited for in any order, each exactly once. */
+#define CMW_HOST_SLOTS 4
+int cmw_search_host_submit(cmw_store* s, const float* queries_host, int batch, int k, int metric, int mode,
+                           float* out_scores_host, int64_t* out_ids_host, int32_t* out_flags_host,
+                           int* ticket_out);
+int cmw_search_host_wait(cmw_store* s, int ticket);
 
 /* ---- multi-vector reduction: replaces the Python loops of
  *      rag_engine/retrieval/retriever.py:185-194 (ordered union, first-seen dedup),

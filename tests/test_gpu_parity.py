@@ -563,6 +563,78 @@ def test_repair_chain_on_near_duplicates(torch_cuda):
     st.close()
 
 
+def test_pipelined_host_api_matches_blocking(cfg1):
+    """cmw_search_host_submit / _wait: several tickets in flight (pageable and page-locked buffers mixed,
+    different batch sizes), waited for out of order, must return exactly what the blocking call returns."""
+    from cmw_rag_b200 import _native as N
+    from cmw_rag_b200.engine import pinned_empty
+
+    st, q = cfg1["store"], cfg1["q"]
+    parts = [q[:64], q[:1], q[5:38], q[10:26]]
+    outs = [None, (pinned_empty((1, 20), np.float32), pinned_empty((1, 20), np.int64), np.zeros((1,), np.int32)), None, None]
+    qin = [parts[0], parts[1], None, parts[3]]
+    qin[2] = pinned_empty(parts[2].shape, np.float32)
+    qin[2][:] = parts[2]
+    tickets = [st.search_host_submit(qin[i], 20, mode="f32", out=outs[i]) for i in range(4)]
+    assert sorted(tickets) == list(range(N.HOST_SLOTS))
+    with pytest.raises(N.NativeError, match="slots are in flight"):
+        st.search_host_submit(parts[0], 20, mode="f32")
+    for i in (2, 0, 3, 1):
+        sc, ids, fl = st.search_host_wait(tickets[i])
+        lo = [0, 0, 5, 10][i]
+        _check_exact(ids, sc, cfg1["ref_ids"][lo:lo + len(parts[i])], cfg1["ref_sc"][lo:lo + len(parts[i])])
+        assert (fl == 0).all()
+        if outs[i] is not None:
+            assert ids is outs[i][1]
+    with pytest.raises(N.NativeError, match="not in flight"):
+        N.check(N.lib().cmw_search_host_wait(st._h, 0), "cmw_search_host_wait")
+    # a steady pipeline: depth 2, 12 requests
+    from collections import deque
+
+    pending, done = deque(), 0
+    for step in range(12):
+        if len(pending) == 2:
+            sc, ids, fl = st.search_host_wait(pending.popleft())
+            _check_exact(ids, sc, cfg1["ref_ids"], cfg1["ref_sc"])
+            done += 1
+        pending.append(st.search_host_submit(q, 20, mode="f32"))
+    while pending:
+        sc, ids, fl = st.search_host_wait(pending.popleft())
+        _check_exact(ids, sc, cfg1["ref_ids"], cfg1["ref_sc"])
+        done += 1
+    assert done == 12
+    # and the blocking call still works next to it
+    sc, ids, fl = st.search_host(q, 20, mode="f32")
+    _check_exact(ids, sc, cfg1["ref_ids"], cfg1["ref_sc"])
+
+
+def test_pipelined_host_api_repairs_flagged_queries(torch_cuda):
+    """A ticket whose queries fail the certificate goes through the repair chain inside the wait."""
+    from cmw_rag_b200 import DenseStore
+
+    n, d, k = 20000, 256, 20
+    c = synth.make_corpus(n, d, seed=31, ties=False)
+    rng = np.random.default_rng(2)
+    base = c[7].copy()
+    noise = rng.standard_normal((600, d)).astype(np.float32)
+    c[1000:1600] = base[None, :] + 2e-4 * noise / np.sqrt(d)
+    c[1000:1600] /= np.linalg.norm(c[1000:1600].astype(np.float64), axis=1, keepdims=True).astype(np.float32)
+    q = np.stack([base + 0.05 * rng.standard_normal(d).astype(np.float32) / np.sqrt(d) for _ in range(8)])
+    q2, _ = synth.make_queries(c, 8, seed=4, tie_probe=False)
+    q = np.concatenate([q, q2]).astype(np.float32)
+    st = DenseStore(d, n)
+    st.append(c)
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, k)
+    t0 = st.search_host_submit(q, k, mode="f32", algo="gemm")
+    t1 = st.search_host_submit(q[8:], k, mode="f32", algo="gemm")
+    sc, ids, fl = st.search_host_wait(t0)
+    _check_exact(ids, sc, ref_ids, ref_sc)
+    assert (fl == 0).all()
+    sc, ids, fl = st.search_host_wait(t1)
+    _check_exact(ids, sc, ref_ids[8:], ref_sc[8:])
+    st.close()
+
+
 def test_pure_c_client(tmp_path):
     """The C-ABI boundary used from plain C (examples/c_client.c): no CUDA headers, no Python objects."""
     import subprocess
