@@ -157,7 +157,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccStride);
             uint64_t* rel = &tmem_empty[acc];
-            epilogue_item(p, taddr, row_warp0, lane, q0, ncols, stg,
+            epilogue_item(p, taddr, row_warp0, lane, q0, ncols, p.nt, stg, kStageCap,
                           [rel, lane]() { if (lane == 0) ptx::mbar_arrive(rel); });
         }
     }

@@ -83,7 +83,8 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 
 }  // namespace ptx2
 
-constexpr int kGemm2Threads = 192;
+constexpr int kGemm2Threads = 320;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kGemm2EpiWarps = 8;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -118,7 +119,7 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tmem_full[s], 1);   // multicast tcgen05.commit
-            ptx::mbar_init(&tmem_empty[s], 8);  // 4 epilogue warps x 2 CTAs
+            ptx::mbar_init(&tmem_empty[s], 2 * kGemm2EpiWarps);  // 8 epilogue warps x 2 CTAs
         }
         ptx::fence_barrier_init();
     }
@@ -199,9 +200,14 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5 of both CTAs) =====================
+        // ===================== epilogue (warps 2..9 of both CTAs) =====================
+        // Two warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31): warps 2-5 take the
+        // first half of the query columns, warps 6-9 the second.  With one epilogue warp per scheduler the
+        // epilogue ran at ~0.2 IPC (every dependent-issue latency exposed) and took as long as the MMAs of a
+        // tile; two warps per scheduler hide each other's latencies.
         const int quarter = warp & 3;
-        uint2* stg = stage_buf + (size_t)(warp - 2) * kStageCap;
+        const int half = (warp - 2) >> 2;
+        uint2* stg = stage_buf + (size_t)(warp - 2) * kStageCap2;
         int it = 0;
         for (int item = cid; item < n_items; item += ncl, ++it) {
             const int tile = item / p.n_groups;
@@ -210,14 +216,16 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             const int64_t row_warp0 =
                 p.row_begin + (int64_t)tile * (2 * kTileM) + (int64_t)rank * kTileM + quarter * 32;
-            const int q0 = group * p.nt;
+            const int q0 = group * p.nt + half * half_nt;
             int ncols = p.batch - q0;
-            if (ncols > p.nt) ncols = p.nt;
+            if (ncols > half_nt) ncols = half_nt;
+            if (ncols < 0) ncols = 0;
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccStride);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                   (uint32_t)(acc * kAccStride + half * half_nt);
             uint64_t* rel = &tmem_empty[acc];
-            epilogue_item(p, taddr, row_warp0, lane, q0, ncols, stg,
+            epilogue_item(p, taddr, row_warp0, lane, q0, ncols, half_nt, stg, kStageCap2,
                           [rel, lane]() { if (lane == 0) ptx2::mbar_arrive_cluster(rel, 0); });
         }
     }
@@ -240,14 +248,14 @@ int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
     p.dim = s->dim;
     p.num_kb = (s->dim + kBlockK - 1) / kBlockK;
     p.nt = a.bpad < kMaxNT ? a.bpad : kMaxNT;
-    CMW_REQUIRE(p.nt % 32 == 0 && a.bpad % p.nt == 0, "launch_gemm_2cta: bad query padding %d", a.bpad);
+    CMW_REQUIRE(p.nt % 64 == 0 && a.bpad % p.nt == 0, "launch_gemm_2cta: bad query padding %d", a.bpad);
     p.n_groups = a.bpad / p.nt;
     p.batch = a.batch;
     p.row_begin = a.row_begin;
     p.row_end = a.row_end;
     p.n_tiles = (int)((a.row_end - a.row_begin + 2 * kTileM - 1) / (2 * kTileM));
     p.stage_bytes = kABytes + (p.nt / 2) * kBlockK * 2;
-    const size_t tail = (2 * kMaxStages + 4) * sizeof(uint64_t) + 64 + 4 * kStageCap * sizeof(uint2);
+    const size_t tail = (2 * kMaxStages + 4) * sizeof(uint64_t) + 64 + kGemm2EpiWarps * kStageCap2 * sizeof(uint2);
     int nst = (int)((220 * 1024 - tail - 1024) / (size_t)p.stage_bytes);
     if (nst > kMaxStages) nst = kMaxStages;
     p.nstages = nst;

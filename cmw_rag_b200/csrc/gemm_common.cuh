@@ -14,7 +14,8 @@ constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KB
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;      // TMEM columns per accumulator stage
-constexpr int kStageCap = 512;       // staged survivors per epilogue warp (8 bytes each)
+constexpr int kStageCap = 512;       // staged survivors per epilogue warp (8 bytes each), 1-CTA kernel
+constexpr int kStageCap2 = 256;      // same, CTA-pair kernel (8 epilogue warps, 128 columns each)
 
 struct GemmParams {
     int dim;
@@ -74,9 +75,12 @@ __device__ __forceinline__ void flush_staged(const uint2* stg, int wcount, int l
 // and the rare survivors are staged in the warp's shared-memory buffer (ballot + popc, no atomics).
 // `release()` is called once every tcgen05.ld of this accumulator has completed -- before the
 // global-atomic flush, so the MMA warp gets the accumulator back as early as possible.
+// `nt_local` = TMEM columns this warp owns from `taddr` on (the whole query group, or half of it when two
+// warps share a lane quarter), `ncols` <= nt_local of them are real queries; `stage_cap` = entries in `stg`.
 template <typename Release>
 __device__ __forceinline__ void epilogue_item(const GemmParams& p, uint32_t taddr, int64_t row_warp0, int lane,
-                                              int q0, int ncols, uint2* stg, Release release) {
+                                              int q0, int ncols, int nt_local, uint2* stg, int stage_cap,
+                                              Release release) {
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const int64_t row = row_warp0 + lane;
     const bool row_ok = row < p.row_end;
@@ -84,7 +88,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, uint32_t tadd
     int wcount = 0;  // survivors staged by this warp (warp-uniform)
     for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
-        const bool wide = (p.nt - c0 >= 32);
+        const bool wide = (nt_local - c0 >= 32);
         if (wide) {
             ptx::tmem_ld_32x32(taddr + (uint32_t)c0, v);
         } else {
@@ -140,7 +144,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, uint32_t tadd
                         }
                         wcount += __popc(m);
                     }
-                    if (wcount > kStageCap - 128) {
+                    if (wcount > stage_cap - 128) {
                         flush_staged(stg, wcount, lane, row_warp0, p);
                         wcount = 0;
                     }
