@@ -47,12 +47,15 @@ def main():
     tk = [st.search_host_submit(q_host, k, out=outs[i]) for i in range(N.HOST_SLOTS)]
     for t in tk:
         st.search_host_wait(t)
+    time.sleep(1.0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         st.search_host(q_host, k, out=outs[0])
     blocking_ms = (time.perf_counter() - t0) / args.steps * 1e3
     print(json.dumps({"api": "cmw_search_host", "ms_per_step": blocking_ms, "qps": B / blocking_ms * 1e3}), flush=True)
-    for depth in range(1, N.HOST_SLOTS + 1):
+    for overlap, depth in [(o, d) for o in (0, 1) for d in range(1, N.HOST_SLOTS + 1)]:
+        N.set_option("host_overlap", overlap)
+        time.sleep(1.0)  # every configuration starts from an idle (cool) GPU
         pending = deque()
         trace = []
         t0 = time.perf_counter()
@@ -67,7 +70,7 @@ def main():
             trace.append(("w", round((time.perf_counter() - t0) * 1e3, 2)))
         ms = (time.perf_counter() - t0) / args.steps * 1e3
         ok = all((o[1] == ref).all() for o in outs[:depth])
-        line = {"api": "cmw_search_host_submit/_wait", "in_flight": depth, "ms_per_step": ms, "qps": B / ms * 1e3,
+        line = {"api": "cmw_search_host_submit/_wait", "host_overlap": overlap, "in_flight": depth, "ms_per_step": ms, "qps": B / ms * 1e3,
                 "results_ok": bool(ok)}
         if args.trace:
             line["trace_ms"] = trace

@@ -355,9 +355,16 @@ size_t cmw_search_workspace_bytes(const cmw_store* h, int batch, int k, int mode
     return ws_layout(s->dim, batch, kMaxKPrime).total;
 }
 
-int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int metric, int mode,
-               float* out_scores_dev, int64_t* out_ids_dev, double* out_scores64_dev,
-               int32_t* out_flags_dev, void* ws_dev, size_t ws_bytes, void* stream_v) {
+}  // extern "C"
+
+// The search itself.  `fin_stream` == `stream`: everything in order on one stream (the public cmw_search).
+// Otherwise the finalisation (fp64 rescoring + selection, or emit) is forked onto `fin_stream` behind
+// `fork_ev`, so that the caller may put the next search's filter on `stream` right away: the rescoring is an
+// HBM gather that needs no shared memory or TMEM and runs next to the persistent tensor-core filter CTAs.
+static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k, int metric, int mode,
+                       float* out_scores_dev, int64_t* out_ids_dev, double* out_scores64_dev,
+                       int32_t* out_flags_dev, void* ws_dev, size_t ws_bytes, cudaStream_t stream,
+                       cudaStream_t fin_stream, cudaEvent_t fork_ev) {
     CMW_REQUIRE(h != nullptr, "cmw_search: store is NULL");
     Store* s = reinterpret_cast<Store*>(h);
     if (batch == 0) return 0;
@@ -375,7 +382,6 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
     if (base_mode == CMW_MODE_BF16)
         CMW_REQUIRE(s->bf16 != nullptr, "cmw_search: CMW_MODE_BF16 needs a CMW_STORE_BF16 store");
     CMW_CUDA_OK(cudaSetDevice(s->device));
-    cudaStream_t stream = (cudaStream_t)stream_v;
 
     const bool gemm = use_gemm(s, batch, mode);
     if ((mode & 0xff00) == CMW_ALGO_GEMM)
@@ -488,7 +494,11 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
         }
     }
 
-    PhaseTimer tfin(2, stream);
+    if (fin_stream != stream) {
+        CMW_CUDA_OK(cudaEventRecord(fork_ev, stream));
+        CMW_CUDA_OK(cudaStreamWaitEvent(fin_stream, fork_ev, 0));
+    }
+    PhaseTimer tfin(2, fin_stream);
     if (base_mode == CMW_MODE_F32_EXACT) {
         CertParams cert;
         cert.eps_fixed = g_opt.f32_eps;
@@ -504,10 +514,20 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
         cert.metric = metric;
         return launch_rescore_select(s, pool, batch, k, kprime, metric, queries_dev, cert, exact,
                                      out_scores_dev, out_ids_dev, out_scores64_dev, out_flags_dev,
-                                     stream);
+                                     fin_stream);
     }
     return launch_pool_emit(s, pool, batch, k, out_scores_dev, out_ids_dev, out_scores64_dev,
-                            out_flags_dev, stream);
+                            out_flags_dev, fin_stream);
+}
+
+extern "C" {
+
+int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int metric, int mode,
+               float* out_scores_dev, int64_t* out_ids_dev, double* out_scores64_dev,
+               int32_t* out_flags_dev, void* ws_dev, size_t ws_bytes, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    return search_impl(h, queries_dev, batch, k, metric, mode, out_scores_dev, out_ids_dev, out_scores64_dev,
+                       out_flags_dev, ws_dev, ws_bytes, stream, stream, nullptr);
 }
 
 int cmw_search_host(cmw_store* h, const float* queries_host, int batch, int k, int metric, int mode,
@@ -566,6 +586,10 @@ int cmw_search_host_submit(cmw_store* h, const float* queries_host, int batch, i
     if (rc) return rc;
     if (s->copy_in == nullptr) CMW_CUDA_OK(cudaStreamCreateWithFlags(&s->copy_in, cudaStreamNonBlocking));
     if (s->copy_out == nullptr) CMW_CUDA_OK(cudaStreamCreateWithFlags(&s->copy_out, cudaStreamNonBlocking));
+    if (s->tail == nullptr) CMW_CUDA_OK(cudaStreamCreateWithFlags(&s->tail, cudaStreamNonBlocking));
+    if (sl.ev_fork == nullptr) CMW_CUDA_OK(cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming));
+    const bool overlap_tail = g_opt.host_overlap != 0;
+    cudaStream_t fin = overlap_tail ? s->tail : compute;
     if (sl.ev_in == nullptr) CMW_CUDA_OK(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
     if (sl.ev_compute == nullptr) CMW_CUDA_OK(cudaEventCreateWithFlags(&sl.ev_compute, cudaEventDisableTiming));
     if (sl.ev_done == nullptr) CMW_CUDA_OK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
@@ -588,14 +612,16 @@ int cmw_search_host_submit(cmw_store* h, const float* queries_host, int batch, i
             return -2;
         }
         CMW_CUDA_OK(cudaEventRecord(sl.ev_in, s->copy_in));
-        // compute stream (in order over all tickets and blocking calls of this store)
         CMW_CUDA_OK(cudaStreamWaitEvent(compute, sl.ev_in, 0));
-        rc = cmw_search(h, reinterpret_cast<const float*>(dev), batch, k, metric, mode,
-                        reinterpret_cast<float*>(dev + io.q_bytes), reinterpret_cast<int64_t*>(dev + io.q_bytes + io.sc_bytes),
-                        nullptr, reinterpret_cast<int32_t*>(dev + io.q_bytes + io.sc_bytes + io.id_bytes), sl.ws,
-                        sl.ws_bytes, compute);
+        // filter phases on the compute stream (in order over all tickets and blocking calls of this store);
+        // the finalisation on the tail stream, where it overlaps the next ticket's filter
+        rc = search_impl(h, reinterpret_cast<const float*>(dev), batch, k, metric, mode,
+                         reinterpret_cast<float*>(dev + io.q_bytes),
+                         reinterpret_cast<int64_t*>(dev + io.q_bytes + io.sc_bytes), nullptr,
+                         reinterpret_cast<int32_t*>(dev + io.q_bytes + io.sc_bytes + io.id_bytes), sl.ws, sl.ws_bytes,
+                         compute, fin, sl.ev_fork);
         if (rc) return rc;
-        CMW_CUDA_OK(cudaEventRecord(sl.ev_compute, compute));
+        CMW_CUDA_OK(cudaEventRecord(sl.ev_compute, fin));
         // copy-out stream: D2H of the results
         CMW_CUDA_OK(cudaStreamWaitEvent(s->copy_out, sl.ev_compute, 0));
         if (out_pinned) {
@@ -617,6 +643,7 @@ int cmw_search_host_submit(cmw_store* h, const float* queries_host, int batch, i
         // part of the chain may already be queued on buffers this slot will hand out again: drain it
         cudaStreamSynchronize(s->copy_in);
         cudaStreamSynchronize(compute);
+        cudaStreamSynchronize(s->tail);
         cudaStreamSynchronize(s->copy_out);
         return rc;
     }

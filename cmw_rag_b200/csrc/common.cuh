@@ -75,7 +75,7 @@ struct HostSlot {
     size_t dev_io_bytes = 0;
     void* ws = nullptr;
     size_t ws_bytes = 0;
-    cudaEvent_t ev_in = nullptr, ev_compute = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_fork = nullptr, ev_compute = nullptr, ev_done = nullptr;
     bool busy = false;
     // the request, kept for cmw_search_host_wait
     const float* q_host = nullptr;
@@ -114,6 +114,7 @@ struct Store {
     size_t ws_bytes = 0;
     // pipelined host API: copy streams either side of `stream` (the compute stream) and the ticket slots
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaStream_t tail = nullptr;  // finalisation of a ticket, next to the following ticket's filter
     HostSlot slots[kHostSlots];
     // TMA descriptor of the bf16 tiles (K2), encoded at create time
     alignas(64) CUtensorMap tmap_bf16;
@@ -149,6 +150,9 @@ struct Options {
     // K' - k straddling the k-th place stay flagged whatever the stage -- the ids are still the lowest of
     // the tie by construction -- so tie-heavy corpora may prefer 1.
     double repair = 2;
+    // pipelined host API: 1 = a ticket's finalisation (fp64 rescoring + selection) runs on its own stream next
+    // to the following ticket's filter; 0 = every ticket strictly after the previous one
+    double host_overlap = 0;
     double slab_growth = 0;   // 0 = automatic ((cap - K') / (3 K'), at most 8); else the fixed growth factor
 };
 extern Options g_opt;

@@ -31,9 +31,10 @@
 
 namespace cmw {
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 192;      // TMA warp, MMA warp, 4 epilogue warps
+constexpr int kGemmThreadsWide = 320;  // ... 8 epilogue warps (query groups of 128+ columns)
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreadsWide, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -48,9 +49,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    uint2* stage_buf = reinterpret_cast<uint2*>(tmem_empty + 4);  // [4 warps][kStageCap] survivors
+    uint2* stage_buf = reinterpret_cast<uint2*>(tmem_empty + 4);  // [4][kStageCap] or [8][kStageCap2] survivors
 
     const int n_items = p.n_tiles * p.n_groups;
+    const int n_epi = (int)(blockDim.x >> 5) - 2;  // 4, or 8 = two warps per TMEM lane quarter
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmap_a);
@@ -61,7 +63,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tmem_full[s], 1);
-            ptx::mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+            ptx::mbar_init(&tmem_empty[s], (uint32_t)n_epi);  // one arrive per epilogue warp
         }
         ptx::fence_barrier_init();
     }
@@ -140,9 +142,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter + 32) belong to this warp
-        uint2* stg = stage_buf + (size_t)(warp - 2) * kStageCap;
+        // ===================== epilogue (warps 2..5, or 2..9) =====================
+        // TMEM lanes [32*quarter, 32*quarter + 32) belong to this warp.  With 8 epilogue warps, two share a
+        // quarter and split the query columns (see gemm2.cu: one epilogue warp per scheduler runs at ~0.2 IPC).
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int nt_local = (n_epi == 8) ? (p.nt >> 1) : p.nt;
+        const int stage_cap = (n_epi == 8) ? kStageCap2 : kStageCap;
+        uint2* stg = stage_buf + (size_t)(warp - 2) * stage_cap;
         int it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int tile = item / p.n_groups;
@@ -150,14 +157,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             const int64_t row_warp0 = p.row_begin + (int64_t)tile * kTileM + quarter * 32;
-            const int q0 = group * p.nt;
-            int ncols = p.batch - q0;  // real (unpadded) queries in this group
-            if (ncols > p.nt) ncols = p.nt;
+            const int q0 = group * p.nt + half * nt_local;
+            int ncols = p.batch - q0;  // real (unpadded) queries in this warp's columns
+            if (ncols > nt_local) ncols = nt_local;
+            if (ncols < 0) ncols = 0;
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccStride);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                   (uint32_t)(acc * kAccStride + half * nt_local);
             uint64_t* rel = &tmem_empty[acc];
-            epilogue_item(p, taddr, row_warp0, lane, q0, ncols, p.nt, stg, kStageCap,
+            epilogue_item(p, taddr, row_warp0, lane, q0, ncols, nt_local, stg, stage_cap,
                           [rel, lane]() { if (lane == 0) ptx::mbar_arrive(rel); });
         }
     }
@@ -262,7 +271,9 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     }
     const int n_items = p.n_tiles * p.n_groups;
     const int grid = n_items < s->sm_count ? n_items : s->sm_count;
-    gemm_topk_kernel<<<grid, kGemmThreads, smem, stream>>>(s->tmap_bf16, tmap_b, p);
+    // 8 epilogue warps for the widest query groups (192 or 256 columns): there the 4-warp epilogue of a tile takes as long as streaming its rows from HBM; narrower groups measured no gain
+    const int threads = (p.nt >= 192 && p.nt % 64 == 0) ? kGemmThreadsWide : kGemmThreads;
+    gemm_topk_kernel<<<grid, threads, smem, stream>>>(s->tmap_bf16, tmap_b, p);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;

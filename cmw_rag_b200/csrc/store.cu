@@ -177,6 +177,7 @@ int cmw_set_option(const char* name, double value) {
     else if (!strcmp(name, "slab_growth")) g_opt.slab_growth = value;
     else if (!strcmp(name, "strict_certificate")) g_opt.strict_certificate = value;
     else if (!strcmp(name, "repair")) g_opt.repair = value;
+    else if (!strcmp(name, "host_overlap")) g_opt.host_overlap = value;
     else if (!strcmp(name, "gemm_2cta")) g_opt.gemm_2cta = value;
     else if (!strcmp(name, "gemm_2cta_min_batch")) g_opt.gemm_2cta_min_batch = value;
     else {
@@ -197,6 +198,7 @@ double cmw_get_option(const char* name) {
     if (!strcmp(name, "slab_growth")) return g_opt.slab_growth;
     if (!strcmp(name, "strict_certificate")) return g_opt.strict_certificate;
     if (!strcmp(name, "repair")) return g_opt.repair;
+    if (!strcmp(name, "host_overlap")) return g_opt.host_overlap;
     if (!strcmp(name, "gemm_2cta")) return g_opt.gemm_2cta;
     if (!strcmp(name, "gemm_2cta_min_batch")) return g_opt.gemm_2cta_min_batch;
     if (!strcmp(name, "pool_cap")) return (double)kPoolCap;
@@ -281,17 +283,20 @@ int cmw_store_destroy(cmw_store* h) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->copy_in) cudaStreamSynchronize(s->copy_in);
+    if (s->tail) cudaStreamSynchronize(s->tail);
     if (s->copy_out) cudaStreamSynchronize(s->copy_out);
     for (HostSlot& sl : s->slots) {
         cudaFree(sl.dev_io);
         cudaFree(sl.ws);
         if (sl.pinned) cudaFreeHost(sl.pinned);
         if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+        if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
         if (sl.ev_compute) cudaEventDestroy(sl.ev_compute);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     }
     if (s->copy_in) cudaStreamDestroy(s->copy_in);
     if (s->copy_out) cudaStreamDestroy(s->copy_out);
+    if (s->tail) cudaStreamDestroy(s->tail);
     cudaFree(s->f32);
     cudaFree(s->bf16);
     cudaFree(s->inv_norm);
