@@ -53,6 +53,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     const int n_items = p.n_tiles * p.n_groups;
     const int n_epi = (int)(blockDim.x >> 5) - 2;  // 4, or 8 = two warps per TMEM lane quarter
+    int item_begin, item_end, item_step;
+    item_range(n_items, p.n_groups, (int)blockIdx.x, (int)gridDim.x, item_begin, item_end, item_step);
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmap_a);
@@ -84,7 +86,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t tx_bytes = (uint32_t)(kABytes + p.nt * kBlockK * 2);
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int item = item_begin; item != item_end; item += item_step) {
                 const int tile = item / p.n_groups;
                 const int group = item - tile * p.n_groups;
                 const int row0 = (int)(p.row_begin + (int64_t)tile * kTileM);
@@ -113,7 +115,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        for (int item = item_begin; item != item_end; item += item_step, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
@@ -151,7 +153,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int stage_cap = (n_epi == 8) ? kStageCap2 : kStageCap;
         uint2* stg = stage_buf + (size_t)(warp - 2) * stage_cap;
         int it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        for (int item = item_begin; item != item_end; item += item_step, ++it) {
             const int tile = item / p.n_groups;
             const int group = item - tile * p.n_groups;
             const int acc = it & 1;

@@ -109,6 +109,8 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const int ncl = gridDim.x >> 1;
     const int half_nt = p.nt >> 1;
     const int b_bytes = half_nt * kBlockK * 2;
+    int item_begin, item_end, item_step;
+    item_range(n_items, p.n_groups, cid, ncl, item_begin, item_end, item_step);
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmap_a);
@@ -141,7 +143,7 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const uint32_t pair_bytes = 2u * (uint32_t)(kABytes + b_bytes);
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = cid; item < n_items; item += ncl) {
+            for (int item = item_begin; item != item_end; item += item_step) {
                 const int tile = item / p.n_groups;
                 const int group = item - tile * p.n_groups;
                 const int row0 = (int)(p.row_begin + (int64_t)tile * (2 * kTileM)) + (int)rank * kTileM;
@@ -170,7 +172,7 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int item = cid; item < n_items; item += ncl, ++it) {
+            for (int item = item_begin; item != item_end; item += item_step, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
                 ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
@@ -209,7 +211,7 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int half = (warp - 2) >> 2;
         uint2* stg = stage_buf + (size_t)(warp - 2) * kStageCap2;
         int it = 0;
-        for (int item = cid; item < n_items; item += ncl, ++it) {
+        for (int item = item_begin; item != item_end; item += item_step, ++it) {
             const int tile = item / p.n_groups;
             const int group = item - tile * p.n_groups;
             const int acc = it & 1;

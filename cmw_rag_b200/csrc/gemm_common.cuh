@@ -36,6 +36,21 @@ struct GemmParams {
     const float* pool_thr;
 };
 
+// Which (row tile, query group) items worker `w` of `nw` (a CTA, or a CTA pair) processes; item = tile *
+// n_groups + group: round-robin, so that at any moment the workers are on the same few row tiles (one HBM
+// read per tile, L2 hits for its other query groups; working set ~5 tiles).  Measured alternative (ncu r01h):
+// one contiguous item range per worker -- the re-use then is within a worker, but 74 different row tiles plus
+// the query groups are live at once, the L2 hit rate falls from 93 % to 84 % and DRAM reads rise from 1.66x
+// to 3.5x the corpus per pass.  (The 1.66x itself is drift: since the 8-warp epilogue the workers are no
+// longer paced by a common bottleneck, and late ones find their tile evicted; harmless at 8 % DRAM load.)
+__device__ __forceinline__ void item_range(int n_items, int n_groups, int w, int nw, int& begin, int& end,
+                                           int& step) {
+    (void)n_groups;
+    step = nw;
+    begin = w;
+    end = (w < n_items) ? w + ((n_items - 1 - w) / nw + 1) * nw : w;
+}
+
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     // K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), LBO unused,
     // descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
