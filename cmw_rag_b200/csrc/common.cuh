@@ -142,6 +142,7 @@ struct Options {
     double gemm_enabled = 1;
     double gemm_2cta = 1;            // CTA-pair (cta_group::2) K2 kernel for large batches
     double gemm_2cta_min_batch = 256;
+    double gemm_clc = 1;             // CTA-pair kernel: dynamic item scheduling through cluster launch control
     // 1 = rigorous certificate behind the bf16 filter: eps = 2u(1+u) + fp32 accumulation slack = 4.1e-3
     // (Cauchy-Schwarz over unit vectors, u = 2^-9) and K' = max(512, 4k); ~17 % slower at B=4096
     double strict_certificate = 0;

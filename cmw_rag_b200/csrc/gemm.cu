@@ -254,6 +254,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     if (nst > kMaxStages) nst = kMaxStages;
     p.nstages = nst;
     p.dense = a.dense;
+    p.dynamic = 0;
     // instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     p.row_mul = a.row_mul;

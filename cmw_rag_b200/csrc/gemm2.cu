@@ -81,7 +81,51 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
         : "memory");
 }
 
+// ---- cluster launch control (Blackwell's hardware work-stealing scheduler) -------------------------------
+// The grid holds one cluster per work item; the clusters that are resident cancel the launch of pending
+// ones and do their work themselves.  try_cancel writes a 16-byte response to the same shared-memory offset
+// in every CTA of the cluster and completes 16 transaction bytes on each CTA's mbarrier at `bar`'s offset.
+__device__ __forceinline__ void clc_try_cancel_multicast(void* resp_smem, uint64_t* bar) {
+    asm volatile(
+        "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 "
+        "[%0], [%1];" ::"r"(ptx::smem_u32(resp_smem)),
+        "r"(ptx::smem_u32(bar))
+        : "memory");
+}
+// (valid, first CTA's blockIdx.x of the cancelled cluster); the trailing proxy fence orders this generic read
+// before the async-proxy write of a later response into the same slot
+__device__ __forceinline__ int clc_decode(const void* resp_smem) {
+    uint32_t valid, x;
+    asm volatile(
+        "{\n"
+        ".reg .pred p1;\n"
+        ".reg .b128 r;\n"
+        "ld.shared.b128 r, [%2];\n"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n"
+        "selp.u32 %1, 1, 0, p1;\n"
+        "mov.u32 %0, 0;\n"
+        "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %0, r;\n"
+        "}\n"
+        : "=r"(x), "=r"(valid)
+        : "r"(ptx::smem_u32(resp_smem))
+        : "memory");
+    ptx::fence_proxy_async();
+    return valid ? (int)x : -1;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint64_t* bar, uint32_t cta, uint32_t bytes) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n"
+        "}\n" ::"r"(ptx::smem_u32(bar)),
+        "r"(cta), "r"(bytes)
+        : "memory");
+}
+
 }  // namespace ptx2
+
+constexpr int kClcDepth = 4;  // responses in flight (the scheduler runs one item ahead; consumers lag <= 3)
 
 constexpr int kGemm2Threads = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kGemm2EpiWarps = 8;
@@ -103,14 +147,37 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     uint64_t* tmem_empty = tmem_full + 2;           // [2]           used in the leader only
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     uint2* stage_buf = reinterpret_cast<uint2*>(tmem_empty + 4);
+    uint4* clc_resp = reinterpret_cast<uint4*>(stage_buf + (size_t)kGemm2EpiWarps * kStageCap2);  // [kClcDepth]
+    uint64_t* clc_full = reinterpret_cast<uint64_t*>(clc_resp + kClcDepth);  // [kClcDepth] one set per CTA
+    uint64_t* clc_empty = clc_full + kClcDepth;                              // [kClcDepth] used in the leader only
 
     const int n_items = p.n_tiles * p.n_groups;
     const int cid = blockIdx.x >> 1;
     const int ncl = gridDim.x >> 1;
     const int half_nt = p.nt >> 1;
     const int b_bytes = half_nt * kBlockK * 2;
-    int item_begin, item_end, item_step;
-    item_range(n_items, p.n_groups, cid, ncl, item_begin, item_end, item_step);
+    // Work distribution.  Static: pair c takes items c, c + ncl, ... (grid = one pair per two SMs).  Dynamic
+    // (cluster launch control): the grid has one pair per item; a resident pair does its own item, then keeps
+    // cancelling the launch of pending pairs and doing their items, until nothing is pending.  The pairs thus
+    // stay within one item of each other whatever their individual speed: a row tile is read from HBM once
+    // and found in L2 by its other query groups, and the tail of a slab is one item, not one static share.
+    const bool dyn = p.dynamic != 0;
+    // every consumer of the schedule (TMA lanes, MMA warp, epilogue warps of both CTAs) walks the same
+    // sequence: `cons` counts the responses it has consumed
+    auto next_item = [&](int item, uint32_t& cons, bool whole_warp) -> int {
+        if (!dyn) {
+            const int n = item + ncl;
+            return n < n_items ? n : -1;
+        }
+        const int slot = (int)(cons % kClcDepth);
+        const uint32_t ph = (cons / kClcDepth) & 1u;
+        ptx::mbar_wait(&clc_full[slot], ph);
+        const int x = ptx2::clc_decode(&clc_resp[slot]);
+        if (whole_warp) __syncwarp();
+        if (!whole_warp || lane == 0) ptx2::mbar_arrive_cluster(&clc_empty[slot], 0);
+        ++cons;
+        return x < 0 ? -1 : (x >> 1);
+    };
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmap_a);
@@ -122,6 +189,11 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tmem_full[s], 1);   // multicast tcgen05.commit
             ptx::mbar_init(&tmem_empty[s], 2 * kGemm2EpiWarps);  // 8 epilogue warps x 2 CTAs
+        }
+        for (int s = 0; s < kClcDepth; ++s) {
+            ptx::mbar_init(&clc_full[s], 1);  // the scheduler's arrive.expect_tx (+ 16 response bytes)
+            // leader: TMA lane, MMA warp, 8 epilogue warps; peer: TMA lane, 8 epilogue warps
+            ptx::mbar_init(&clc_empty[s], 2 * kGemm2EpiWarps + 3);
         }
         ptx::fence_barrier_init();
     }
@@ -143,7 +215,17 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const uint32_t pair_bytes = 2u * (uint32_t)(kABytes + b_bytes);
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = item_begin; item != item_end; item += item_step) {
+            uint32_t cons = 0, fetch = 0;
+            for (int item = cid; item >= 0; item = next_item(item, cons, false)) {
+                if (dyn && leader) {
+                    // the scheduler: ask for the item after this one before loading this one's operands
+                    const int slot = (int)(fetch % kClcDepth);
+                    ptx::mbar_wait(&clc_empty[slot], ((fetch / kClcDepth) & 1u) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(&clc_full[slot], 16);
+                    ptx2::mbar_arrive_expect_tx_cluster(&clc_full[slot], 1, 16);
+                    ptx2::clc_try_cancel_multicast(&clc_resp[slot], &clc_full[slot]);
+                    ++fetch;
+                }
                 const int tile = item / p.n_groups;
                 const int group = item - tile * p.n_groups;
                 const int row0 = (int)(p.row_begin + (int64_t)tile * (2 * kTileM)) + (int)rank * kTileM;
@@ -172,7 +254,8 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int item = item_begin; item != item_end; item += item_step, ++it) {
+            uint32_t cons = 0;
+            for (int item = cid; item >= 0; item = next_item(item, cons, true), ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
                 ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
@@ -211,7 +294,8 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int half = (warp - 2) >> 2;
         uint2* stg = stage_buf + (size_t)(warp - 2) * kStageCap2;
         int it = 0;
-        for (int item = item_begin; item != item_end; item += item_step, ++it) {
+        uint32_t cons = 0;
+        for (int item = cid; item >= 0; item = next_item(item, cons, true), ++it) {
             const int tile = item / p.n_groups;
             const int group = item - tile * p.n_groups;
             const int acc = it & 1;
@@ -257,7 +341,8 @@ int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
     p.row_end = a.row_end;
     p.n_tiles = (int)((a.row_end - a.row_begin + 2 * kTileM - 1) / (2 * kTileM));
     p.stage_bytes = kABytes + (p.nt / 2) * kBlockK * 2;
-    const size_t tail = (2 * kMaxStages + 4) * sizeof(uint64_t) + 64 + kGemm2EpiWarps * kStageCap2 * sizeof(uint2);
+    const size_t tail = (2 * kMaxStages + 4) * sizeof(uint64_t) + 64 + kGemm2EpiWarps * kStageCap2 * sizeof(uint2) +
+                        kClcDepth * (sizeof(uint4) + 2 * sizeof(uint64_t));
     int nst = (int)((220 * 1024 - tail - 1024) / (size_t)p.stage_bytes);
     if (nst > kMaxStages) nst = kMaxStages;
     p.nstages = nst;
@@ -282,6 +367,9 @@ int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
     const int n_items = p.n_tiles * p.n_groups;
     int clusters = s->sm_count / 2;
     if (n_items < clusters) clusters = n_items;
+    // dynamic scheduling (cluster launch control): one pair per item in the grid, the resident pairs steal the rest
+    p.dynamic = (g_opt.gemm_clc != 0 && n_items > clusters) ? 1 : 0;
+    if (p.dynamic) clusters = n_items;
     gemm_topk_kernel_2cta<<<2 * clusters, kGemm2Threads, smem, stream>>>(s->tmap_bf16, tmap_b, p);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());

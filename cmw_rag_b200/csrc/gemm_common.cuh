@@ -28,6 +28,7 @@ struct GemmParams {
     int nstages;
     int stage_bytes;
     int dense;
+    int dynamic;          // CTA-pair kernel: 1 = work items handed out by cluster launch control
     uint32_t idesc;
     const float* row_mul;
     float* pool_scores;
