@@ -69,6 +69,9 @@ def _match(meta: dict[str, Any], where: dict[str, Any] | None) -> bool:
 
 
 class B200Store:
+    # metadata keys with a hash index for `where` equality (every other filter scans the sidecar)
+    INDEXED_KEYS = ("doc_stable_id", "kbId", "stable_id", "source_file")
+
     def __init__(
         self,
         collection_name: str = "default",
@@ -102,6 +105,10 @@ class B200Store:
         self._metas: list[dict[str, Any] | None] = []
         self._alive: list[bool] = []
         self._row_of: dict[str, int] = {}
+        self._n_alive = 0
+        # equality index on the metadata keys the reference filters by (vector_store.py:87,96,105 as driven
+        # by core/indexer.py:397,432,505 and scripts/build_index.py:161-182): value -> rows in append order
+        self._eq_index: dict[str, dict[Any, list[int]]] = {key: {} for key in self.INDEXED_KEYS}
         self._gid_of_key: dict[str, int] = {}
         self._key_of_gid: list[str] = []
         # micro-batching of concurrent awaits
@@ -134,7 +141,39 @@ class B200Store:
         return self._dense
 
     def count(self) -> int:
-        return sum(self._alive)
+        return self._n_alive
+
+    def _index_row(self, row: int, meta: dict[str, Any] | None) -> None:
+        if not meta:
+            return
+        for key in self.INDEXED_KEYS:
+            if key in meta:
+                try:
+                    self._eq_index[key].setdefault(meta[key], []).append(row)
+                except TypeError:  # unhashable value: only reachable through the full scan
+                    pass
+
+    def _index_candidates(self, where) -> list[int] | None:
+        """Rows that can match `where` according to the equality index (None = no indexed condition:
+        scan).  Only top-level `key: value` / `key: {"$eq": value}` conditions are used; the caller still
+        applies the whole filter."""
+        if not isinstance(where, dict):
+            return None
+        best = None
+        for key, cond in where.items():
+            if key not in self._eq_index:
+                continue
+            if isinstance(cond, dict):
+                if set(cond) != {"$eq"}:
+                    continue
+                cond = cond["$eq"]
+            try:
+                rows = self._eq_index[key].get(cond, [])
+            except TypeError:
+                continue
+            if best is None or len(rows) < len(best):
+                best = rows
+        return best
 
     def gid_for(self, raw_kb_id) -> int:
         """Dense group number of a kbId (retriever.py:236-239 grouping key), -1 for a falsy kbId."""
@@ -182,6 +221,8 @@ class B200Store:
                 self._docs.append(texts[i])
                 self._metas.append(dict(metadatas[i]) if metadatas[i] is not None else None)
                 self._alive.append(True)
+                self._index_row(base + j, metadatas[i])
+            self._n_alive += len(keep)
 
     def _grow(self, needed: int, chunk_rows: int = 65536) -> DenseStore:
         """A Chroma collection grows without bound; the HBM store is sized up front.  When an add would
@@ -207,13 +248,50 @@ class B200Store:
         return new
 
     def _rows_where(self, where, limit: int | None = None) -> list[int]:
+        cand = self._index_candidates(where)
+        rows = cand if cand is not None else range(len(self._ids))
         out = []
-        for r, (alive, meta) in enumerate(zip(self._alive, self._metas)):
-            if alive and _match(meta or {}, where):
+        for r in rows:
+            if self._alive[r] and _match(self._metas[r] or {}, where):
                 out.append(r)
                 if limit is not None and len(out) >= limit:
                     break
         return out
+
+    def compact(self, chunk_rows: int = 65536) -> int:
+        """Drop tombstoned rows physically (they cost scan bandwidth until then): the live rows are copied,
+        in order, into a fresh HBM store through the read-back entry point and the sidecar is renumbered.
+        Row numbers returned by :meth:`search` change; string ids, documents and metadata do not.  Returns
+        the number of rows reclaimed.  Needs the fp32 tiles."""
+        with self._lock:
+            n = len(self._ids)
+            dead = n - self._n_alive
+            if dead == 0 or self._dense is None:
+                return 0
+            if not self._keep[0]:
+                raise RuntimeError("compact() re-ingests from the fp32 tiles, which this collection does not keep")
+            old = self._dense
+            new = DenseStore(self._pdim, self._capacity, device=self._device, f32=self._keep[0], bf16=self._keep[1],
+                             id_offset=self._id_offset)
+            alive = np.asarray(self._alive, bool)
+            for lo in range(0, n, chunk_rows):
+                m = min(chunk_rows, n - lo)
+                keep = alive[lo:lo + m]
+                if keep.any():
+                    rows, gid, _ = old.read_rows(lo, m)
+                    new.append(np.ascontiguousarray(rows[keep]), gid[keep])
+            old.close()
+            self._dense = new
+            live_rows = np.flatnonzero(alive).tolist()
+            self._ids = [self._ids[r] for r in live_rows]
+            self._docs = [self._docs[r] for r in live_rows]
+            self._metas = [self._metas[r] for r in live_rows]
+            self._alive = [True] * len(live_rows)
+            self._row_of = {sid: r for r, sid in enumerate(self._ids)}
+            self._eq_index = {key: {} for key in self.INDEXED_KEYS}
+            for r, meta in enumerate(self._metas):
+                self._index_row(r, meta)
+            return dead
 
     def delete(self, where=None, ids=None) -> int:
         with self._lock:
@@ -231,7 +309,8 @@ class B200Store:
                 self._alive[r] = False
                 self._row_of.pop(self._ids[r], None)
                 self._docs[r] = None
-                self._metas[r] = None
+                self._metas[r] = None  # its index entries stay behind and are skipped by the alive check
+            self._n_alive -= len(rows)
             return len(rows)
 
     def get(self, where=None, ids=None, include=("metadatas", "documents"), limit=None) -> dict:
@@ -410,6 +489,8 @@ class B200Store:
                 store._alive.append(bool(alive[i]))
                 if alive[i]:
                     store._row_of[rec["id"]] = i
+                    store._index_row(i, rec["metadata"])
+                    store._n_alive += 1
         dead = np.flatnonzero(~alive)
         if dead.size:
             dense.tombstone(dead)

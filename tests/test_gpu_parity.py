@@ -704,6 +704,36 @@ def test_fuzz_search_against_oracle(torch_cuda, seed):
     st.close()
 
 
+def test_b200store_compaction_gpu(torch_cuda):
+    """B200Store.compact(): tombstoned rows are physically dropped; results (as stable ids and scores) are
+    those of the oracle over the live rows before and after."""
+    from cmw_rag_b200 import B200Store
+
+    n, d, k = 6000, 64, 10
+    c = synth.make_corpus(n, d, seed=77, ties=False)
+    q, _ = synth.make_queries(c, 9, seed=78, tie_probe=False)
+    store = B200Store("cmp", capacity=8192)
+    store.add([f"t{i}" for i in range(n)], [{"doc_stable_id": f"D{i // 3}", "kbId": str(i // 3)} for i in range(n)],
+              ids=[f"c{i}" for i in range(n)], embeddings=c)
+    for doc in range(0, 2000, 2):
+        store.delete(where={"doc_stable_id": f"D{doc}"})
+    live = np.ones(n, bool)
+    for doc in range(0, 2000, 2):
+        live[3 * doc:3 * doc + 3] = False
+    assert store.count() == int(live.sum()) == 3000
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, k, live=live)
+    want = [[f"c{r}" for r in row] for row in ref_ids]
+    res = store.query(q, k)
+    assert res["ids"] == want
+    assert store.compact() == 3000 and store.dense.rows == 3000
+    res2 = store.query(q, k)
+    assert res2["ids"] == want
+    assert np.allclose(np.array(res2["distances"]), 1.0 - ref_sc, atol=F32_TOL)
+    assert np.array_equal(np.array(res2["distances"]), np.array(res["distances"]))
+    store.add(["z"], [{"doc_stable_id": "Z", "kbId": "77"}], ids=["z"], embeddings=q[:1])
+    assert store.query(q[:1], 1)["ids"] == [["z"]]
+
+
 def test_pure_c_client(tmp_path):
     """The C-ABI boundary used from plain C (examples/c_client.c): no CUDA headers, no Python objects."""
     import subprocess

@@ -254,6 +254,46 @@ def test_collection_grows_past_its_capacity(monkeypatch):
     assert (ids == ref).all()
 
 
+def test_where_index_and_compaction(fake_store):
+    """the indexer's per-document lookups (`get_any_doc_meta_async({"doc_stable_id": ..})`,
+    `delete_where_async`, core/indexer.py:397,432,505) hit a hash index instead of scanning the sidecar, and
+    compact() reclaims tombstoned rows without changing what a search returns."""
+    store = fake_store
+    rng = np.random.default_rng(3)
+    n = 400
+    emb = rng.standard_normal((n, 8)).astype(np.float32)
+    metas = [{"doc_stable_id": f"D{i // 4}", "stable_id": f"c{i}", "kbId": str(500 + i // 4), "n": i} for i in range(n)]
+    store.add([f"t{i}" for i in range(n)], metas, ids=[f"c{i}" for i in range(n)], embeddings=emb)
+    assert store._index_candidates({"doc_stable_id": "D7"}) == [28, 29, 30, 31]
+    assert store._index_candidates({"n": 5}) is None  # not an indexed key: full scan
+    assert store._index_candidates({"doc_stable_id": {"$eq": "D7"}, "n": 30}) == [28, 29, 30, 31]
+    assert store.get(where={"doc_stable_id": "D7", "n": 30})["ids"] == ["c30"]
+    assert store.get(where={"doc_stable_id": {"$ne": "D7"}}, limit=2)["ids"] == ["c0", "c1"]  # scan path
+    assert store.get(where={"kbId": "507"})["ids"] == ["c28", "c29", "c30", "c31"]
+    # re-index documents 0..49: delete their chunks, add new versions (the indexer's update flow)
+    for doc in range(50):
+        assert store.delete(where={"doc_stable_id": f"D{doc}"}) == 4
+    assert store.count() == n - 200 and store.get(where={"doc_stable_id": "D7"})["ids"] == []
+    emb2 = rng.standard_normal((200, 8)).astype(np.float32)
+    store.add([f"u{i}" for i in range(200)],
+              [{"doc_stable_id": f"D{i // 4}", "stable_id": f"v{i}", "kbId": str(500 + i // 4)} for i in range(200)],
+              ids=[f"v{i}" for i in range(200)], embeddings=emb2)
+    assert store.get(where={"doc_stable_id": "D7"})["ids"] == ["v28", "v29", "v30", "v31"]
+    q = rng.standard_normal((6, 8)).astype(np.float32)
+    before = [[d.metadata["stable_id"] for d in store.similarity_search(v, 9)] for v in q]
+    dist_before = store.query(q, 9)["distances"]
+    assert store.compact() == 200
+    assert store.count() == n and len(store._ids) == n and store.compact() == 0
+    after = [[d.metadata["stable_id"] for d in store.similarity_search(v, 9)] for v in q]
+    assert after == before and store.query(q, 9)["distances"] == dist_before
+    assert store.get(where={"doc_stable_id": "D7"})["ids"] == ["v28", "v29", "v30", "v31"]
+    assert store.get(ids=["c399", "c0"])["ids"] == ["c399"]
+    _, ids, _ = store.search(q[:1], 3)
+    assert all(store._ids[r] == sid for r, sid in zip(ids[0].tolist(), before[0][:3]))
+    store.add(["w"], [{"doc_stable_id": "Dnew", "kbId": "9"}], ids=["w"], embeddings=rng.standard_normal((1, 8)))
+    assert store.get(where={"doc_stable_id": "Dnew"})["ids"] == ["w"] and store.count() == n + 1
+
+
 def test_shard_bounds():
     from cmw_rag_b200.sharded import shard_bounds
 
