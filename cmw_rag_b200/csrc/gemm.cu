@@ -10,13 +10,14 @@
 //   both K-major bf16 in shared memory, 128-byte swizzle, written by TMA (cp.async.bulk.tensor.2d);
 //   fp32 accumulators in TMEM, two stages of 256 columns so the epilogue of item i overlaps the
 //   MMAs of item i+1.
-// Warp roles (192 threads, one persistent CTA per SM):
+// Warp roles (192 threads, or 320 with 8 epilogue warps for 192/256-column query groups; one persistent CTA
+// per SM):
 //   warp 0   TMA producer (one elected lane): ring of [A 16 KB | B NT*128 B] stages, mbarrier tx
 //   warp 1   TMEM allocator + MMA issuer: the whole warp walks the pipeline warp-uniformly (operand
 //            descriptors stay in uniform registers), one elect.sync lane issues 4 back-to-back
 //            tcgen05.mma.cta_group::1.kind::f16 (K = 16) per k-block; tcgen05.commit releases
 //            shared-memory stages and publishes finished accumulators
-//   warps 2-5 epilogue (gemm_common.cuh): tcgen05.ld (32 lanes x 32 columns), multiply by the per-row
+//   warps 2-5 (2-9) epilogue (gemm_common.cuh): tcgen05.ld (32 lanes x 32 columns), multiply by the per-row
 //            multiplier (NaN for tombstoned rows), compare with the per-query admission thresholds
 //            (fetched as one batch while the TMEM load is in flight), stage the rare survivors in
 //            shared memory (ballot + popc), hand the accumulator back, then flush the staged entries
@@ -32,7 +33,7 @@
 namespace cmw {
 
 constexpr int kGemmThreads = 192;      // TMA warp, MMA warp, 4 epilogue warps
-constexpr int kGemmThreadsWide = 320;  // ... 8 epilogue warps (query groups of 128+ columns)
+constexpr int kGemmThreadsWide = 320;  // ... 8 epilogue warps (query groups of 192 / 256 columns)
 
 __global__ void __launch_bounds__(kGemmThreadsWide, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,

@@ -11,8 +11,12 @@
 //   * TMA completions of both CTAs signal the LEADER's full barrier (peer bit of the barrier address
 //     cleared); tcgen05.commit multicasts to both CTAs' empty / tmem_full barriers; the epilogue warps of
 //     both CTAs release the accumulator on the leader's tmem_empty barrier (remote mbarrier arrive).
-// Used when NT is a multiple of 32 and the batch is large enough to be tensor-bound; otherwise the
-// 1-CTA kernel (HBM-bound regime) runs.
+//   * 8 epilogue warps per CTA (two per TMEM lane quarter, 128 query columns each);
+//   * work items come from cluster launch control (clusterlaunchcontrol.try_cancel): the grid holds one
+//     pair per item, the resident pairs steal the pending ones -- a hardware dynamic scheduler that keeps
+//     the pairs within one item of each other (L2 re-use of the corpus rows, one-item tails).
+// Used when the padded batch is a multiple of 256 (NT = 256) and large enough to be tensor-bound; otherwise
+// the 1-CTA kernel (HBM-bound regime) runs.
 #include "gemm_common.cuh"
 
 namespace cmw {
