@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--no-f32", action="store_true")
     ap.add_argument("--multivector", action="store_true")
     ap.add_argument("--out", default="")
+    ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE",
+                    help="cmw_set_option before the sweep (repeatable), e.g. --set gemm_prefetch=0")
     args = ap.parse_args()
 
     import torch
@@ -44,6 +46,11 @@ def main():
 
     device = torch.device("cuda:0")
     torch.cuda.set_device(device)
+    options = {}
+    for kv in args.set:
+        name, value = kv.split("=", 1)
+        N.set_option(name, float(value))
+        options[name] = float(value)
 
     class A:
         pass
@@ -137,7 +144,7 @@ def main():
                 nbytes = passes * args.rows * (args.dim * elt + 4)
                 flops = 2.0 * b * args.rows * args.dim
                 emit({"config": "sweep", "rows": args.rows, "batch": b, "mode": mode, "algo": algo, "k": args.k,
-                      "needles_ok": ok, "uncertified": int(fl.sum().item()),
+                      "options": options, "needles_ok": ok, "uncertified": int(fl.sum().item()),
                       "batch_ms_p50": float(np.median(ms)), "batch_ms_p99": float(np.percentile(ms, 99)),
                       "per_query_ms_p50": float(np.median(ms)) / b, "qps": b / (float(np.median(ms)) * 1e-3),
                       "filter_ms": filt, "hbm_gbs_filter": nbytes / (filt * 1e-3) / 1e9,
