@@ -141,7 +141,7 @@ struct Options {
     double scan_max_batch = 0;
     double gemm_enabled = 1;
     double gemm_2cta = 1;            // CTA-pair (cta_group::2) K2 kernel for large batches
-    double gemm_2cta_min_batch = 256;
+    double gemm_2cta_min_batch = 128;  // padded batches of 128 / 192 gain 2-5 % from the halved query-operand traffic
     double gemm_clc = 1;             // CTA-pair kernel: dynamic item scheduling through cluster launch control
     // 1 = rigorous certificate behind the bf16 filter: eps = 2u(1+u) + fp32 accumulation slack = 4.1e-3
     // (Cauchy-Schwarz over unit vectors, u = 2^-9) and K' = max(512, 4k); ~17 % slower at B=4096

@@ -236,7 +236,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     if (a.dense)
         CMW_REQUIRE(a.row_end - a.row_begin <= kPoolCap, "launch_gemm: dense slab larger than the pool");
     // tensor-bound batches run on CTA pairs (cta_group::2); the HBM-bound ones on single CTAs
-    if (g_opt.gemm_2cta != 0 && a.bpad >= (int)g_opt.gemm_2cta_min_batch && a.bpad % 256 == 0 &&
+    if (g_opt.gemm_2cta != 0 && a.bpad >= (int)g_opt.gemm_2cta_min_batch && (a.bpad % 256 == 0 || (a.bpad < 256 && a.bpad % 64 == 0)) &&
         (a.row_begin % (2 * kTileM)) == 0)
         return launch_gemm_2cta(a, stream);
     GemmParams p;

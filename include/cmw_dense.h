@@ -184,7 +184,7 @@ int cmw_profile_enable(int on);
 int cmw_profile_read(double* ms, int64_t* counts, int n);
 /* Process-wide tunables (defaults in parentheses):
  *   "scan_max_batch" (0)      batches up to this size use K1 (scan), larger ones K2 (GEMM)
- *   "gemm_enabled" (1), "gemm_2cta" (1), "gemm_2cta_min_batch" (256)   K2 kernel selection
+ *   "gemm_enabled" (1), "gemm_2cta" (1), "gemm_2cta_min_batch" (128), "gemm_clc" (1)   K2 kernel selection
  *   "kprime" (0 = automatic)  candidates kept per query between slabs and handed to K3
  *   "bf16_eps" (0 = automatic, dimension-aware), "bf16_sigmas" (8), "f32_eps" (4e-6)   certificate bounds
  *   "strict_certificate" (0)  1 = rigorous Cauchy-Schwarz bound behind the bf16 filter (K' = max(512, 4k))

@@ -372,7 +372,7 @@ def test_full_size_1m_properties(torch_cuda):
     st.close()
 
 
-@pytest.mark.parametrize("batch", [1, 7, 16, 33, 300])
+@pytest.mark.parametrize("batch", [1, 7, 16, 33, 64, 128, 130, 192, 300])
 def test_gemm_filter_exact(cfg1, batch):
     """K2 (tcgen05 GEMM filter) forced for every batch size: one partial group, exactly one group,
     several groups (300 -> 2 groups of 256 with padding)."""
