@@ -734,6 +734,46 @@ def test_b200store_compaction_gpu(torch_cuda):
     assert store.query(q[:1], 1)["ids"] == [["z"]]
 
 
+def test_repeated_host_searches_track_store_changes(torch_cuda):
+    """The same small blocking host search repeated across tombstones, appends (new slab schedule) and option
+    changes keeps returning the oracle's answer for the store as it is at that moment."""
+    from cmw_rag_b200 import DenseStore
+    from cmw_rag_b200 import _native as N
+
+    n, d, k = 9000, 128, 10
+    c = synth.make_corpus(n, d, seed=91, ties=False)
+    q, _ = synth.make_queries(c, 3, seed=92, tie_probe=False)
+    st = DenseStore(d, n + 500)
+    st.append(c[:8000])
+    live = np.ones(8000, bool)
+    ref_ids, ref_sc, _ = exact_topk_c(c[:8000], q, k)
+    for call in range(3):
+        sc, ids, fl = st.search_host(q, k)
+        _check_exact(ids, sc, ref_ids, ref_sc)
+        sc1, ids1, _ = st.search_host(q[:1], k)
+        _check_exact(ids1, sc1, ref_ids[:1], ref_sc[:1])
+    dead = ref_ids[:, 0].tolist()
+    st.tombstone(dead)
+    live[dead] = False
+    ref2, ref2_sc, _ = exact_topk_c(c[:8000], q, k, live=live)
+    sc, ids, fl = st.search_host(q, k)
+    _check_exact(ids, sc, ref2, ref2_sc)
+    st.append(c[8000:])
+    live = np.concatenate([live, np.ones(n - 8000, bool)])
+    ref3, ref3_sc, _ = exact_topk_c(c, q, k, live=live)
+    for algo in ("auto", "scan", "gemm"):
+        for call in range(2):
+            sc, ids, fl = st.search_host(q, k, algo=algo)
+            _check_exact(ids, sc, ref3, ref3_sc)
+    N.set_option("gemm_clc", 0)
+    try:
+        sc, ids, fl = st.search_host(np.repeat(q, 100, axis=0), k)
+        _check_exact(ids, sc, np.repeat(ref3, 100, axis=0), np.repeat(ref3_sc, 100, axis=0))
+    finally:
+        N.set_option("gemm_clc", 1)
+    st.close()
+
+
 def test_pure_c_client(tmp_path):
     """The C-ABI boundary used from plain C (examples/c_client.c): no CUDA headers, no Python objects."""
     import subprocess
