@@ -128,16 +128,21 @@ def main():
                 nd = needle.cpu().numpy()
                 ok = bool(((ids[:, 0].cpu().numpy() == nd) | (nd < 0)).all())
                 iters = max(10, args.iters // max(1, b // 64))
-                N.profile_enable(True)
+                # latency loop with the phase profiler off (its event records cost ~50 us per search), then a
+                # second loop with it on for the per-phase kernel times
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
                 ev[0].record()
                 for i in range(iters):
                     st.search(q, args.k, mode=mode, algo=algo)
                     ev[i + 1].record()
                 torch.cuda.synchronize()
+                ms = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(iters)])
+                N.profile_enable(True)
+                for i in range(iters):
+                    st.search(q, args.k, mode=mode, algo=algo)
+                torch.cuda.synchronize()
                 prof = N.profile_read()
                 N.profile_enable(False)
-                ms = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(iters)])
                 filt = prof["filter"][0] / iters
                 elt = 4 if (mode == "f32" and b <= int(N.get_option("scan_max_batch")) and algo != "gemm") else 2
                 passes = (b + 1) // 2 if (b <= int(N.get_option("scan_max_batch")) and algo != "gemm") or algo == "scan" else 1
