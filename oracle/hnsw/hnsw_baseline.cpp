@@ -123,7 +123,14 @@ void search_layer(const Index& ix, const float* q, int32_t ep, float ep_dist, in
             nb.assign(l + 1, l + 1 + l[0]);
             if (lock_nodes) mix.locks[c.second].unlock();
         }
-        for (int32_t n : nb) {
+        for (size_t ni = 0; ni < nb.size(); ++ni) {
+            const int32_t n = nb[ni];
+            // like hnswlib's searchBaseLayer: start fetching the next neighbour's vector while this one is scored
+            if (ni + 1 < nb.size()) {
+                const char* nx = reinterpret_cast<const char*>(ix.v(nb[ni + 1]));
+                __builtin_prefetch(nx);
+                __builtin_prefetch(nx + 64);
+            }
             if (vis.tag[n] == vis.cur) continue;
             vis.tag[n] = vis.cur;
             const float d = dist_ip(q, ix.v(n), ix.dim);
