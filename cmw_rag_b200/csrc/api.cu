@@ -86,42 +86,6 @@ static int pick_kprime(int k, int mode, bool gemm) {
     return kp;
 }
 
-// ---------------------------------------------------------------------------------------------
-// host staging for the *_host entry points
-// ---------------------------------------------------------------------------------------------
-static int stage_h2d(int device, uint8_t* pin, uint8_t* dev, const uint8_t* src, size_t bytes,
-                     cudaStream_t stream) {
-    const size_t piece = 1u << 20;
-    const size_t npieces = (bytes + piece - 1) / piece;
-    unsigned hw = std::thread::hardware_concurrency();
-    size_t nthreads = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
-    if (npieces < 4) nthreads = 1;
-    std::atomic<int> err{0};
-    auto work = [&](size_t t) {
-        if (t != 0 && cudaSetDevice(device) != cudaSuccess) err.store(1);
-        for (size_t i = t; i < npieces; i += nthreads) {
-            const size_t off = i * piece;
-            const size_t n = bytes - off < piece ? bytes - off : piece;
-            memcpy(pin + off, src + off, n);
-            if (cudaMemcpyAsync(dev + off, pin + off, n, cudaMemcpyHostToDevice, stream) != cudaSuccess)
-                err.store(1);
-        }
-    };
-    if (nthreads == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> th;
-        for (size_t t = 1; t < nthreads; ++t) th.emplace_back(work, t);
-        work(0);
-        for (auto& x : th) x.join();
-    }
-    if (err.load()) {
-        set_error("cmw_search_host: staging copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return -2;
-    }
-    return 0;
-}
-
 // Layout of one host call's I/O block (the same offsets in the pinned staging buffer and in its device twin):
 // queries | scores | ids | flags.
 struct HostIo {

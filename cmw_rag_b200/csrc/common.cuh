@@ -218,6 +218,8 @@ int ensure_pinned(Store* s, size_t bytes);
 int ensure_dev_io(Store* s, size_t bytes);
 int ensure_ws(Store* s, size_t bytes);
 int get_stream(Store* s, cudaStream_t* out);
+// pageable host -> pinned block -> device, pipelined over a few host threads (all pieces on `stream`)
+int stage_h2d(int device, uint8_t* pin, uint8_t* dev, const uint8_t* src, size_t bytes, cudaStream_t stream);
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remember what was set where
 struct SmemAttrCache {

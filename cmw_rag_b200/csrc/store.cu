@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -155,6 +156,43 @@ int get_stream(Store* s, cudaStream_t* out) {
 }
 
 int encode_bf16_tmap(Store* s);  // gemm.cu
+
+// ---------------------------------------------------------------------------------------------
+// host staging for the *_host entry points
+// ---------------------------------------------------------------------------------------------
+int stage_h2d(int device, uint8_t* pin, uint8_t* dev, const uint8_t* src, size_t bytes,
+                     cudaStream_t stream) {
+    const size_t piece = 1u << 20;
+    const size_t npieces = (bytes + piece - 1) / piece;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nthreads = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
+    if (npieces < 4) nthreads = 1;
+    std::atomic<int> err{0};
+    auto work = [&](size_t t) {
+        if (t != 0 && cudaSetDevice(device) != cudaSuccess) err.store(1);
+        for (size_t i = t; i < npieces; i += nthreads) {
+            const size_t off = i * piece;
+            const size_t n = bytes - off < piece ? bytes - off : piece;
+            memcpy(pin + off, src + off, n);
+            if (cudaMemcpyAsync(dev + off, pin + off, n, cudaMemcpyHostToDevice, stream) != cudaSuccess)
+                err.store(1);
+        }
+    };
+    if (nthreads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    if (err.load()) {
+        set_error("host staging copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -2;
+    }
+    return 0;
+}
+
 
 }  // namespace cmw
 
@@ -376,12 +414,21 @@ int cmw_store_append_host_f32(cmw_store* h, const float* rows_host, const int32_
     const size_t need = gid_off + (size_t)chunk * sizeof(int32_t);
     if ((rc = ensure_pinned(s, need))) return rc;
     if ((rc = ensure_dev_io(s, need))) return rc;
+    // page-locked source rows are DMA-copied directly; pageable ones go through the pinned block in 1 MB
+    // pieces staged by a few host threads, each piece's H2D queued as soon as it is staged
+    cudaPointerAttributes attr;
+    bool src_pinned = cudaPointerGetAttributes(&attr, rows_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
     for (int64_t lo = 0; lo < n; lo += chunk) {
         const int64_t m = (n - lo < chunk) ? (n - lo) : chunk;
-        memcpy(s->pinned, rows_host + lo * s->dim, (size_t)m * row_bytes);
+        const float* src = rows_host + lo * s->dim;
+        if (src_pinned) {
+            CMW_CUDA_OK(cudaMemcpyAsync(s->dev_io, src, (size_t)m * row_bytes, cudaMemcpyHostToDevice, s->stream));
+        } else if (stage_h2d(s->device, reinterpret_cast<uint8_t*>(s->pinned), reinterpret_cast<uint8_t*>(s->dev_io),
+                             reinterpret_cast<const uint8_t*>(src), (size_t)m * row_bytes, s->stream)) {
+            return -2;
+        }
         if (kb_gid_host) memcpy((char*)s->pinned + gid_off, kb_gid_host + lo, (size_t)m * sizeof(int32_t));
-        CMW_CUDA_OK(cudaMemcpyAsync(s->dev_io, s->pinned, (size_t)m * row_bytes, cudaMemcpyHostToDevice,
-                                    s->stream));
         if (kb_gid_host)
             CMW_CUDA_OK(cudaMemcpyAsync((char*)s->dev_io + gid_off, (char*)s->pinned + gid_off,
                                         (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
