@@ -608,6 +608,37 @@ def test_pipelined_host_api_matches_blocking(cfg1):
     _check_exact(ids, sc, cfg1["ref_ids"], cfg1["ref_sc"])
 
 
+def test_pipelined_host_api_from_several_threads(cfg1):
+    """Four host threads, each keeping one ticket in flight on the same store (the header's threading
+    contract for the pipelined entry points), next to a fifth thread issuing blocking calls."""
+    import threading
+
+    st, q = cfg1["store"], cfg1["q"]
+    errors = []
+
+    def worker(tid):
+        try:
+            lo = 8 * tid
+            for it in range(25):
+                if tid < 4:
+                    t = st.search_host_submit(q[lo:lo + 8 + it % 3], 20, mode="f32")
+                    sc, ids, fl = st.search_host_wait(t)
+                else:
+                    sc, ids, fl = st.search_host(q[lo:lo + 8 + it % 3], 20, mode="f32")
+                n = 8 + it % 3
+                _check_exact(ids, sc, cfg1["ref_ids"][lo:lo + n], cfg1["ref_sc"][lo:lo + n])
+                assert (fl == 0).all()
+        except Exception as exc:  # noqa: BLE001 - reported below
+            errors.append((tid, repr(exc)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(5)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_pipelined_host_api_repairs_flagged_queries(torch_cuda):
     """A ticket whose queries fail the certificate goes through the repair chain inside the wait."""
     from cmw_rag_b200 import DenseStore
