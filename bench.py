@@ -559,7 +559,9 @@ def run_ours(args):
 
     cpu = None
     parity = None
-    if world == 1 and not args.skip_cpu:
+
+    def cpu_legs():
+        nonlocal cpu, parity
         # the CPU legs run on the SAME corpus bits (read back from the HBM store) and the same queries
         index_rows = min(args.rows, args.hnsw_rows or 50_000)
         if args.no_f32 or args.skip_cpu_exact:
@@ -594,6 +596,16 @@ def run_ours(args):
             assert parity["ids_identical_to_fp64_oracle"], "top-k ids differ from the fp64 oracle"
             assert parity["max_abs_score_err"] <= 1e-5, parity
         del corpus
+
+    if world == 1 and not args.skip_cpu:
+        try:
+            cpu_legs()
+        except AssertionError:
+            raise  # a parity failure invalidates the line: fail loudly
+        except Exception as exc:  # host-side trouble (memory, compiler) must not lose the GPU measurement
+            print(f"bench.py: CPU legs failed: {exc!r}", file=sys.stderr)
+            cpu = cpu or {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                          "sample": f"CPU legs failed: {exc!r}"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
