@@ -153,6 +153,22 @@ def cpu_exact_sample(corpus: np.ndarray, queries: np.ndarray, k: int, steps: int
     return queries.shape[0] * steps / dt, dt, num_threads()
 
 
+def cpu_exact_sgemm_sample(corpus: np.ndarray, queries: np.ndarray, k: int):
+    """Exact fp32 top-k the way a CPU library does it: one sgemm ``Q @ C.T`` on all host
+    threads (torch CPU = MKL / oneDNN) and a partial sort per query.  The corpus rows are unit vectors here,
+    so the dot product is the cosine.  Returns (qps, seconds, threads, ids)."""
+    import torch
+
+    c = torch.from_numpy(corpus)
+    q = torch.from_numpy(np.ascontiguousarray(queries))
+    torch.topk(q[:2] @ c[:4096].T, min(k, 4096), dim=1)  # thread pool / kernel selection warm-up
+    t0 = time.perf_counter()
+    scores = q @ c.T
+    _, ids = torch.topk(scores, k, dim=1, sorted=True)
+    dt = time.perf_counter() - t0
+    return queries.shape[0] / dt, dt, torch.get_num_threads(), ids.numpy()
+
+
 def cpu_hnsw_sample(corpus: np.ndarray, queries: np.ndarray, k: int, index_rows: int, steps: int = 1):
     """The "Chroma HNSW" baseline (BASELINE.json north_star): an hnswlib-equivalent index with
     Chroma's defaults (M=16, ef_construction=100, ef_search=100) over the first `index_rows` rows,
@@ -586,6 +602,12 @@ def run_ours(args):
             cpu["exact_port"] = {"value": xq, "unit": UNIT, "cores": xthreads,
                                  "sample": f"{nchk} queries x {args.rows} rows, exact fp64 brute force "
                                            f"(oracle/c/oracle_topk.c, OpenMP, {dt:.1f} s)"}
+            nsg = min(128, B)
+            sq, sdt, sthreads, sids = cpu_exact_sgemm_sample(corpus, cq[:nsg], k)
+            agree = float(np.mean([len(np.intersect1d(sids[i], ids0_h[i])) / k for i in range(min(nsg, nchk))]))
+            cpu["exact_sgemm"] = {"value": sq, "unit": UNIT, "cores": sthreads,
+                                  "sample": f"{nsg} queries x {args.rows} rows, fp32 sgemm (torch CPU) + top-{k} per "
+                                            f"query ({sdt:.1f} s); recall@{k} vs the GPU's exact ids {agree:.4f}"}
         if not (args.no_f32 or args.skip_cpu_exact) and args.mode == "f32":
             # parity of the timed workload itself: the first queries of the batch against the oracle
             ref_ids, ref_sc, _ = exact_topk_c(corpus, cq[:nchk], k)
