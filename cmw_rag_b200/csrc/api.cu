@@ -24,7 +24,7 @@ namespace cmw {
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-    size_t qn64, q4, q_f32, q_bf16, pool_scores, pool_ids, pool_cnt, pool_thr, pool_ovf, exact, total;
+    size_t qn64, q4, q_f32, q_bf16, pool_scores, pool_ids, pool_cnt, pool_thr, pool_ovf, exact, wide, total;
     int bpad;
 };
 
@@ -53,6 +53,11 @@ static WsLayout ws_layout(int dim, int batch, int kprime) {
     w.pool_thr = take((size_t)w.bpad * sizeof(float));
     w.pool_ovf = take((size_t)w.bpad * sizeof(int32_t));
     w.exact = take((size_t)batch * kprime * sizeof(double));
+    // scratch of the wide first slab, small batches only: scores + ids in 16 pool-sized segments per query, and
+    // the segments' cnt / thr / ovf
+    w.wide = take(batch <= kWideDenseMaxBatch
+                      ? (size_t)batch * kWideDenseRows * 8 + (size_t)batch * kWideSegments * 12 + 1024
+                      : 0);
     w.total = off;
     return w;
 }
@@ -371,11 +376,37 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
 
     int rc;
     const int64_t rows = s->rows;
-    const int64_t slab0 = rows < kDenseSlabRows ? rows : kDenseSlabRows;
+    // First slab: every row's score is kept (no threshold exists yet).  Large batches write it straight into
+    // the pools (4096 rows = the pool capacity).  Small batches take a WIDE first slab of up to 65536 rows
+    // whose scores go to a scratch matrix of 16 pool-sized segments per query, from which a two-level
+    // selection fills the pools.  (The segments' survivors, kprime and ties each, must fit one pool: fewer
+    // segments for a large kprime.)
+    int wide_segs = (kPoolCap - 256) / kprime;
+    if (wide_segs > kWideSegments) wide_segs = kWideSegments;
+    const bool wide = g_opt.wide_dense != 0 && batch <= kWideDenseMaxBatch && rows > kDenseSlabRows && wide_segs >= 2 &&
+                      !(mode & CMW_SLABS_SAFE);
+    const int64_t wide_rows = (int64_t)wide_segs * kPoolCap;
+    const int64_t slab0 = wide ? (rows < wide_rows ? rows : wide_rows)
+                               : (rows < kDenseSlabRows ? rows : (int64_t)kDenseSlabRows);
+    float* wide_scores = nullptr;
+    int32_t* wide_ids = nullptr;
+    Pool seg = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (wide) {
+        uint8_t* base = ws + w.wide;
+        wide_scores = reinterpret_cast<float*>(base);
+        wide_ids = reinterpret_cast<int32_t*>(base + (size_t)batch * kWideDenseRows * 4);
+        uint8_t* tail = base + (size_t)batch * kWideDenseRows * 8;
+        const size_t seg_bytes = align_up((size_t)batch * kWideSegments * 4, 256);
+        seg.scores = wide_scores;
+        seg.ids = wide_ids;
+        seg.cnt = reinterpret_cast<int32_t*>(tail);
+        seg.thr = reinterpret_cast<float*>(tail + seg_bytes);
+        seg.ovf = reinterpret_cast<int32_t*>(tail + 2 * seg_bytes);
+    }
     {
         PhaseTimer t(3, stream);
         if ((rc = launch_prep_queries(queries_dev, batch, w.bpad, s->dim, metric, qn64, q4, q_f32,
-                                      gemm ? q_bf16 : nullptr, pool, (int)slab0, stream)))
+                                      gemm ? q_bf16 : nullptr, pool, wide ? 0 : (int)slab0, seg, (int)slab0, stream)))
             return rc;
     }
 
@@ -399,6 +430,9 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
             g.row_end = r1;
             g.pool = pool;
             g.dense = dense;
+            g.wide_scores = dense ? wide_scores : nullptr;
+            g.wide_ids = wide_ids;
+            g.wide_stride = kWideDenseRows;
             return launch_gemm(g, stream);
         }
         for (int b0 = 0; b0 < batch; b0 += 2) {
@@ -417,6 +451,9 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
             a.pool.thr = pool.thr + b0;
             a.pool.ovf = pool.ovf + b0;
             a.dense = dense;
+            a.wide_scores = (dense && wide_scores) ? wide_scores + (size_t)b0 * kWideDenseRows : nullptr;
+            a.wide_ids = wide_ids ? wide_ids + (size_t)b0 * kWideDenseRows : nullptr;
+            a.wide_stride = kWideDenseRows;
             a.sm_count = s->sm_count;
             int r = launch_scan(a, stream);
             if (r) return r;
@@ -436,10 +473,29 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
     int64_t seen = 0;
     if (rows > 0) {
         if ((rc = run_filter(0, slab0, 1))) return rc;
-        if ((rc = compact(slab0 == rows))) return rc;
+        if (wide) {
+            {
+                PhaseTimer t(1, stream);
+                if ((rc = launch_wide_select(seg, pool, batch, kprime, stream))) return rc;
+            }
+            if (slab0 == rows && (rc = compact(true))) return rc;  // nothing else follows: sort the survivors
+        } else if ((rc = compact(slab0 == rows))) {
+            return rc;
+        }
         seen = slab0;
         while (seen < rows) {
             int64_t m, end;
+            // After a wide first slab the threshold is the kprime-th best of 65536 rows: the rest of the corpus
+            // goes through ONE launch when its expected admissions, (rows - seen) * kprime / seen, and the kprime
+            // survivors fill at most 85 % of the pool (up to ~1.05M rows at kprime = 224).  An unlucky row order
+            // overflows the pool, is flagged, and goes through the overflow-proof schedule like any other.
+            if (wide && seen == slab0 &&
+                (double)(rows - seen) * kprime / (double)seen + kprime <= 0.85 * kPoolCap) {
+                if ((rc = run_filter(seen, rows, 0))) return rc;
+                if ((rc = compact(true))) return rc;
+                seen = rows;
+                break;
+            }
             if (mode & CMW_SLABS_SAFE) {
                 // a slab can add at most m rows to a pool holding at most kprime: never overflows
                 m = (int64_t)((kPoolCap - kprime) & ~255);

@@ -53,6 +53,12 @@ extern std::atomic<long long> g_kernel_launches;
 constexpr int kPoolCap = 4096;      // entries per query
 constexpr int kDenseSlabRows = 4096;  // first slab: every row is written (no threshold yet); = kPoolCap
 constexpr int kMaxKPrime = 1024;
+// Small batches take a WIDE first slab: its scores and ids go to a scratch matrix in the workspace, laid out as
+// 16 pool-sized segments per query, instead of the pools (fewer slabs -- filter launches and compactions, 7-12 us
+// each however little they do -- per search)
+constexpr int kWideDenseRows = 65536;
+constexpr int kWideSegments = kWideDenseRows / kPoolCap;
+constexpr int kWideDenseMaxBatch = 32;
 
 struct Pool {
     float* scores;   // [B, kPoolCap]
@@ -154,6 +160,9 @@ struct Options {
     // pipelined host API: 1 = a ticket's finalisation (fp64 rescoring + selection) runs on its own stream next
     // to the following ticket's filter; 0 = every ticket strictly after the previous one
     double host_overlap = 0;
+    // batches up to 32: a 65536-row first slab through a scratch matrix, and the rest of the corpus in ONE launch
+    // when the expected admissions fit the pool (two filter launches per search instead of four at 1M rows)
+    double wide_dense = 1;
     double slab_growth = 0;   // 0 = automatic ((cap - K') / (3 K'), at most 8); else the fixed growth factor
 };
 extern Options g_opt;
@@ -171,6 +180,9 @@ struct ScanArgs {
     int nq;                // 1 or 2
     Pool pool;             // already offset to the first of the nq queries
     int dense;             // 1 = write every row at slot (row - row_begin)
+    float* wide_scores;    // dense only: scratch [nq, wide_stride] for the wide first slab (NULL = the pools)
+    int32_t* wide_ids;
+    int wide_stride;
     int sm_count;
 };
 int launch_scan(const ScanArgs& a, cudaStream_t stream);
@@ -184,12 +196,15 @@ struct GemmArgs {
     int64_t row_begin, row_end;
     Pool pool;
     int dense;
+    float* wide_scores;           // dense only: scratch [batch, wide_stride] (NULL = the pools)
+    int32_t* wide_ids;
+    int wide_stride;
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 bool gemm_supported(const Store* s);
 
 int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64, double* q4,
-                        float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count,
+                        float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count, Pool seg, int wide_rows,
                         cudaStream_t stream);
 
 // how the certificate / rescoring cut bound is obtained (see Options::bf16_eps)
@@ -202,6 +217,8 @@ struct CertParams {
     int metric;
 };
 int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_t stream);
+// wide first slab: the best kprime (and ties) of the 16 scratch segments of every query -> its pool
+int launch_wide_select(Pool seg, Pool pool, int batch, int kprime, cudaStream_t stream);
 // exact fp64 rescoring of the pool's first min(cnt, kprime) entries + final (score desc, id asc)
 // selection with the exactness certificate
 int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprime, int metric,

@@ -234,7 +234,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     CMW_REQUIRE(gemm_supported(s), "launch_gemm: store has no bf16 tiles / TMA descriptor");
     if (a.row_end <= a.row_begin) return 0;
     if (a.dense)
-        CMW_REQUIRE(a.row_end - a.row_begin <= kPoolCap, "launch_gemm: dense slab larger than the pool");
+        CMW_REQUIRE(a.row_end - a.row_begin <= (a.wide_scores ? a.wide_stride : kPoolCap),
+                    "launch_gemm: dense slab larger than its destination");
     // tensor-bound batches run on CTA pairs (cta_group::2); the HBM-bound ones on single CTAs
     if (g_opt.gemm_2cta != 0 && a.bpad >= (int)g_opt.gemm_2cta_min_batch && (a.bpad % 256 == 0 || (a.bpad < 256 && a.bpad % 64 == 0)) &&
         (a.row_begin % (2 * kTileM)) == 0)
@@ -255,6 +256,9 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     if (nst > kMaxStages) nst = kMaxStages;
     p.nstages = nst;
     p.dense = a.dense;
+    p.dense_scores = a.wide_scores ? a.wide_scores : a.pool.scores;
+    p.dense_ids = a.wide_scores ? a.wide_ids : a.pool.ids;
+    p.dense_stride = a.wide_scores ? a.wide_stride : kPoolCap;
     p.dynamic = 0;
     // instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);

@@ -351,6 +351,9 @@ int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
     if (nst > kMaxStages) nst = kMaxStages;
     p.nstages = nst;
     p.dense = a.dense;
+    p.dense_scores = a.wide_scores ? a.wide_scores : a.pool.scores;
+    p.dense_ids = a.wide_scores ? a.wide_ids : a.pool.ids;
+    p.dense_stride = a.wide_scores ? a.wide_stride : kPoolCap;
     // instruction descriptor: D = f32, A = B = bf16, K-major, N >> 3 at bit 17, M = 256 >> 4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
     p.row_mul = a.row_mul;

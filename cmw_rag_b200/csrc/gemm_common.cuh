@@ -28,6 +28,9 @@ struct GemmParams {
     int nstages;
     int stage_bytes;
     int dense;
+    float* dense_scores;  // dense slab: where the scores go ([query, dense_stride]: the pools, or the wide scratch)
+    int32_t* dense_ids;
+    int dense_stride;
     int dynamic;          // CTA-pair kernel: 1 = work items handed out by cluster launch control
     uint32_t idesc;
     const float* row_mul;
@@ -131,9 +134,9 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, uint32_t tadd
             for (int j = 0; j < 32; ++j) {
                 if (j < cend && row_ok) {
                     const float s = __uint_as_float(v[j]) * mul;
-                    const size_t pos = (size_t)(q0 + c0 + j) * kPoolCap + slot;
-                    p.pool_scores[pos] = (s == s) ? s : -INFINITY;
-                    p.pool_ids[pos] = (int32_t)row;
+                    const size_t pos = (size_t)(q0 + c0 + j) * (size_t)p.dense_stride + slot;
+                    p.dense_scores[pos] = (s == s) ? s : -INFINITY;
+                    p.dense_ids[pos] = (int32_t)row;
                 }
             }
         } else {

@@ -14,10 +14,18 @@ namespace cmw {
 __global__ void __launch_bounds__(256)
 prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, int metric,
                     double* __restrict__ qn64, double* __restrict__ q4, float* __restrict__ q_f32,
-                    __nv_bfloat16* __restrict__ q_bf16, Pool pool, int dense_count) {
+                    __nv_bfloat16* __restrict__ q_bf16, Pool pool, int dense_count, Pool seg, int wide_rows) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= bpad) return;
+    // wide first slab: the 16 scratch segments of this query start out holding their share of its rows
+    if (seg.cnt != nullptr && b < batch && lane < kWideSegments) {
+        int c = wide_rows - lane * kPoolCap;
+        c = c < 0 ? 0 : (c > kPoolCap ? kPoolCap : c);
+        seg.cnt[b * kWideSegments + lane] = c;
+        seg.thr[b * kWideSegments + lane] = -INFINITY;
+        seg.ovf[b * kWideSegments + lane] = 0;
+    }
     const int nvec = dim >> 2;
     // pool state for the new search: the dense slab will fill `dense_count` slots of every real query;
     // cnt/thr/ovf hold bpad entries and the padded queries of the last K2 group keep thr = +inf so that
@@ -76,11 +84,11 @@ prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, i
 }
 
 int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64, double* q4,
-                        float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count,
+                        float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count, Pool seg, int wide_rows,
                         cudaStream_t stream) {
     const int wpb = 8;
-    prep_queries_kernel<<<(bpad + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, batch, bpad, dim, metric,
-                                                                        qn64, q4, q_f32, q_bf16, pool, dense_count);
+    prep_queries_kernel<<<(bpad + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, batch, bpad, dim, metric, qn64, q4, q_f32,
+                                                                        q_bf16, pool, dense_count, seg, wide_rows);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
@@ -229,6 +237,140 @@ __global__ void __launch_bounds__(kCompactThreads, 5) pool_compact_kernel(Pool p
 int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_t stream) {
     const size_t smem = final ? (size_t)kPoolCap * sizeof(uint64_t) : 0;
     pool_compact_kernel<<<batch, kCompactThreads, smem, stream>>>(pool, kprime, final);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wide first slab (small batches): the filter wrote the scores and ids of up to 65536 rows into a scratch
+// matrix laid out as 16 pool-sized segments per query.  Level 1 = the ordinary compaction kernel over the
+// batch * 16 segments (each keeps its best kprime and ties, in parallel on as many SMs); level 2 = this
+// kernel: one CTA per query gathers the segments' survivors (<= 16 * kprime + ties), selects the kprime-th
+// best of them exactly like the compaction kernel, moves those entries into the query's pool and publishes
+// thr.  An entry that is among the best kprime overall is among the best kprime of its segment, so the cut
+// is exact; ties at the cut survive level 1 for the same reason.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCompactThreads, 5) wide_merge_kernel(Pool seg, Pool pool, int kprime) {
+    __shared__ int hist[256];
+    __shared__ int warp_sums[32];
+    __shared__ int sel_digit, sel_below;
+    __shared__ int seg_off[kWideSegments + 1];
+    __shared__ int seg_flag;
+    const int b = blockIdx.x;
+    const int t = threadIdx.x;
+    if (t < 32) {
+        const int c = (t < kWideSegments) ? seg.cnt[b * kWideSegments + t] : 0;
+        const int of = (t < kWideSegments) ? seg.ovf[b * kWideSegments + t] : 0;
+        int v = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, v, o);
+            if (t >= o) v += u;
+        }
+        if (t < kWideSegments) seg_off[t + 1] = v;
+        if (t == 0) seg_off[0] = 0;
+        const unsigned any = __ballot_sync(0xffffffffu, of != 0);
+        if (t == 0) seg_flag = any != 0u;
+    }
+    __syncthreads();
+    const int n_in = seg_off[kWideSegments];
+    const int n = n_in < kPoolCap ? n_in : kPoolCap;
+    uint32_t key[kCompactPer];
+    int32_t rid[kCompactPer];
+#pragma unroll
+    for (int j = 0; j < kCompactPer; ++j) {
+        const int i = t + j * kCompactThreads;
+        key[j] = 0xffffffffu;
+        rid[j] = -1;
+        if (i < n) {
+            int sgm = 0;
+#pragma unroll
+            for (int q = 1; q < kWideSegments; ++q) sgm += (i >= seg_off[q]) ? 1 : 0;
+            const size_t src = ((size_t)b * kWideSegments + sgm) * kPoolCap + (size_t)(i - seg_off[sgm]);
+            key[j] = (uint32_t)(desc_key(seg.scores[src], 0u) >> 32);
+            rid[j] = seg.ids[src];
+        }
+    }
+    uint32_t T = 0xffffffffu;
+    const bool select = n > kprime;
+    if (select) {
+        uint32_t prefix = 0, mask = 0;
+        int remaining = kprime;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            hist[t] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < kCompactPer; ++j) {
+                if (rid[j] >= 0 && (key[j] & mask) == prefix) atomicAdd(&hist[(key[j] >> shift) & 255u], 1);
+            }
+            __syncthreads();
+            const int h = hist[t];
+            int v = h;
+            const int lane = t & 31, w = t >> 5;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += u;
+            }
+            if (lane == 31) warp_sums[w] = v;
+            __syncthreads();
+            int base = 0;
+            for (int ww = 0; ww < w; ++ww) base += warp_sums[ww];
+            const int cum = base + v;
+            if (cum >= remaining && cum - h < remaining) {
+                sel_digit = t;
+                sel_below = cum - h;
+            }
+            __syncthreads();
+            prefix |= (uint32_t)sel_digit << shift;
+            mask |= 0xffu << shift;
+            remaining -= sel_below;
+            __syncthreads();
+        }
+        T = prefix;
+    }
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < kCompactPer; ++j) mine += (rid[j] >= 0 && key[j] <= T) ? 1 : 0;
+    const int lane = t & 31, w = t >> 5;
+    int v = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    __syncthreads();
+    if (lane == 31) warp_sums[w] = v;
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int ww = 0; ww < kCompactThreads / 32; ++ww) {
+        if (ww < w) base += warp_sums[ww];
+        total += warp_sums[ww];
+    }
+    int pos = base + v - mine;
+    float* sc = pool.scores + (size_t)b * kPoolCap;
+    int32_t* id = pool.ids + (size_t)b * kPoolCap;
+#pragma unroll
+    for (int j = 0; j < kCompactPer; ++j) {
+        if (rid[j] >= 0 && key[j] <= T) {
+            sc[pos] = f32_from_orderable(~key[j]);
+            id[pos] = rid[j];
+            ++pos;
+        }
+    }
+    if (t == 0) {
+        pool.cnt[b] = total;
+        if (select) pool.thr[b] = f32_from_orderable(~T);
+        if (n_in > kPoolCap || seg_flag) pool.ovf[b] = 1;
+    }
+}
+
+int launch_wide_select(Pool seg, Pool pool, int batch, int kprime, cudaStream_t stream) {
+    int rc = launch_pool_compact(seg, batch * kWideSegments, kprime, 0, stream);
+    if (rc) return rc;
+    wide_merge_kernel<<<batch, kCompactThreads, 0, stream>>>(seg, pool, kprime);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;

@@ -36,6 +36,9 @@ struct ScanParams {
     int mul_offset;   // byte offset of the multiplier region inside a stage
     int nstages;
     int dense;
+    float* dense_scores;
+    int32_t* dense_ids;
+    int dense_stride;
     float* pool_scores;
     int32_t* pool_ids;
     int32_t* pool_cnt;
@@ -224,9 +227,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
                 for (int i = 0; i < NQ; ++i) {
                     const float sc = acc[i] * m;
                     if (p.dense) {
-                        const size_t pos = (size_t)i * kPoolCap + (size_t)(r - p.row_begin);
-                        p.pool_scores[pos] = (sc == sc) ? sc : -INFINITY;
-                        p.pool_ids[pos] = (int32_t)r;
+                        const size_t pos = (size_t)i * (size_t)p.dense_stride + (size_t)(r - p.row_begin);
+                        p.dense_scores[pos] = (sc == sc) ? sc : -INFINITY;
+                        p.dense_ids[pos] = (int32_t)r;
                     } else if (sc >= thr[i]) {
                         const int pos = atomicAdd(p.pool_cnt + i, 1);
                         if (pos < kPoolCap) {
@@ -290,12 +293,16 @@ int launch_scan(const ScanArgs& a, cudaStream_t stream) {
     CMW_REQUIRE(nst >= 2, "launch_scan: dim %d too large for the staging ring", a.dim);
     p.nstages = nst;
     p.dense = a.dense;
+    p.dense_scores = a.wide_scores ? a.wide_scores : a.pool.scores;
+    p.dense_ids = a.wide_scores ? a.wide_ids : a.pool.ids;
+    p.dense_stride = a.wide_scores ? a.wide_stride : kPoolCap;
     p.pool_scores = a.pool.scores;
     p.pool_ids = a.pool.ids;
     p.pool_cnt = a.pool.cnt;
     p.pool_thr = a.pool.thr;
     if (a.dense)
-        CMW_REQUIRE(a.row_end - a.row_begin <= kPoolCap, "launch_scan: dense slab larger than the pool");
+        CMW_REQUIRE(a.row_end - a.row_begin <= (a.wide_scores ? a.wide_stride : kPoolCap),
+                    "launch_scan: dense slab larger than its destination");
     const size_t smem = (size_t)nst * p.stage_bytes + tail;
     const int64_t total_stages = (a.row_end - a.row_begin + R - 1) / R;
     int grid = a.sm_count;

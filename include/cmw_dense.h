@@ -189,6 +189,8 @@ int cmw_profile_read(double* ms, int64_t* counts, int n);
  *   "bf16_eps" (0 = automatic, dimension-aware), "bf16_sigmas" (8), "f32_eps" (4e-6)   certificate bounds
  *   "strict_certificate" (0)  1 = rigorous Cauchy-Schwarz bound behind the bf16 filter (K' = max(512, 4k))
  *   "repair" (2)              cmw_search_host repair chain for flagged queries: 0 off, 1 stage 1, 2 both stages
+ *   "wide_dense" (1)          batches up to 32: 65536-row first slab through a scratch matrix, then the rest of
+ *                             the corpus in one launch when the expected admissions fit the pool
  *   "host_overlap" (0)        pipelined host API: 1 = a ticket's finalisation runs next to the following ticket's filter (measured: no gain)
  *   "slab_growth" (0 = automatic)   cap on the geometric growth of the slabs
  *   "pool_cap" (read-only)    candidate-pool slots per query */

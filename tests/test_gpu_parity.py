@@ -194,11 +194,78 @@ def test_adversarial_ascending_order(torch_cuda):
     _check_exact(ids, sc, ref_ids, ref_sc)
     import torch
 
-    _, _, fl_dev = st.search(torch.from_numpy(q).cuda(), 10)  # device API: reports, never hides
-    sc2, ids2, fl2 = st.search(torch.from_numpy(q).cuda(), 10, algo="scan_safe")
+    from cmw_rag_b200 import _native as N
+
+    # small batches take a wide first slab (65536 rows through a scratch matrix): this whole corpus fits in
+    # it, so even the device API gets the exact answer without a flag
+    sc1, ids1, fl1 = st.search(torch.from_numpy(q).cuda(), 10)
     torch.cuda.synchronize()
-    assert int(fl_dev[0]) == 1 and int(fl2[0]) == 0
-    _check_exact(ids2.cpu().numpy(), sc2.cpu().numpy(), ref_ids, ref_sc)
+    assert int(fl1[0]) == 0
+    _check_exact(ids1.cpu().numpy(), sc1.cpu().numpy(), ref_ids, ref_sc)
+    N.set_option("wide_dense", 0)
+    try:
+        _, _, fl_dev = st.search(torch.from_numpy(q).cuda(), 10)  # device API: reports, never hides
+        sc2, ids2, fl2 = st.search(torch.from_numpy(q).cuda(), 10, algo="scan_safe")
+        torch.cuda.synchronize()
+        assert int(fl_dev[0]) == 1 and int(fl2[0]) == 0
+        _check_exact(ids2.cpu().numpy(), sc2.cpu().numpy(), ref_ids, ref_sc)
+        sc, ids, fl = st.search_host(q, 10)  # host API: falls back to the overflow-proof schedule
+        assert fl[0] == 0
+        _check_exact(ids, sc, ref_ids, ref_sc)
+    finally:
+        N.set_option("wide_dense", 1)
+    st.close()
+
+
+def test_wide_first_slab_paths(torch_cuda):
+    """Small batches: wide first slab (two-level selection over 16 scratch segments per query) and the rest of
+    the corpus in one launch.  Ties at the cut, thousands of near matches, tombstones inside the slab, corpora
+    just below / at / above one wide slab, a sorted corpus whose single rest launch overflows the pool (flagged
+    on the device API, repaired by the host API) -- and the answer must not depend on the option."""
+    import torch
+
+    from cmw_rag_b200 import DenseStore
+    from cmw_rag_b200 import _native as N
+
+    d, k = 64, 50
+    rng = np.random.default_rng(8)
+    for n in (4097, 20000, 65536, 65537, 150000):
+        c = synth.make_corpus(n, d, seed=300 + n % 97, ties=False)
+        q, _ = synth.make_queries(c, 5, seed=9, tie_probe=False)
+        c[100:400] = c[7]  # 300 exact duplicates near the top of query 0
+        q[0] = c[7] + 0.1 * q[0]
+        strong = np.arange(2100) + min(n - 2200, 9000) if n >= 12000 else np.arange(0)
+        c[strong] = q[1][None, :] + 0.02 * rng.standard_normal((strong.size, d)).astype(np.float32)
+        live = np.ones(n, bool)
+        live[rng.integers(0, n, size=n // 50)] = False
+        st = DenseStore(d, n)
+        st.append(c)
+        st.tombstone(np.flatnonzero(~live))
+        ref_ids, ref_sc, _ = exact_topk_c(c, q, k, live=live)
+        for wide in (1, 0):
+            N.set_option("wide_dense", wide)
+            try:
+                for algo in ("auto", "scan"):
+                    sc, ids, fl = st.search_host(q, k, algo=algo)
+                    assert (fl == 0).all(), (n, wide, algo)
+                    _check_exact(ids, sc, ref_ids, ref_sc)
+            finally:
+                N.set_option("wide_dense", 1)
+        st.close()
+    # rows sorted by ascending score, more than one wide slab: the rest launch admits far more than a pool
+    n = 200000
+    q = rng.standard_normal((1, d)).astype(np.float32)
+    c = rng.standard_normal((n, d)).astype(np.float32)
+    c = np.ascontiguousarray(c[np.argsort((c @ q[0]) / np.linalg.norm(c, axis=1))])
+    st = DenseStore(d, n)
+    st.append(c)
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, 10)
+    _, _, fl_dev = st.search(torch.from_numpy(q).cuda(), 10)
+    torch.cuda.synchronize()
+    assert int(fl_dev[0]) == 1
+    sc, ids, fl = st.search_host(q, 10)
+    assert fl[0] == 0
+    _check_exact(ids, sc, ref_ids, ref_sc)
     st.close()
 
 
