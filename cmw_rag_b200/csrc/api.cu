@@ -476,9 +476,9 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
         if (wide) {
             {
                 PhaseTimer t(1, stream);
-                if ((rc = launch_wide_select(seg, pool, batch, kprime, stream))) return rc;
+                // (the merge kernel also sorts and truncates when nothing else follows)
+                if ((rc = launch_wide_select(seg, pool, batch, kprime, slab0 == rows ? 1 : 0, stream))) return rc;
             }
-            if (slab0 == rows && (rc = compact(true))) return rc;  // nothing else follows: sort the survivors
         } else if ((rc = compact(slab0 == rows))) {
             return rc;
         }

@@ -218,7 +218,7 @@ struct CertParams {
 };
 int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_t stream);
 // wide first slab: the best kprime (and ties) of the 16 scratch segments of every query -> its pool
-int launch_wide_select(Pool seg, Pool pool, int batch, int kprime, cudaStream_t stream);
+int launch_wide_select(Pool seg, Pool pool, int batch, int kprime, int final, cudaStream_t stream);
 // exact fp64 rescoring of the pool's first min(cnt, kprime) entries + final (score desc, id asc)
 // selection with the exactness certificate
 int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprime, int metric,

@@ -251,7 +251,8 @@ int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_
 // thr.  An entry that is among the best kprime overall is among the best kprime of its segment, so the cut
 // is exact; ties at the cut survive level 1 for the same reason.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCompactThreads, 5) wide_merge_kernel(Pool seg, Pool pool, int kprime) {
+__global__ void __launch_bounds__(kCompactThreads, 5) wide_merge_kernel(Pool seg, Pool pool, int kprime, int final) {
+    extern __shared__ __align__(16) uint8_t wm_smem[];
     __shared__ int hist[256];
     __shared__ int warp_sums[32];
     __shared__ int sel_digit, sel_below;
@@ -352,25 +353,53 @@ __global__ void __launch_bounds__(kCompactThreads, 5) wide_merge_kernel(Pool seg
     int pos = base + v - mine;
     float* sc = pool.scores + (size_t)b * kPoolCap;
     int32_t* id = pool.ids + (size_t)b * kPoolCap;
+    if (!final) {
+#pragma unroll
+        for (int j = 0; j < kCompactPer; ++j) {
+            if (rid[j] >= 0 && key[j] <= T) {
+                sc[pos] = f32_from_orderable(~key[j]);
+                id[pos] = rid[j];
+                ++pos;
+            }
+        }
+        if (t == 0) {
+            pool.cnt[b] = total;
+            if (select) pool.thr[b] = f32_from_orderable(~T);
+            if (n_in > kPoolCap || seg_flag) pool.ovf[b] = 1;
+        }
+        return;
+    }
+    // the wide slab was the whole corpus: sort the survivors by (score desc, id asc) and keep kprime, exactly
+    // like the final call of the compaction kernel
+    uint64_t* keys = reinterpret_cast<uint64_t*>(wm_smem);
+    const int m = next_pow2(total < 2 ? 2 : total);
+    for (int i = total + t; i < m; i += kCompactThreads) keys[i] = ~0ull;
 #pragma unroll
     for (int j = 0; j < kCompactPer; ++j) {
         if (rid[j] >= 0 && key[j] <= T) {
-            sc[pos] = f32_from_orderable(~key[j]);
-            id[pos] = rid[j];
+            keys[pos] = ((uint64_t)key[j] << 32) | (uint64_t)(uint32_t)rid[j];
             ++pos;
         }
     }
+    bitonic_sort_u64(keys, m);
+    const int keep = total < kprime ? total : kprime;
+    for (int i = t; i < keep; i += kCompactThreads) {
+        const uint64_t kk = keys[i];
+        sc[i] = desc_key_score(kk);
+        id[i] = (int32_t)(uint32_t)kk;
+    }
     if (t == 0) {
-        pool.cnt[b] = total;
-        if (select) pool.thr[b] = f32_from_orderable(~T);
+        pool.cnt[b] = keep;
+        if (total >= kprime) pool.thr[b] = desc_key_score(keys[kprime - 1]);
         if (n_in > kPoolCap || seg_flag) pool.ovf[b] = 1;
     }
 }
 
-int launch_wide_select(Pool seg, Pool pool, int batch, int kprime, cudaStream_t stream) {
+int launch_wide_select(Pool seg, Pool pool, int batch, int kprime, int final, cudaStream_t stream) {
     int rc = launch_pool_compact(seg, batch * kWideSegments, kprime, 0, stream);
     if (rc) return rc;
-    wide_merge_kernel<<<batch, kCompactThreads, 0, stream>>>(seg, pool, kprime);
+    const size_t smem = final ? (size_t)kPoolCap * sizeof(uint64_t) : 0;
+    wide_merge_kernel<<<batch, kCompactThreads, smem, stream>>>(seg, pool, kprime, final);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
