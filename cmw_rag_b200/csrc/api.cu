@@ -8,6 +8,9 @@
 //   for each slab of rows (first slab dense, later slabs growing geometrically):
 //       filter kernel (K1 scan or K2 tcgen05 GEMM) admits rows with score >= thr into the pools
 //       compaction keeps the best K' per query and raises thr
+//   (batches <= 32: a 65536-row first slab through a scratch matrix + two-level selection, then the rest of
+//    the corpus in one launch when its expected admissions fit the pool)
+//   cmw_search_host / _submit / _wait: the same behind H2D / D2H copies, blocking or pipelined
 //   F32_EXACT: fp64 rescoring of the K' survivors from the fp32 tiles + final selection + certificate
 //   BF16:      emit the pool's best k
 #include <string.h>

@@ -1,5 +1,6 @@
-// pool.cu -- query preparation, candidate-pool maintenance, K3 (exact fp64 rescoring + final
-// deterministic selection with an exactness certificate) and K5 (cross-shard merge).
+// pool.cu -- query preparation, candidate-pool maintenance (radix-select compaction; the merge kernel of the
+// wide first slab that small batches take), K3 (exact fp64 rescoring + final deterministic selection with an
+// exactness certificate) and K5 (cross-shard merge).
 //
 // Ordering contract everywhere: score descending, then id ascending (BASELINE.json north_star:
 // "ties broken by lower id"); results are best-first like collection.query() of
