@@ -199,6 +199,9 @@ struct GemmArgs {
     float* wide_scores;           // dense only: scratch [batch, wide_stride] (NULL = the pools)
     int32_t* wide_ids;
     int wide_stride;
+    int strat_mode = 0;           // see GemmParams::strat_mode (1-CTA kernel only)
+    int nseg = 0;
+    int64_t seg_stride = 0;
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 bool gemm_supported(const Store* s);

@@ -90,7 +90,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int item = item_begin; item != item_end; item += item_step) {
                 const int tile = item / p.n_groups;
                 const int group = item - tile * p.n_groups;
-                const int row0 = (int)(p.row_begin + (int64_t)tile * kTileM);
+                const int row0 = (int)tile_row0(p, tile);
                 const int q0 = group * p.nt;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1u);
@@ -159,7 +159,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int group = item - tile * p.n_groups;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-            const int64_t row_warp0 = p.row_begin + (int64_t)tile * kTileM + quarter * 32;
+            const int64_t row_warp0 = tile_row0(p, tile) + quarter * 32;
+            const int64_t dense_slot0 = (p.strat_mode == 1 ? (int64_t)tile * kTileM : row_warp0 - quarter * 32 - p.row_begin) + quarter * 32;
             const int q0 = group * p.nt + half * nt_local;
             int ncols = p.batch - q0;  // real (unpadded) queries in this warp's columns
             if (ncols > nt_local) ncols = nt_local;
@@ -169,7 +170,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                    (uint32_t)(acc * kAccStride + half * nt_local);
             uint64_t* rel = &tmem_empty[acc];
-            epilogue_item(p, taddr, row_warp0, lane, q0, ncols, nt_local, stg, stage_cap,
+            epilogue_item(p, taddr, row_warp0, dense_slot0, lane, q0, ncols, nt_local, stg, stage_cap,
                           [rel, lane]() { if (lane == 0) ptx::mbar_arrive(rel); });
         }
     }
@@ -234,10 +235,11 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     CMW_REQUIRE(gemm_supported(s), "launch_gemm: store has no bf16 tiles / TMA descriptor");
     if (a.row_end <= a.row_begin) return 0;
     if (a.dense)
-        CMW_REQUIRE(a.row_end - a.row_begin <= (a.wide_scores ? a.wide_stride : kPoolCap),
+        CMW_REQUIRE((a.strat_mode == 1 ? (int64_t)a.nseg * kPoolCap : a.row_end - a.row_begin) <=
+                        (a.wide_scores ? a.wide_stride : kPoolCap),
                     "launch_gemm: dense slab larger than its destination");
     // tensor-bound batches run on CTA pairs (cta_group::2); the HBM-bound ones on single CTAs
-    if (g_opt.gemm_2cta != 0 && a.bpad >= (int)g_opt.gemm_2cta_min_batch && (a.bpad % 256 == 0 || (a.bpad < 256 && a.bpad % 64 == 0)) &&
+    if (a.strat_mode == 0 && g_opt.gemm_2cta != 0 && a.bpad >= (int)g_opt.gemm_2cta_min_batch && (a.bpad % 256 == 0 || (a.bpad < 256 && a.bpad % 64 == 0)) &&
         (a.row_begin % (2 * kTileM)) == 0)
         return launch_gemm_2cta(a, stream);
     GemmParams p;
@@ -249,7 +251,25 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.batch = a.batch;
     p.row_begin = a.row_begin;
     p.row_end = a.row_end;
-    p.n_tiles = (int)((a.row_end - a.row_begin + kTileM - 1) / kTileM);
+    p.strat_mode = a.strat_mode;
+    p.nseg = a.nseg;
+    p.seg_stride = a.seg_stride;
+    if (a.strat_mode == 0) {
+        p.n_tiles = (int)((a.row_end - a.row_begin + kTileM - 1) / kTileM);
+    } else {
+        CMW_REQUIRE(a.row_begin == 0 && a.seg_stride % kTileM == 0 && a.seg_stride >= kPoolCap && a.nseg >= 2 &&
+                        (int64_t)(a.nseg - 1) * a.seg_stride + kPoolCap <= a.row_end,
+                    "launch_gemm: bad sampled-slab geometry");
+        const int seg_tiles = kPoolCap / kTileM;
+        if (a.strat_mode == 1) {
+            p.n_tiles = a.nseg * seg_tiles;
+        } else {
+            const int per_block = (int)(a.seg_stride / kTileM) - seg_tiles;
+            const int64_t covered = (int64_t)(a.nseg - 1) * a.seg_stride + kPoolCap;
+            p.n_tiles = (a.nseg - 1) * per_block + (int)((a.row_end - covered + kTileM - 1) / kTileM);
+        }
+        if (p.n_tiles == 0) return 0;
+    }
     p.stage_bytes = kABytes + p.nt * kBlockK * 2;
     const size_t tail = (2 * kMaxStages + 4) * sizeof(uint64_t) + 64 + 4 * kStageCap * sizeof(uint2);
     int nst = (int)((220 * 1024 - tail - 1024) / (size_t)p.stage_bytes);

@@ -315,7 +315,7 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                    (uint32_t)(acc * kAccStride + half * half_nt);
             uint64_t* rel = &tmem_empty[acc];
-            epilogue_item(p, taddr, row_warp0, lane, q0, ncols, half_nt, stg, kStageCap2,
+            epilogue_item(p, taddr, row_warp0, row_warp0 - p.row_begin, lane, q0, ncols, half_nt, stg, kStageCap2,
                           [rel, lane]() { if (lane == 0) ptx2::mbar_arrive_cluster(rel, 0); });
         }
     }
@@ -351,6 +351,9 @@ int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
     if (nst > kMaxStages) nst = kMaxStages;
     p.nstages = nst;
     p.dense = a.dense;
+    p.strat_mode = 0;
+    p.nseg = 0;
+    p.seg_stride = 0;
     p.dense_scores = a.wide_scores ? a.wide_scores : a.pool.scores;
     p.dense_ids = a.wide_scores ? a.wide_ids : a.pool.ids;
     p.dense_stride = a.wide_scores ? a.wide_stride : kPoolCap;

@@ -31,6 +31,13 @@ struct GemmParams {
     float* dense_scores;  // dense slab: where the scores go ([query, dense_stride]: the pools, or the wide scratch)
     int32_t* dense_ids;
     int dense_stride;
+    // 1-CTA kernel, small batches: 0 = tiles are consecutive from row_begin; 1 = the wide first slab SAMPLES the
+    // corpus: nseg segments of 32 tiles (4096 rows), segment j starting at row j * seg_stride, the first at the
+    // first row and the last ending (within a tile) at the last; 2 = the rest of the corpus: every tile that
+    // mode 1 did not take
+    int strat_mode;
+    int nseg;
+    int64_t seg_stride;   // rows, a multiple of 128, >= 4096
     int dynamic;          // CTA-pair kernel: 1 = work items handed out by cluster launch control
     uint32_t idesc;
     const float* row_mul;
@@ -53,6 +60,21 @@ __device__ __forceinline__ void item_range(int n_items, int n_groups, int w, int
     step = nw;
     begin = w;
     end = (w < n_items) ? w + ((n_items - 1 - w) / nw + 1) * nw : w;
+}
+
+// first corpus row of a 128-row tile of the 1-CTA kernel (see GemmParams::strat_mode)
+__device__ __forceinline__ int64_t tile_row0(const GemmParams& p, int tile) {
+    if (p.strat_mode == 0) return p.row_begin + (int64_t)tile * kTileM;
+    constexpr int kSegTiles = kPoolCap / kTileM;  // 32
+    if (p.strat_mode == 1) return (int64_t)(tile / kSegTiles) * p.seg_stride + (int64_t)(tile % kSegTiles) * kTileM;
+    // everything else: the gaps between the segments, then the rows behind the last one
+    const int per_block = (int)(p.seg_stride / kTileM) - kSegTiles;  // unsampled tiles per gap
+    const int in_blocks = (p.nseg - 1) * per_block;
+    if (tile < in_blocks) {
+        const int blk = tile / per_block;
+        return (int64_t)blk * p.seg_stride + (int64_t)(kSegTiles + tile % per_block) * kTileM;
+    }
+    return (int64_t)(p.nseg - 1) * p.seg_stride + kPoolCap + (int64_t)(tile - in_blocks) * kTileM;
 }
 
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
@@ -94,12 +116,13 @@ __device__ __forceinline__ void flush_staged(const uint2* stg, int wcount, int l
 // and the rare survivors are staged in the warp's shared-memory buffer (ballot + popc, no atomics).
 // `release()` is called once every tcgen05.ld of this accumulator has completed -- before the
 // global-atomic flush, so the MMA warp gets the accumulator back as early as possible.
-// `nt_local` = TMEM columns this warp owns from `taddr` on (the whole query group, or half of it when two
+// `dense_slot0` = dense slab only: the slot of row_warp0 in the destination (row - row_begin, or the position in
+// the sampled wide slab).  `nt_local` = TMEM columns this warp owns from `taddr` on (the whole query group, or half of it when two
 // warps share a lane quarter), `ncols` <= nt_local of them are real queries; `stage_cap` = entries in `stg`.
 template <typename Release>
-__device__ __forceinline__ void epilogue_item(const GemmParams& p, uint32_t taddr, int64_t row_warp0, int lane,
-                                              int q0, int ncols, int nt_local, uint2* stg, int stage_cap,
-                                              Release release) {
+__device__ __forceinline__ void epilogue_item(const GemmParams& p, uint32_t taddr, int64_t row_warp0,
+                                              int64_t dense_slot0, int lane, int q0, int ncols, int nt_local,
+                                              uint2* stg, int stage_cap, Release release) {
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const int64_t row = row_warp0 + lane;
     const bool row_ok = row < p.row_end;
@@ -129,7 +152,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, uint32_t tadd
         ptx::tmem_ld_wait();
         if (p.dense) {
             const int cend = (ncols - c0 < 32) ? (ncols - c0) : 32;
-            const size_t slot = (size_t)(row - p.row_begin);
+            const size_t slot = (size_t)(dense_slot0 + lane);  // where lane 0's row goes in the dense destination
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 if (j < cend && row_ok) {
