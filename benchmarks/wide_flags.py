@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""How often does the single rest launch behind the wide first slab overflow a pool?  Clustered corpus (rows in
-random order, and sorted by cluster = the worst realistic order), batch 16, device API (flags not repaired)."""
+"""How often does a candidate pool overflow?  Clustered corpus, rows in random order and sorted by one coordinate
+(a bad realistic order), batches of 16 (wide first slab + one rest launch) and 256 (4096-row first slab, geometric
+slabs), with the stride permutation of the scan order on and off; device API (flags not repaired)."""
 import json
 import os
 import sys
@@ -26,20 +27,16 @@ for name in ("random_order", "sorted_by_first_coordinate"):
     st = DenseStore(d, n)
     st.append(c)
     res = {}
-    for wide in (1, 0):
-        N.set_option("wide_dense", wide)
-        flags = 0
-        ids_all = []
-        for lo in range(0, 256, 16):
-            sc, ids, fl = st.search(torch.from_numpy(q[lo:lo + 16]).cuda(), k)
-            torch.cuda.synchronize()
-            flags += int(fl.sum())
-            ids_all.append(ids.cpu().numpy())
-        res[f"wide_dense={wide}"] = {"flagged_queries": flags}
-        res[f"ids_{wide}"] = np.concatenate(ids_all)
-    N.set_option("wide_dense", 1)
-    same = bool((res.pop("ids_1") == res.pop("ids_0")).all())
-    res["same_ids_both_ways"] = same
+    for batch in (16, 256):
+        for permute in (1, 0):
+            N.set_option("scan_permute", permute)
+            flags = 0
+            for lo in range(0, 256, batch):
+                sc, ids, fl = st.search(torch.from_numpy(q[lo:lo + batch]).cuda(), k)
+                torch.cuda.synchronize()
+                flags += int(fl.sum())
+            res[f"batch={batch},scan_permute={permute}"] = {"flagged_queries_of_256": flags}
+    N.set_option("scan_permute", 1)
     out[name] = res
     st.close()
 print(json.dumps(out))

@@ -393,13 +393,6 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
                                : (rows < kDenseSlabRows ? rows : (int64_t)kDenseSlabRows);
     // expected pool fill if everything after the first slab went through one launch
     const double rest_fill = (double)(rows - slab0) * kprime / (double)(slab0 > 0 ? slab0 : 1) + kprime;
-    // K2 takes the wide slab as a STRATIFIED SAMPLE -- wide_segs segments of 4096 rows spread evenly over the
-    // corpus -- whenever the rest then fits one launch: a threshold from the first rows of a corpus that is
-    // sorted by anything correlated with relevance admits several times the estimate (clustered corpus sorted by
-    // one coordinate: 15 % of the queries overflowed behind a contiguous wide slab, none behind the sample)
-    const bool strat = wide && gemm && rows > wide_rows && rest_fill <= 0.85 * kPoolCap;
-    // (the first segment starts at the first row, the last one ends -- within a tile -- at the last row)
-    const int64_t seg_stride = strat ? ((rows - kPoolCap) / (wide_segs - 1)) / 128 * 128 : 0;
     float* wide_scores = nullptr;
     int32_t* wide_ids = nullptr;
     Pool seg = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -429,7 +422,7 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
     if (filter_bf16) row_mul = (metric == CMW_METRIC_COSINE) ? s->live : s->norm;  // rows pre-normalised
     else row_mul = (metric == CMW_METRIC_COSINE) ? s->inv_norm : s->live;          // raw rows
 
-    auto run_filter = [&](int64_t r0, int64_t r1, int dense, int strat_mode) -> int {
+    auto run_filter = [&](int64_t r0, int64_t r1, int dense) -> int {
         PhaseTimer t(0, stream);
         if (gemm) {
             GemmArgs g;
@@ -445,9 +438,6 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
             g.wide_scores = dense ? wide_scores : nullptr;
             g.wide_ids = wide_ids;
             g.wide_stride = kWideDenseRows;
-            g.strat_mode = strat_mode;
-            g.nseg = wide_segs;
-            g.seg_stride = seg_stride;
             return launch_gemm(g, stream);
         }
         for (int b0 = 0; b0 < batch; b0 += 2) {
@@ -487,7 +477,7 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
     if (growth < 1.0) growth = 1.0;
     int64_t seen = 0;
     if (rows > 0) {
-        if ((rc = run_filter(0, strat ? rows : slab0, 1, strat ? 1 : 0))) return rc;
+        if ((rc = run_filter(0, slab0, 1))) return rc;
         if (wide) {
             {
                 PhaseTimer t(1, stream);
@@ -500,14 +490,14 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
         seen = slab0;
         while (seen < rows) {
             int64_t m, end;
-            // After a wide first slab the threshold is the kprime-th best of its rows: the rest of the corpus goes
-            // through ONE launch when its expected admissions, (rows - seen) * kprime / seen, plus the kprime
-            // survivors fill at most 85 % of the pool (up to ~1.05M rows at kprime = 224) and the slab was a
-            // stratified sample (so the estimate holds whatever the row order); behind a contiguous wide slab
-            // (K1, or too many rows) only up to 50 %.  A pool that overflows all the same is flagged and the
-            // query goes through the overflow-proof schedule like any other.
-            if (wide && seen == slab0 && (strat || rest_fill <= 0.5 * kPoolCap)) {
-                if ((rc = run_filter(strat ? 0 : seen, rows, 0, strat ? 2 : 0))) return rc;
+            // After a wide first slab the threshold is the kprime-th best of 65536 rows: the rest of the corpus
+            // goes through ONE launch when its expected admissions, (rows - seen) * kprime / seen, plus the
+            // kprime survivors fill at most 85 % of the pool (up to ~1.05M rows at kprime = 224).  K2 scans the
+            // tiles in a stride permutation, so the slab was a representative sample and the estimate holds
+            // whatever the row order; K1 scans in storage order and gets the single launch only up to 50 %.
+            // A pool that overflows all the same is flagged and repaired like any other overflow.
+            if (wide && seen == slab0 && rest_fill <= ((gemm && g_opt.scan_permute != 0) ? 0.85 : 0.5) * kPoolCap) {
+                if ((rc = run_filter(seen, rows, 0))) return rc;
                 if ((rc = compact(true))) return rc;
                 seen = rows;
                 break;
@@ -524,7 +514,7 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
                 end = seen + m;
                 if (end > rows || rows - end < 4096) end = rows;
             }
-            if ((rc = run_filter(seen, end, 0, 0))) return rc;
+            if ((rc = run_filter(seen, end, 0))) return rc;
             if ((rc = compact(end == rows))) return rc;
             seen = end;
         }

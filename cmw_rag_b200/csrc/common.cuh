@@ -163,6 +163,8 @@ struct Options {
     // batches up to 32: a 65536-row first slab through a scratch matrix, and the rest of the corpus in ONE launch
     // when the expected admissions fit the pool (two filter launches per search instead of four at 1M rows)
     double wide_dense = 1;
+    // K2 scans the row tiles in a stride permutation, so that every slab is a representative sample of the corpus
+    double scan_permute = 1;
     double slab_growth = 0;   // 0 = automatic ((cap - K') / (3 K'), at most 8); else the fixed growth factor
 };
 extern Options g_opt;
@@ -199,9 +201,6 @@ struct GemmArgs {
     float* wide_scores;           // dense only: scratch [batch, wide_stride] (NULL = the pools)
     int32_t* wide_ids;
     int wide_stride;
-    int strat_mode = 0;           // see GemmParams::strat_mode (1-CTA kernel only)
-    int nseg = 0;
-    int64_t seg_stride = 0;
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 bool gemm_supported(const Store* s);

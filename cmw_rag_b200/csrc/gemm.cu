@@ -90,7 +90,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int item = item_begin; item != item_end; item += item_step) {
                 const int tile = item / p.n_groups;
                 const int group = item - tile * p.n_groups;
-                const int row0 = (int)tile_row0(p, tile);
+                const int row0 = (int)(scan_tile(p, tile) * kTileM);
                 const int q0 = group * p.nt;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1u);
@@ -159,8 +159,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int group = item - tile * p.n_groups;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-            const int64_t row_warp0 = tile_row0(p, tile) + quarter * 32;
-            const int64_t dense_slot0 = (p.strat_mode == 1 ? (int64_t)tile * kTileM : row_warp0 - quarter * 32 - p.row_begin) + quarter * 32;
+            const int64_t row_warp0 = scan_tile(p, tile) * kTileM + quarter * 32;
+            const int64_t dense_slot0 = (int64_t)tile * kTileM + quarter * 32;  // position within the slab
             const int q0 = group * p.nt + half * nt_local;
             int ncols = p.batch - q0;  // real (unpadded) queries in this warp's columns
             if (ncols > nt_local) ncols = nt_local;
@@ -230,16 +230,40 @@ bool gemm_supported(const Store* s) { return s->bf16 != nullptr && s->tmap_ok; }
 
 int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream);  // gemm2.cu
 
+// Stride permutation of the store's tiles (GemmParams::perm_mul): multiplier ~ tiles / golden ratio, coprime to
+// the tile count.  Off for a launch that covers the whole store (nothing to be representative of) and for tiny
+// stores.
+void set_scan_order(GemmParams& p, const GemmArgs& a, int tile_rows) {
+    const Store* s = a.store;
+    p.tile_begin = a.row_begin / tile_rows;
+    p.perm_mul = 0;
+    p.perm_tiles = (s->rows + tile_rows - 1) / tile_rows;
+    const bool whole = a.row_begin == 0 && a.row_end >= s->rows;
+    if (g_opt.scan_permute == 0 || whole || p.perm_tiles < 64) return;
+    auto gcd = [](int64_t x, int64_t y) {
+        while (y) {
+            const int64_t t = x % y;
+            x = y;
+            y = t;
+        }
+        return x;
+    };
+    int64_t m = (int64_t)((double)p.perm_tiles * 0.6180339887498949) | 1;
+    while (gcd(m, p.perm_tiles) != 1) m += 2;
+    p.perm_mul = m % p.perm_tiles;
+    // rows are validated against the end of the STORE: a permuted tile can lie anywhere in it
+    p.row_end = s->rows;
+}
+
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     const Store* s = a.store;
     CMW_REQUIRE(gemm_supported(s), "launch_gemm: store has no bf16 tiles / TMA descriptor");
     if (a.row_end <= a.row_begin) return 0;
     if (a.dense)
-        CMW_REQUIRE((a.strat_mode == 1 ? (int64_t)a.nseg * kPoolCap : a.row_end - a.row_begin) <=
-                        (a.wide_scores ? a.wide_stride : kPoolCap),
+        CMW_REQUIRE(a.row_end - a.row_begin <= (a.wide_scores ? a.wide_stride : kPoolCap),
                     "launch_gemm: dense slab larger than its destination");
     // tensor-bound batches run on CTA pairs (cta_group::2); the HBM-bound ones on single CTAs
-    if (a.strat_mode == 0 && g_opt.gemm_2cta != 0 && a.bpad >= (int)g_opt.gemm_2cta_min_batch && (a.bpad % 256 == 0 || (a.bpad < 256 && a.bpad % 64 == 0)) &&
+    if (g_opt.gemm_2cta != 0 && a.bpad >= (int)g_opt.gemm_2cta_min_batch && (a.bpad % 256 == 0 || (a.bpad < 256 && a.bpad % 64 == 0)) &&
         (a.row_begin % (2 * kTileM)) == 0)
         return launch_gemm_2cta(a, stream);
     GemmParams p;
@@ -251,25 +275,9 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.batch = a.batch;
     p.row_begin = a.row_begin;
     p.row_end = a.row_end;
-    p.strat_mode = a.strat_mode;
-    p.nseg = a.nseg;
-    p.seg_stride = a.seg_stride;
-    if (a.strat_mode == 0) {
-        p.n_tiles = (int)((a.row_end - a.row_begin + kTileM - 1) / kTileM);
-    } else {
-        CMW_REQUIRE(a.row_begin == 0 && a.seg_stride % kTileM == 0 && a.seg_stride >= kPoolCap && a.nseg >= 2 &&
-                        (int64_t)(a.nseg - 1) * a.seg_stride + kPoolCap <= a.row_end,
-                    "launch_gemm: bad sampled-slab geometry");
-        const int seg_tiles = kPoolCap / kTileM;
-        if (a.strat_mode == 1) {
-            p.n_tiles = a.nseg * seg_tiles;
-        } else {
-            const int per_block = (int)(a.seg_stride / kTileM) - seg_tiles;
-            const int64_t covered = (int64_t)(a.nseg - 1) * a.seg_stride + kPoolCap;
-            p.n_tiles = (a.nseg - 1) * per_block + (int)((a.row_end - covered + kTileM - 1) / kTileM);
-        }
-        if (p.n_tiles == 0) return 0;
-    }
+    p.n_tiles = (int)((a.row_end - a.row_begin + kTileM - 1) / kTileM);
+    CMW_REQUIRE(a.row_begin % kTileM == 0, "launch_gemm: slab start must be a multiple of %d rows", kTileM);
+    set_scan_order(p, a, kTileM);
     p.stage_bytes = kABytes + p.nt * kBlockK * 2;
     const size_t tail = (2 * kMaxStages + 4) * sizeof(uint64_t) + 64 + 4 * kStageCap * sizeof(uint2);
     int nst = (int)((220 * 1024 - tail - 1024) / (size_t)p.stage_bytes);

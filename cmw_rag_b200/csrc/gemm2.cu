@@ -232,7 +232,7 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 }
                 const int tile = item / p.n_groups;
                 const int group = item - tile * p.n_groups;
-                const int row0 = (int)(p.row_begin + (int64_t)tile * (2 * kTileM)) + (int)rank * kTileM;
+                const int row0 = (int)(scan_tile(p, tile) * (2 * kTileM)) + (int)rank * kTileM;
                 const int q0 = group * p.nt + (int)rank * half_nt;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1u);
@@ -304,8 +304,8 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const int group = item - tile * p.n_groups;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-            const int64_t row_warp0 =
-                p.row_begin + (int64_t)tile * (2 * kTileM) + (int64_t)rank * kTileM + quarter * 32;
+            const int64_t row_warp0 = scan_tile(p, tile) * (2 * kTileM) + (int64_t)rank * kTileM + quarter * 32;
+            const int64_t dense_slot0 = (int64_t)tile * (2 * kTileM) + (int64_t)rank * kTileM + quarter * 32;
             const int q0 = group * p.nt + half * half_nt;
             int ncols = p.batch - q0;
             if (ncols > half_nt) ncols = half_nt;
@@ -315,7 +315,7 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                    (uint32_t)(acc * kAccStride + half * half_nt);
             uint64_t* rel = &tmem_empty[acc];
-            epilogue_item(p, taddr, row_warp0, row_warp0 - p.row_begin, lane, q0, ncols, half_nt, stg, kStageCap2,
+            epilogue_item(p, taddr, row_warp0, dense_slot0, lane, q0, ncols, half_nt, stg, kStageCap2,
                           [rel, lane]() { if (lane == 0) ptx2::mbar_arrive_cluster(rel, 0); });
         }
     }
@@ -331,6 +331,7 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 }
 
 int encode_2d(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows);  // gemm.cu
+void set_scan_order(GemmParams& p, const GemmArgs& a, int tile_rows);                     // gemm.cu
 
 int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
     const Store* s = a.store;
@@ -344,6 +345,7 @@ int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
     p.row_begin = a.row_begin;
     p.row_end = a.row_end;
     p.n_tiles = (int)((a.row_end - a.row_begin + 2 * kTileM - 1) / (2 * kTileM));
+    set_scan_order(p, a, 2 * kTileM);
     p.stage_bytes = kABytes + (p.nt / 2) * kBlockK * 2;
     const size_t tail = (2 * kMaxStages + 4) * sizeof(uint64_t) + 64 + kGemm2EpiWarps * kStageCap2 * sizeof(uint2) +
                         kClcDepth * (sizeof(uint4) + 2 * sizeof(uint64_t));
@@ -351,9 +353,6 @@ int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
     if (nst > kMaxStages) nst = kMaxStages;
     p.nstages = nst;
     p.dense = a.dense;
-    p.strat_mode = 0;
-    p.nseg = 0;
-    p.seg_stride = 0;
     p.dense_scores = a.wide_scores ? a.wide_scores : a.pool.scores;
     p.dense_ids = a.wide_scores ? a.wide_ids : a.pool.ids;
     p.dense_stride = a.wide_scores ? a.wide_stride : kPoolCap;

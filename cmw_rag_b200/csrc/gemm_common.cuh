@@ -31,13 +31,14 @@ struct GemmParams {
     float* dense_scores;  // dense slab: where the scores go ([query, dense_stride]: the pools, or the wide scratch)
     int32_t* dense_ids;
     int dense_stride;
-    // 1-CTA kernel, small batches: 0 = tiles are consecutive from row_begin; 1 = the wide first slab SAMPLES the
-    // corpus: nseg segments of 32 tiles (4096 rows), segment j starting at row j * seg_stride, the first at the
-    // first row and the last ending (within a tile) at the last; 2 = the rest of the corpus: every tile that
-    // mode 1 did not take
-    int strat_mode;
-    int nseg;
-    int64_t seg_stride;   // rows, a multiple of 128, >= 4096
+    // Scan order.  Tile g of the store (g = tile_begin + the launch's tile index; a tile = 128 rows, or 256 for a
+    // CTA pair) covers the rows of tile (g * perm_mul) mod perm_tiles: a stride permutation with perm_mul
+    // coprime to perm_tiles and close to perm_tiles / golden ratio, so that ANY range of consecutive tile
+    // indices -- every slab -- is a low-discrepancy sample of the whole corpus and the admission thresholds
+    // it yields are valid estimates whatever order the corpus is stored in.  perm_mul = 0: identity.
+    int64_t tile_begin;
+    int64_t perm_mul;
+    int64_t perm_tiles;
     int dynamic;          // CTA-pair kernel: 1 = work items handed out by cluster launch control
     uint32_t idesc;
     const float* row_mul;
@@ -62,19 +63,10 @@ __device__ __forceinline__ void item_range(int n_items, int n_groups, int w, int
     end = (w < n_items) ? w + ((n_items - 1 - w) / nw + 1) * nw : w;
 }
 
-// first corpus row of a 128-row tile of the 1-CTA kernel (see GemmParams::strat_mode)
-__device__ __forceinline__ int64_t tile_row0(const GemmParams& p, int tile) {
-    if (p.strat_mode == 0) return p.row_begin + (int64_t)tile * kTileM;
-    constexpr int kSegTiles = kPoolCap / kTileM;  // 32
-    if (p.strat_mode == 1) return (int64_t)(tile / kSegTiles) * p.seg_stride + (int64_t)(tile % kSegTiles) * kTileM;
-    // everything else: the gaps between the segments, then the rows behind the last one
-    const int per_block = (int)(p.seg_stride / kTileM) - kSegTiles;  // unsampled tiles per gap
-    const int in_blocks = (p.nseg - 1) * per_block;
-    if (tile < in_blocks) {
-        const int blk = tile / per_block;
-        return (int64_t)blk * p.seg_stride + (int64_t)(kSegTiles + tile % per_block) * kTileM;
-    }
-    return (int64_t)(p.nseg - 1) * p.seg_stride + kPoolCap + (int64_t)(tile - in_blocks) * kTileM;
+// store tile scanned as tile `tile` of this launch (see GemmParams::perm_mul)
+__device__ __forceinline__ int64_t scan_tile(const GemmParams& p, int tile) {
+    const int64_t g = p.tile_begin + tile;
+    return p.perm_mul ? (g * p.perm_mul) % p.perm_tiles : g;
 }
 
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
@@ -155,11 +147,13 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, uint32_t tadd
             const size_t slot = (size_t)(dense_slot0 + lane);  // where lane 0's row goes in the dense destination
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                if (j < cend && row_ok) {
-                    const float s = __uint_as_float(v[j]) * mul;
+                if (j < cend) {
+                    // (a row beyond the end of the store -- the partial last tile can sit anywhere in a permuted
+                    // slab -- gets -inf like a tombstoned one)
+                    const float s = row_ok ? __uint_as_float(v[j]) * mul : -INFINITY;
                     const size_t pos = (size_t)(q0 + c0 + j) * (size_t)p.dense_stride + slot;
                     p.dense_scores[pos] = (s == s) ? s : -INFINITY;
-                    p.dense_ids[pos] = (int32_t)row;
+                    p.dense_ids[pos] = row_ok ? (int32_t)row : 0;
                 }
             }
         } else {

@@ -217,6 +217,7 @@ int cmw_set_option(const char* name, double value) {
     else if (!strcmp(name, "repair")) g_opt.repair = value;
     else if (!strcmp(name, "host_overlap")) g_opt.host_overlap = value;
     else if (!strcmp(name, "wide_dense")) g_opt.wide_dense = value;
+    else if (!strcmp(name, "scan_permute")) g_opt.scan_permute = value;
     else if (!strcmp(name, "gemm_2cta")) g_opt.gemm_2cta = value;
     else if (!strcmp(name, "gemm_clc")) g_opt.gemm_clc = value;
     else if (!strcmp(name, "gemm_2cta_min_batch")) g_opt.gemm_2cta_min_batch = value;
@@ -240,6 +241,7 @@ double cmw_get_option(const char* name) {
     if (!strcmp(name, "repair")) return g_opt.repair;
     if (!strcmp(name, "host_overlap")) return g_opt.host_overlap;
     if (!strcmp(name, "wide_dense")) return g_opt.wide_dense;
+    if (!strcmp(name, "scan_permute")) return g_opt.scan_permute;
     if (!strcmp(name, "gemm_2cta")) return g_opt.gemm_2cta;
     if (!strcmp(name, "gemm_clc")) return g_opt.gemm_clc;
     if (!strcmp(name, "gemm_2cta_min_batch")) return g_opt.gemm_2cta_min_batch;

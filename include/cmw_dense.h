@@ -191,6 +191,8 @@ int cmw_profile_read(double* ms, int64_t* counts, int n);
  *   "repair" (2)              cmw_search_host repair chain for flagged queries: 0 off, 1 stage 1, 2 both stages
  *   "wide_dense" (1)          batches up to 32: 65536-row first slab through a scratch matrix, then the rest of
  *                             the corpus in one launch when the expected admissions fit the pool
+ *   "scan_permute" (1)        K2 scans the row tiles in a stride permutation: every slab is a representative sample
+ *                             of the corpus, the admission thresholds hold whatever order the corpus is stored in
  *   "host_overlap" (0)        pipelined host API: 1 = a ticket's finalisation runs next to the following ticket's filter (measured: no gain)
  *   "slab_growth" (0 = automatic)   cap on the geometric growth of the slabs
  *   "pool_cap" (read-only)    candidate-pool slots per query */

@@ -202,18 +202,29 @@ def test_adversarial_ascending_order(torch_cuda):
     torch.cuda.synchronize()
     assert int(fl1[0]) == 0
     _check_exact(ids1.cpu().numpy(), sc1.cpu().numpy(), ref_ids, ref_sc)
+    # without the wide slab K2 still scans the tiles in a stride permutation: every slab is a representative
+    # sample, no pool overflows
     N.set_option("wide_dense", 0)
     try:
+        sc3, ids3, fl3 = st.search(torch.from_numpy(q).cuda(), 10)
+        torch.cuda.synchronize()
+        assert int(fl3[0]) == 0
+        _check_exact(ids3.cpu().numpy(), sc3.cpu().numpy(), ref_ids, ref_sc)
+        # in storage order (scan_permute = 0, or K1) every slab floods the pool: the device API reports it, the
+        # overflow-proof schedule and the host API's repair chain get the exact answer
+        N.set_option("scan_permute", 0)
         _, _, fl_dev = st.search(torch.from_numpy(q).cuda(), 10)  # device API: reports, never hides
+        _, _, fl_k1 = st.search(torch.from_numpy(q).cuda(), 10, algo="scan")
         sc2, ids2, fl2 = st.search(torch.from_numpy(q).cuda(), 10, algo="scan_safe")
         torch.cuda.synchronize()
-        assert int(fl_dev[0]) == 1 and int(fl2[0]) == 0
+        assert int(fl_dev[0]) == 1 and int(fl_k1[0]) == 1 and int(fl2[0]) == 0
         _check_exact(ids2.cpu().numpy(), sc2.cpu().numpy(), ref_ids, ref_sc)
         sc, ids, fl = st.search_host(q, 10)  # host API: falls back to the overflow-proof schedule
         assert fl[0] == 0
         _check_exact(ids, sc, ref_ids, ref_sc)
     finally:
         N.set_option("wide_dense", 1)
+        N.set_option("scan_permute", 1)
     st.close()
 
 
@@ -252,9 +263,9 @@ def test_wide_first_slab_paths(torch_cuda):
             finally:
                 N.set_option("wide_dense", 1)
         st.close()
-    # rows sorted by ascending score, more rows than one wide slab.  K2 takes the slab as a stratified sample of
-    # the corpus, so its threshold holds for the rest and even the device API is exact without a flag; K1 takes
-    # the first 65536 rows, its geometric slabs overflow, and the host API's repair chain settles it
+    # rows sorted by ascending score, more rows than one wide slab.  K2 scans the tiles in a stride permutation, so
+    # the slab is a representative sample, its threshold holds for the rest and even the device API is exact
+    # without a flag; K1 scans in storage order, overflows, and the host API's repair chain settles it
     n = 200000
     q = rng.standard_normal((1, d)).astype(np.float32)
     c = rng.standard_normal((n, d)).astype(np.float32)
@@ -874,6 +885,14 @@ def test_repeated_host_searches_track_store_changes(torch_cuda):
         _check_exact(ids, sc, np.repeat(ref3, 100, axis=0), np.repeat(ref3_sc, 100, axis=0))
     finally:
         N.set_option("gemm_clc", 1)
+    N.set_option("scan_permute", 0)
+    try:
+        for qq in (q, np.repeat(q, 100, axis=0)):
+            sc, ids, fl = st.search_host(qq, k)
+            reps = qq.shape[0] // 3
+            _check_exact(ids, sc, np.repeat(ref3, reps, axis=0), np.repeat(ref3_sc, reps, axis=0))
+    finally:
+        N.set_option("scan_permute", 1)
     st.close()
 
 
