@@ -353,3 +353,46 @@ def test_sharded_search_world_size_2_gloo(tmp_path):
         capture_output=True, text=True, timeout=300, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert res.stdout.count("ok") == 2
+
+
+def test_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on a tiny corpus: one JSON line with
+    the contract's keys, rank 0 only."""
+    import json
+
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--rows", "12000",
+                          "--hnsw-rows", "12000", "--steps", "2", "--warmup", "1", "--hnsw-queries", "32", "--k", "10"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 2 and d["warmup"] == 1 and d["vs_baseline"] is None
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "HNSW" in cb["sample"]
+    assert cb["index_rows"] == 12000 and 0.0 <= cb["recall_at_k"] <= 1.0
+    # the other ranks of a torchrun launch exit without work and without output
+    res2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                          capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert res2.returncode == 0 and res2.stdout.strip() == ""
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """The last bench line of the round (profiles/) carries every key of the driver contract."""
+    import json
+
+    with open(os.path.join(ROOT, "profiles", "r01z_bench_final.json")) as f:
+        d = json.loads(f.read().strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
+    assert d["gpu_launches"] > 0 and d["parity"]["ids_identical_to_fp64_oracle"] is True
