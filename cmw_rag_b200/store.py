@@ -113,6 +113,9 @@ class B200Store:
         self._key_of_gid: list[str] = []
         # micro-batching of concurrent awaits
         self._pending: list[tuple[np.ndarray, int, asyncio.Future]] = []
+        import concurrent.futures
+
+        self._executor = concurrent.futures.ThreadPoolExecutor(max_workers=2, thread_name_prefix="b200store")
         self._flush_scheduled = False
         self.stats = {"searches": 0, "launch_batches": 0, "max_batch": 0}
 
@@ -361,13 +364,14 @@ class B200Store:
 
     def _docs_for(self, ids_row: np.ndarray) -> list[RetrievedDoc]:
         out = []
+        off = self._id_offset
         with self._lock:
+            docs, metas, alive, n = self._docs, self._metas, self._alive, len(self._ids)
             for gid in ids_row.tolist():
-                if gid < 0:
-                    continue
-                r = gid - self._id_offset
-                if 0 <= r < len(self._ids) and self._alive[r]:
-                    out.append(RetrievedDoc(page_content=self._docs[r], metadata=dict(self._metas[r] or {})))
+                r = gid - off
+                if gid >= 0 and 0 <= r < n and alive[r]:
+                    m = metas[r]
+                    out.append(RetrievedDoc(docs[r], m.copy() if m else {}))
         return out
 
     def query(self, query_embeddings, n_results: int = 10, include=("documents", "metadatas", "distances")):
@@ -389,6 +393,10 @@ class B200Store:
         if "distances" in include:
             res["distances"] = dists
         return res
+
+    def _search_docs(self, q: np.ndarray, kmax: int, ks: list[int]) -> list[list[RetrievedDoc]]:
+        _, ids, _ = self.search(q, kmax)
+        return [self._docs_for(ids[i, :k]) for i, k in enumerate(ks)]
 
     def similarity_search(self, query_embedding, k: int = 5) -> list[RetrievedDoc]:
         _, ids, _ = self.search([query_embedding], k)
@@ -417,10 +425,13 @@ class B200Store:
             self.stats["searches"] += len(batch)
             self.stats["launch_batches"] += 1
             self.stats["max_batch"] = max(self.stats["max_batch"], len(batch))
-            _, ids, _ = await asyncio.to_thread(self.search, q, kmax)
-            for i, (_, k, fut) in enumerate(batch):
+            # the search runs on a worker thread of the store's own (the event loop is never blocked); the
+            # documents are materialised there too, the loop only hands them to the waiting futures
+            loop = asyncio.get_running_loop()
+            docs = await loop.run_in_executor(self._executor, self._search_docs, q, kmax, [k for _, k, _ in batch])
+            for (_, _, fut), d in zip(batch, docs):
                 if not fut.done():
-                    fut.set_result(self._docs_for(ids[i, :k]))
+                    fut.set_result(d)
         except Exception as exc:  # propagate like a chromadb error would (retrieve_context.py:435-449)
             for _, _, fut in batch:
                 if not fut.done():
