@@ -396,3 +396,26 @@ def test_committed_bench_line_has_the_contract_keys():
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
     assert d["gpu_launches"] > 0 and d["parity"]["ids_identical_to_fp64_oracle"] is True
+
+
+def test_scan_order_permutation_is_a_bijection_and_spreads_evenly():
+    """The arithmetic of K2's scan order (set_scan_order in csrc/gemm.cu, scan_tile in csrc/gemm_common.cuh),
+    restated: tile g of the scan is store tile (g * m) mod T with m ~ T / golden ratio, coprime to T.  Every tile is
+    visited exactly once, and any range of consecutive scan positions is spread over the whole store."""
+    from math import gcd
+
+    for T in (64, 65, 100, 511, 512, 3907, 7813, 97657, 781250):
+        m = int(T * 0.6180339887498949) | 1
+        while gcd(m, T) != 1:
+            m += 2
+        m %= T
+        g = np.arange(T, dtype=np.int64)
+        perm = (g * m) % T
+        assert np.array_equal(np.sort(perm), g), T
+        # a slab of 1/16 of the scan positions, anywhere: its tiles leave no gap wider than a few times the ideal
+        # spacing (1.2-4.8x for these sizes)
+        n = max(8, T // 16)
+        for start in (0, T // 3, T - n):
+            tiles = np.sort(perm[start:start + n])
+            gaps = np.diff(np.concatenate([tiles, [tiles[0] + T]]))
+            assert gaps.max() <= 8 * (T / n) + 2, (T, start, int(gaps.max()))
