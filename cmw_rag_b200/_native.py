@@ -25,7 +25,9 @@ KPRIME_MAX = 1 << 17
 STORE_F32 = 1
 STORE_BF16 = 2
 FLAG_UNCERTIFIED = 1
+FLAG_PEER_TIMEOUT = 2
 HOST_SLOTS = 4
+MAX_K = 1024
 
 METRICS = {"cosine": METRIC_COSINE, "ip": METRIC_IP, METRIC_COSINE: METRIC_COSINE, METRIC_IP: METRIC_IP}
 MODES = {"f32": MODE_F32_EXACT, "exact": MODE_F32_EXACT, "bf16": MODE_BF16,
@@ -80,6 +82,17 @@ SIGNATURES = {
     "cmw_peer_free": (c_int, [c_void_p]),
     "cmw_exchange_merge": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_uint32,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cmw_exchange_merge_ex": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_uint32,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                      c_void_p]),
+    "cmw_search_filter": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                  c_void_p]),
+    "cmw_shard_kth": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cmw_shard_block_bytes": (c_size_t, [c_int, c_int]),
+    "cmw_search_finish": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_size_t, c_void_p]),
+    "cmw_shard_merge": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
     "cmw_kernel_launches": (c_int64, []),
     "cmw_profile_enable": (c_int, [c_int]),
     "cmw_profile_read": (c_int, [POINTER(c_double), POINTER(c_int64), c_int]),
@@ -126,7 +139,7 @@ def kernel_launches() -> int:
     return int(lib().cmw_kernel_launches())
 
 
-PHASES = ("filter", "compact", "finalize", "prep")
+PHASES = ("filter", "compact", "finalize", "prep", "shard_kth", "shard_merge")
 
 
 def profile_enable(on: bool = True) -> None:
@@ -135,9 +148,9 @@ def profile_enable(on: bool = True) -> None:
 
 def profile_read() -> dict:
     """{phase: (milliseconds, kernel launches)} accumulated since the last enable/read."""
-    ms = (c_double * 4)()
-    cnt = (c_int64 * 4)()
-    lib().cmw_profile_read(ms, cnt, 4)
+    ms = (c_double * len(PHASES))()
+    cnt = (c_int64 * len(PHASES))()
+    lib().cmw_profile_read(ms, cnt, len(PHASES))
     return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(PHASES)}
 
 

@@ -27,7 +27,7 @@ namespace cmw {
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-    size_t qn64, q4, q_f32, q_bf16, pool_scores, pool_ids, pool_cnt, pool_thr, pool_ovf, exact, wide, total;
+    size_t qn64, q4, qres, q_f32, q_bf16, pool_scores, pool_ids, pool_cnt, pool_thr, pool_ovf, exact, wide, total;
     int bpad;
 };
 
@@ -48,6 +48,7 @@ static WsLayout ws_layout(int dim, int batch, int kprime) {
     w.bpad = pad_batch(batch);
     w.qn64 = take((size_t)batch * sizeof(double));
     w.q4 = take((size_t)batch * sizeof(double));
+    w.qres = take((size_t)batch * sizeof(double));
     w.q_f32 = take((size_t)batch * dim * sizeof(float));
     w.q_bf16 = take((size_t)w.bpad * dim * sizeof(__nv_bfloat16));
     w.pool_scores = take((size_t)batch * kPoolCap * sizeof(float));
@@ -65,28 +66,36 @@ static WsLayout ws_layout(int dim, int batch, int kprime) {
     return w;
 }
 
-static bool use_gemm(const Store* s, int batch, int mode) {
+static bool use_gemm(const Store* s, const Options& opt, int batch, int mode) {
     const int algo = mode & 0xff00;
     if (algo == CMW_ALGO_SCAN) return false;
     if (!gemm_supported(s)) return false;
     if (algo == CMW_ALGO_GEMM) return true;
-    return g_opt.gemm_enabled != 0 && batch > (int)g_opt.scan_max_batch;
+    return opt.gemm_enabled != 0 && batch > (int)opt.scan_max_batch;
 }
 
-static int pick_kprime(int k, int mode, bool gemm) {
+// K': candidates kept per query between slabs and handed to K3.  The certificate needs the K'-th best filter
+// score to lie more than eps below the k-th exact score, so K' follows the bound in use:
+//   fp32 scan filter (eps ~ 3.6e-6): k + 28;
+//   bf16 tensor-core filter, statistical bound (eps ~ 8.6e-4 at D = 1536): max(k + 64, 2k);
+//   bf16 tensor-core filter, rigorous bound (eps ~ 3.5e-3): max(k + 108, 3k + 20) -- at 1M iid rows the k-th and
+//   the K'-th score are then ~7.8e-3 apart for k = 100 (5 standard deviations of the order statistics over eps).
+// k above ~330 cannot be certified behind the bf16 filter (K' is capped at 1024): such queries are flagged and the
+// host API repairs them through the fp32 scan.
+static int pick_kprime(const Options& opt, int k, int mode, bool gemm) {
     int kp;
     if (mode & CMW_KPRIME_MAX) {
         kp = kMaxKPrime;
-    } else if (g_opt.kprime > 0) {
-        kp = (int)g_opt.kprime;
+    } else if (opt.kprime > 0) {
+        kp = (int)opt.kprime;
     } else if ((mode & 0xff) == CMW_MODE_BF16) {
         kp = k;
-    } else if (gemm && g_opt.strict_certificate != 0) {
-        kp = (4 * k > 512) ? 4 * k : 512;  // rigorous bound: ~3.3x the candidates at 1M iid rows
+    } else if (gemm && opt.strict_certificate != 0 && opt.bf16_eps <= 0) {
+        kp = (3 * k + 20 > k + 108) ? 3 * k + 20 : k + 108;
     } else if (gemm) {
-        kp = (k + 64 > 2 * k) ? k + 64 : 2 * k;  // bf16 filter: room for the certificate
+        kp = (k + 64 > 2 * k) ? k + 64 : 2 * k;
     } else {
-        kp = k + 28;  // fp32 filter: the certificate bound is ~1e-6
+        kp = k + 28;
     }
     if (kp < k) kp = k;
     kp = (int)align_up((size_t)kp, 32);
@@ -199,7 +208,7 @@ static int repair_flagged(cmw_store* h, Store* s, cudaStream_t stream, const Hos
     const int64_t* id = reinterpret_cast<const int64_t*>(pin + io.q_bytes + io.sc_bytes);
     const int32_t* fl = reinterpret_cast<const int32_t*>(pin + io.q_bytes + io.sc_bytes + io.id_bytes);
     const bool exact = (mode & 0xff) == CMW_MODE_F32_EXACT;
-    const bool first_was_gemm = use_gemm(s, batch, mode);
+    const bool first_was_gemm = use_gemm(s, g_opt, batch, mode);
     int stages[2];
     int nstage = 0;
     if (g_opt.repair >= 1 && !((mode & CMW_SLABS_SAFE) && (mode & CMW_KPRIME_MAX)))
@@ -237,8 +246,9 @@ static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<PhaseRecord> g_prof_records;
 static std::vector<cudaEvent_t> g_prof_free;
-static double g_prof_ms[4] = {0, 0, 0, 0};
-static long long g_prof_counts[4] = {0, 0, 0, 0};
+constexpr int kPhases = 6;  // filter, compact, finalize, prep, shard kth, shard merge
+static double g_prof_ms[kPhases] = {};
+static long long g_prof_counts[kPhases] = {};
 
 static cudaEvent_t prof_event() {
     if (!g_prof_free.empty()) {
@@ -298,7 +308,7 @@ extern "C" {
 int cmw_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     prof_drain();
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kPhases; ++i) {
         g_prof_ms[i] = 0;
         g_prof_counts[i] = 0;
     }
@@ -309,7 +319,7 @@ int cmw_profile_enable(int on) {
 int cmw_profile_read(double* ms, int64_t* counts, int n) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     prof_drain();
-    for (int i = 0; i < n && i < 4; ++i) {
+    for (int i = 0; i < n && i < kPhases; ++i) {
         if (ms) ms[i] = g_prof_ms[i];
         if (counts) counts[i] = g_prof_counts[i];
         g_prof_ms[i] = 0;
@@ -329,54 +339,98 @@ size_t cmw_search_workspace_bytes(const cmw_store* h, int batch, int k, int mode
 
 }  // extern "C"
 
-// The search itself.  `fin_stream` == `stream`: everything in order on one stream (the public cmw_search).
-// Otherwise the finalisation (fp64 rescoring + selection, or emit) is forked onto `fin_stream` behind
-// `fork_ev`, so that the caller may put the next search's filter on `stream` right away: the rescoring is an
-// HBM gather that needs no shared memory or TMEM and runs next to the persistent tensor-core filter CTAs.
-static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k, int metric, int mode,
-                       float* out_scores_dev, int64_t* out_ids_dev, double* out_scores64_dev,
-                       int32_t* out_flags_dev, void* ws_dev, size_t ws_bytes, cudaStream_t stream,
-                       cudaStream_t fin_stream, cudaEvent_t fork_ev) {
-    CMW_REQUIRE(h != nullptr, "cmw_search: store is NULL");
-    Store* s = reinterpret_cast<Store*>(h);
-    if (batch == 0) return 0;
-    CMW_REQUIRE(batch > 0 && queries_dev && out_scores_dev && out_ids_dev, "cmw_search: bad arguments");
-    CMW_REQUIRE(k >= 1 && k <= kMaxKPrime, "cmw_search: k must be in [1, %d], got %d", kMaxKPrime, k);
-    CMW_REQUIRE(metric == CMW_METRIC_COSINE || metric == CMW_METRIC_IP, "cmw_search: unknown metric %d",
-                metric);
-    const int base_mode = mode & 0xff;
-    CMW_REQUIRE(base_mode == CMW_MODE_F32_EXACT || base_mode == CMW_MODE_BF16,
-                "cmw_search: unknown mode %d", base_mode);
-    CMW_REQUIRE((reinterpret_cast<uintptr_t>(queries_dev) & 15) == 0,
-                "cmw_search: queries_dev must be 16-byte aligned");
-    if (base_mode == CMW_MODE_F32_EXACT)
-        CMW_REQUIRE(s->f32 != nullptr, "cmw_search: CMW_MODE_F32_EXACT needs a CMW_STORE_F32 store");
-    if (base_mode == CMW_MODE_BF16)
-        CMW_REQUIRE(s->bf16 != nullptr, "cmw_search: CMW_MODE_BF16 needs a CMW_STORE_BF16 store");
-    CMW_CUDA_OK(cudaSetDevice(s->device));
-
-    const bool gemm = use_gemm(s, batch, mode);
-    if ((mode & 0xff00) == CMW_ALGO_GEMM)
-        CMW_REQUIRE(gemm, "cmw_search: CMW_ALGO_GEMM requested but the tcgen05 path is unavailable "
-                          "(store without bf16 tiles or TMA descriptor)");
-    const int kprime = pick_kprime(k, mode, gemm);
-    const WsLayout w = ws_layout(s->dim, batch, kprime);
-    CMW_REQUIRE(ws_dev != nullptr && ws_bytes >= w.total,
-                "cmw_search: workspace too small (%zu bytes given, %zu needed)", ws_bytes, w.total);
-    CMW_REQUIRE((reinterpret_cast<uintptr_t>(ws_dev) & 255) == 0, "cmw_search: workspace must be 256-byte aligned");
-    uint8_t* ws = reinterpret_cast<uint8_t*>(ws_dev);
-    double* qn64 = reinterpret_cast<double*>(ws + w.qn64);
-    double* q4 = reinterpret_cast<double*>(ws + w.q4);
-    float* q_f32 = reinterpret_cast<float*>(ws + w.q_f32);
-    __nv_bfloat16* q_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + w.q_bf16);
+// ---------------------------------------------------------------------------------------------
+// The search itself, in two stream-ordered halves:
+//   filter half  -- query preparation, the filter slabs and the pool compactions; ends with every pool sorted
+//                   by filter score and truncated to K'
+//   finish half  -- F32_EXACT: fp64 rescoring + selection + certificate; BF16: emit the pool's best k
+// cmw_search runs both back to back.  The row-sharded search (cmw_search_filter / cmw_shard_kth /
+// cmw_search_finish / cmw_shard_merge) puts the cross-shard exchange of the k-th filter score between them.
+// ---------------------------------------------------------------------------------------------
+struct SearchPlan {
+    Store* s;
+    Options opt;  // snapshot: cmw_set_option during a search must not change what its later slabs do
+    int batch, k, metric, mode, base_mode, kprime;
+    bool gemm;
+    WsLayout w;
+    double *qn64, *q4, *qres, *exact;
+    float* q_f32;
+    __nv_bfloat16* q_bf16;
     Pool pool;
-    pool.scores = reinterpret_cast<float*>(ws + w.pool_scores);
-    pool.ids = reinterpret_cast<int32_t*>(ws + w.pool_ids);
-    pool.cnt = reinterpret_cast<int32_t*>(ws + w.pool_cnt);
-    pool.thr = reinterpret_cast<float*>(ws + w.pool_thr);
-    pool.ovf = reinterpret_cast<int32_t*>(ws + w.pool_ovf);
-    double* exact = reinterpret_cast<double*>(ws + w.exact);
+    uint8_t* ws;
+};
 
+static int make_plan(SearchPlan& pl, cmw_store* h, const float* queries_dev, int batch, int k, int metric, int mode,
+                     void* ws_dev, size_t ws_bytes, const char* who) {
+    CMW_REQUIRE(h != nullptr, "%s: store is NULL", who);
+    Store* s = reinterpret_cast<Store*>(h);
+    CMW_REQUIRE(batch > 0 && queries_dev, "%s: bad arguments", who);
+    CMW_REQUIRE(k >= 1 && k <= kMaxKPrime, "%s: k must be in [1, %d], got %d", who, kMaxKPrime, k);
+    CMW_REQUIRE(metric == CMW_METRIC_COSINE || metric == CMW_METRIC_IP, "%s: unknown metric %d", who, metric);
+    const int base_mode = mode & 0xff;
+    CMW_REQUIRE(base_mode == CMW_MODE_F32_EXACT || base_mode == CMW_MODE_BF16, "%s: unknown mode %d", who, base_mode);
+    CMW_REQUIRE((reinterpret_cast<uintptr_t>(queries_dev) & 15) == 0, "%s: queries_dev must be 16-byte aligned", who);
+    if (base_mode == CMW_MODE_F32_EXACT)
+        CMW_REQUIRE(s->f32 != nullptr, "%s: CMW_MODE_F32_EXACT needs a CMW_STORE_F32 store", who);
+    if (base_mode == CMW_MODE_BF16)
+        CMW_REQUIRE(s->bf16 != nullptr, "%s: CMW_MODE_BF16 needs a CMW_STORE_BF16 store", who);
+    CMW_CUDA_OK(cudaSetDevice(s->device));
+    pl.s = s;
+    pl.opt = g_opt;
+    pl.batch = batch;
+    pl.k = k;
+    pl.metric = metric;
+    pl.mode = mode;
+    pl.base_mode = base_mode;
+    pl.gemm = use_gemm(s, pl.opt, batch, mode);
+    if ((mode & 0xff00) == CMW_ALGO_GEMM)
+        CMW_REQUIRE(pl.gemm, "%s: CMW_ALGO_GEMM requested but the tcgen05 path is unavailable "
+                             "(store without bf16 tiles or TMA descriptor)", who);
+    pl.kprime = pick_kprime(pl.opt, k, mode, pl.gemm);
+    pl.w = ws_layout(s->dim, batch, pl.kprime);
+    CMW_REQUIRE(ws_dev != nullptr && ws_bytes >= pl.w.total, "%s: workspace too small (%zu bytes given, %zu needed)",
+                who, ws_bytes, pl.w.total);
+    CMW_REQUIRE((reinterpret_cast<uintptr_t>(ws_dev) & 255) == 0, "%s: workspace must be 256-byte aligned", who);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(ws_dev);
+    pl.ws = ws;
+    pl.qn64 = reinterpret_cast<double*>(ws + pl.w.qn64);
+    pl.q4 = reinterpret_cast<double*>(ws + pl.w.q4);
+    pl.qres = reinterpret_cast<double*>(ws + pl.w.qres);
+    pl.q_f32 = reinterpret_cast<float*>(ws + pl.w.q_f32);
+    pl.q_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.w.q_bf16);
+    pl.pool.scores = reinterpret_cast<float*>(ws + pl.w.pool_scores);
+    pl.pool.ids = reinterpret_cast<int32_t*>(ws + pl.w.pool_ids);
+    pl.pool.cnt = reinterpret_cast<int32_t*>(ws + pl.w.pool_cnt);
+    pl.pool.thr = reinterpret_cast<float*>(ws + pl.w.pool_thr);
+    pl.pool.ovf = reinterpret_cast<int32_t*>(ws + pl.w.pool_ovf);
+    pl.exact = reinterpret_cast<double*>(ws + pl.w.exact);
+    return 0;
+}
+
+// live rows among the first `pos` rows in STORAGE order (pos a multiple of 256, or the end of the store); a lower
+// bound when pos falls inside a block
+static int64_t live_before(const Store* s, int64_t pos) {
+    if (s->dead_prefix.empty()) return pos;
+    const size_t nblk = s->dead_prefix.size() - 1;  // blocks the prefix covers; nothing is dead beyond them
+    size_t blk = (size_t)(pos / 256);
+    int64_t dead;
+    if (blk >= nblk) {
+        dead = s->dead_prefix[nblk];
+    } else {
+        dead = s->dead_prefix[blk];
+        if (pos % 256) dead += s->dead_prefix[blk + 1] - s->dead_prefix[blk];
+    }
+    const int64_t live = pos - dead;
+    return live > 0 ? live : 0;
+}
+
+static int run_filter_half(const SearchPlan& pl, const float* queries_dev, cudaStream_t stream) {
+    Store* s = pl.s;
+    const Options& opt = pl.opt;
+    const int batch = pl.batch, kprime = pl.kprime, metric = pl.metric, mode = pl.mode;
+    const bool gemm = pl.gemm;
+    const WsLayout& w = pl.w;
+    Pool pool = pl.pool;
     int rc;
     const int64_t rows = s->rows;
     // First slab: every row's score is kept (no threshold exists yet).  Large batches write it straight into
@@ -386,18 +440,30 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
     // segments for a large kprime.)
     int wide_segs = (kPoolCap - 256) / kprime;
     if (wide_segs > kWideSegments) wide_segs = kWideSegments;
-    const bool wide = g_opt.wide_dense != 0 && batch <= kWideDenseMaxBatch && rows > kDenseSlabRows && wide_segs >= 2 &&
+    const bool wide = opt.wide_dense != 0 && batch <= kWideDenseMaxBatch && rows > kDenseSlabRows && wide_segs >= 2 &&
                       !(mode & CMW_SLABS_SAFE);
     const int64_t wide_rows = (int64_t)wide_segs * kPoolCap;
     const int64_t slab0 = wide ? (rows < wide_rows ? rows : wide_rows)
                                : (rows < kDenseSlabRows ? rows : (int64_t)kDenseSlabRows);
+    // What the schedule below reasons about is the number of LIVE rows the slabs so far have seen: the admission
+    // threshold is the kprime-th best of those.  K2 scans a stride permutation of the tiles, so its slabs see the
+    // store-wide live fraction; K1 (and small stores) scan in storage order, where the tombstones may sit in one
+    // block -- a re-indexed collection is exactly that -- and the per-block counts give the exact number.
+    const bool permuted = gemm && gemm_scan_permuted(s, opt, w.bpad);
+    const double live_frac = rows > 0 ? (double)(rows - s->dead) / (double)rows : 1.0;
+    auto live_seen = [&](int64_t seen) -> double {
+        if (s->dead == 0) return (double)seen;
+        return permuted ? (double)seen * live_frac : (double)live_before(s, seen);
+    };
+    const double live0 = live_seen(slab0);
+    const double live_all = (double)(rows - s->dead);
     // expected pool fill if everything after the first slab went through one launch
-    const double rest_fill = (double)(rows - slab0) * kprime / (double)(slab0 > 0 ? slab0 : 1) + kprime;
+    const double rest_fill = (live_all - live0) * kprime / (live0 > 1.0 ? live0 : 1.0) + kprime;
     float* wide_scores = nullptr;
     int32_t* wide_ids = nullptr;
     Pool seg = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (wide) {
-        uint8_t* base = ws + w.wide;
+        uint8_t* base = pl.ws + w.wide;
         wide_scores = reinterpret_cast<float*>(base);
         wide_ids = reinterpret_cast<int32_t*>(base + (size_t)batch * kWideDenseRows * 4);
         uint8_t* tail = base + (size_t)batch * kWideDenseRows * 8;
@@ -410,13 +476,14 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
     }
     {
         PhaseTimer t(3, stream);
-        if ((rc = launch_prep_queries(queries_dev, batch, w.bpad, s->dim, metric, qn64, q4, q_f32,
-                                      gemm ? q_bf16 : nullptr, pool, wide ? 0 : (int)slab0, seg, (int)slab0, stream)))
+        if ((rc = launch_prep_queries(queries_dev, batch, w.bpad, s->dim, metric, pl.qn64, pl.q4, pl.qres, pl.q_f32,
+                                      gemm ? pl.q_bf16 : nullptr, pool, wide ? 0 : (int)slab0, seg, (int)slab0,
+                                      stream)))
             return rc;
     }
 
     // which tiles the filter reads, and the per-row multiplier that goes with them
-    const bool filter_bf16 = gemm || base_mode == CMW_MODE_BF16;
+    const bool filter_bf16 = gemm || pl.base_mode == CMW_MODE_BF16;
     const void* tiles = filter_bf16 ? (const void*)s->bf16 : (const void*)s->f32;
     const float* row_mul;
     if (filter_bf16) row_mul = (metric == CMW_METRIC_COSINE) ? s->live : s->norm;  // rows pre-normalised
@@ -427,7 +494,7 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
         if (gemm) {
             GemmArgs g;
             g.store = s;
-            g.q_bf16 = q_bf16;
+            g.q_bf16 = pl.q_bf16;
             g.batch = batch;
             g.bpad = w.bpad;
             g.row_mul = row_mul;
@@ -438,9 +505,10 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
             g.wide_scores = dense ? wide_scores : nullptr;
             g.wide_ids = wide_ids;
             g.wide_stride = kWideDenseRows;
+            g.opt = &opt;
             return launch_gemm(g, stream);
         }
-        for (int b0 = 0; b0 < batch; b0 += 2) {
+        for (int b0 = 0; b0 < batch; b0 += kScanMaxQueries) {
             ScanArgs a;
             a.rows = tiles;
             a.elt_bytes = filter_bf16 ? 2 : 4;
@@ -448,8 +516,8 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
             a.row_mul = row_mul;
             a.row_begin = r0;
             a.row_end = r1;
-            a.q = q_f32 + (size_t)b0 * s->dim;
-            a.nq = (batch - b0 >= 2) ? 2 : 1;
+            a.q = pl.q_f32 + (size_t)b0 * s->dim;
+            a.nq = (batch - b0 >= kScanMaxQueries) ? kScanMaxQueries : batch - b0;
             a.pool.scores = pool.scores + (size_t)b0 * kPoolCap;
             a.pool.ids = pool.ids + (size_t)b0 * kPoolCap;
             a.pool.cnt = pool.cnt + b0;
@@ -473,8 +541,10 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
 
     double growth = (double)(kPoolCap - kprime) / (3.0 * kprime);
     if (growth > 8.0) growth = 8.0;
-    if (g_opt.slab_growth > 0 && g_opt.slab_growth < growth) growth = g_opt.slab_growth;
+    if (opt.slab_growth > 0 && opt.slab_growth < growth) growth = opt.slab_growth;
     if (growth < 1.0) growth = 1.0;
+    // a slab of this many rows can never overflow a pool that holds at most kprime entries, whatever its threshold
+    const int64_t safe_rows = (int64_t)((kPoolCap - kprime) & ~255);
     int64_t seen = 0;
     if (rows > 0) {
         if ((rc = run_filter(0, slab0, 1))) return rc;
@@ -491,24 +561,27 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
         while (seen < rows) {
             int64_t m, end;
             // After a wide first slab the threshold is the kprime-th best of 65536 rows: the rest of the corpus
-            // goes through ONE launch when its expected admissions, (rows - seen) * kprime / seen, plus the
-            // kprime survivors fill at most 85 % of the pool (up to ~1.05M rows at kprime = 224).  K2 scans the
-            // tiles in a stride permutation, so the slab was a representative sample and the estimate holds
-            // whatever the row order; K1 scans in storage order and gets the single launch only up to 50 %.
+            // goes through ONE launch when its expected admissions, (live rows left) * kprime / (live rows seen),
+            // plus the kprime survivors fill at most 85 % of the pool (up to ~1.05M rows at kprime = 224).  K2
+            // scans the tiles in a stride permutation, so the slab was a representative sample and the estimate
+            // holds whatever the row order; K1 scans in storage order and gets the single launch only up to 50 %.
             // A pool that overflows all the same is flagged and repaired like any other overflow.
-            if (wide && seen == slab0 && rest_fill <= ((gemm && g_opt.scan_permute != 0) ? 0.85 : 0.5) * kPoolCap) {
+            if (wide && seen == slab0 && live0 >= 2.0 * kprime && rest_fill <= (permuted ? 0.85 : 0.5) * kPoolCap) {
                 if ((rc = run_filter(seen, rows, 0))) return rc;
                 if ((rc = compact(true))) return rc;
                 seen = rows;
                 break;
             }
-            if (mode & CMW_SLABS_SAFE) {
-                // a slab can add at most m rows to a pool holding at most kprime: never overflows
-                m = (int64_t)((kPoolCap - kprime) & ~255);
+            const double ls = live_seen(seen);
+            if ((mode & CMW_SLABS_SAFE) || ls < 2.0 * kprime) {
+                // no (useful) threshold yet -- the slabs so far were mostly tombstones -- or the caller asked for
+                // the overflow-proof schedule
+                m = safe_rows;
                 end = seen + m;
                 if (end > rows) end = rows;
             } else {
-                m = (int64_t)((double)seen * growth);
+                // expected admissions: m * kprime / ls = growth * kprime <= a third of the free pool
+                m = (int64_t)(ls * growth);
                 m &= ~(int64_t)255;
                 if (m < kDenseSlabRows) m = kDenseSlabRows;
                 end = seen + m;
@@ -518,32 +591,74 @@ static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k,
             if ((rc = compact(end == rows))) return rc;
             seen = end;
         }
+    } else {
+        if ((rc = compact(true))) return rc;  // empty store: empty, consistent pools
     }
+    return 0;
+}
 
+static CertParams make_cert(const SearchPlan& pl, const float* global_kth) {
+    const Options& opt = pl.opt;
+    CertParams cert;
+    cert.kind = CERT_FIXED;
+    // fp32 FMA filter: one lane's chain of D/32 FMAs + 5 shuffle adds + query scaling + row multiplier
+    cert.eps_fixed = opt.f32_eps > 0 ? opt.f32_eps : (double)(pl.s->dim / 32 + 12) * 5.9604644775390625e-8;
+    cert.sigmas = 0.0;
+    cert.acc_slack = (double)pl.s->dim * 1.1920928955078125e-7 * 1.01;  // D * 2^-23
+    if (pl.gemm) {
+        if (opt.bf16_eps > 0) {
+            cert.eps_fixed = opt.bf16_eps;
+        } else if (opt.strict_certificate != 0) {
+            cert.kind = CERT_RIGOROUS;
+        } else {
+            cert.kind = CERT_STATISTICAL;
+            cert.sigmas = opt.bf16_sigmas;
+        }
+    }
+    cert.q4 = pl.q4;
+    cert.qres = pl.qres;
+    cert.qn64 = pl.qn64;
+    cert.norms = pl.s->maxnorm_bits;
+    cert.metric = pl.metric;
+    cert.global_kth = global_kth;
+    return cert;
+}
+
+static int run_finish_half(const SearchPlan& pl, const float* queries_dev, const float* global_kth,
+                           float* out_scores_dev, int64_t* out_ids_dev, double* out_scores64_dev,
+                           int32_t* out_flags_dev, double* out_aux_dev, cudaStream_t fin_stream) {
+    PhaseTimer tfin(2, fin_stream);
+    if (pl.base_mode == CMW_MODE_F32_EXACT) {
+        const CertParams cert = make_cert(pl, global_kth);
+        return launch_rescore_select(pl.s, pl.pool, pl.batch, pl.k, pl.kprime, pl.metric, queries_dev, cert, pl.exact,
+                                     out_scores_dev, out_ids_dev, out_scores64_dev, out_flags_dev, out_aux_dev,
+                                     fin_stream);
+    }
+    return launch_pool_emit(pl.s, pl.pool, pl.batch, pl.k, out_scores_dev, out_ids_dev, out_scores64_dev,
+                            out_flags_dev, out_aux_dev, fin_stream);
+}
+
+// `fin_stream` == `stream`: everything in order on one stream (the public cmw_search).  Otherwise the finish
+// half is forked onto `fin_stream` behind `fork_ev`, so that the caller may put the next search's filter on
+// `stream` right away: the rescoring is an HBM gather that needs no shared memory or TMEM and runs next to the
+// persistent tensor-core filter CTAs.
+static int search_impl(cmw_store* h, const float* queries_dev, int batch, int k, int metric, int mode,
+                       float* out_scores_dev, int64_t* out_ids_dev, double* out_scores64_dev,
+                       int32_t* out_flags_dev, void* ws_dev, size_t ws_bytes, cudaStream_t stream,
+                       cudaStream_t fin_stream, cudaEvent_t fork_ev) {
+    CMW_REQUIRE(h != nullptr, "cmw_search: store is NULL");
+    if (batch == 0) return 0;
+    CMW_REQUIRE(out_scores_dev && out_ids_dev, "cmw_search: bad arguments");
+    SearchPlan pl;
+    int rc = make_plan(pl, h, queries_dev, batch, k, metric, mode, ws_dev, ws_bytes, "cmw_search");
+    if (rc) return rc;
+    if ((rc = run_filter_half(pl, queries_dev, stream))) return rc;
     if (fin_stream != stream) {
         CMW_CUDA_OK(cudaEventRecord(fork_ev, stream));
         CMW_CUDA_OK(cudaStreamWaitEvent(fin_stream, fork_ev, 0));
     }
-    PhaseTimer tfin(2, fin_stream);
-    if (base_mode == CMW_MODE_F32_EXACT) {
-        CertParams cert;
-        cert.eps_fixed = g_opt.f32_eps;
-        cert.sigmas = 0.0;
-        if (gemm) {
-            if (g_opt.strict_certificate != 0) cert.eps_fixed = 4.1e-3;
-            else if (g_opt.bf16_eps > 0) cert.eps_fixed = g_opt.bf16_eps;
-            else cert.sigmas = g_opt.bf16_sigmas;
-        }
-        cert.q4 = q4;
-        cert.qn64 = qn64;
-        cert.norms = s->maxnorm_bits;
-        cert.metric = metric;
-        return launch_rescore_select(s, pool, batch, k, kprime, metric, queries_dev, cert, exact,
-                                     out_scores_dev, out_ids_dev, out_scores64_dev, out_flags_dev,
-                                     fin_stream);
-    }
-    return launch_pool_emit(s, pool, batch, k, out_scores_dev, out_ids_dev, out_scores64_dev,
-                            out_flags_dev, fin_stream);
+    return run_finish_half(pl, queries_dev, nullptr, out_scores_dev, out_ids_dev, out_scores64_dev, out_flags_dev,
+                           nullptr, fin_stream);
 }
 
 extern "C" {
@@ -554,6 +669,61 @@ int cmw_search(cmw_store* h, const float* queries_dev, int batch, int k, int met
     cudaStream_t stream = (cudaStream_t)stream_v;
     return search_impl(h, queries_dev, batch, k, metric, mode, out_scores_dev, out_ids_dev, out_scores64_dev,
                        out_flags_dev, ws_dev, ws_bytes, stream, stream, nullptr);
+}
+
+// ---- row-sharded search: cmw_search in two halves around the exchange of the k-th filter score ----------
+int cmw_search_filter(cmw_store* h, const float* queries_dev, int batch, int k, int metric, int mode,
+                      float* out_filter_topk_dev, void* ws_dev, size_t ws_bytes, void* stream_v) {
+    CMW_REQUIRE(h != nullptr, "cmw_search_filter: store is NULL");
+    if (batch == 0) return 0;
+    CMW_REQUIRE(out_filter_topk_dev != nullptr, "cmw_search_filter: bad arguments");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    SearchPlan pl;
+    int rc = make_plan(pl, h, queries_dev, batch, k, metric, mode, ws_dev, ws_bytes, "cmw_search_filter");
+    if (rc) return rc;
+    if ((rc = run_filter_half(pl, queries_dev, stream))) return rc;
+    PhaseTimer t(1, stream);
+    return launch_pool_topk_scores(pl.pool, batch, k, out_filter_topk_dev, stream);
+}
+
+int cmw_search_finish(cmw_store* h, const float* queries_dev, int batch, int k, int metric, int mode,
+                      const float* global_kth_dev, void* block_dev, void* ws_dev, size_t ws_bytes, void* stream_v) {
+    CMW_REQUIRE(h != nullptr, "cmw_search_finish: store is NULL");
+    if (batch == 0) return 0;
+    CMW_REQUIRE(block_dev != nullptr && (reinterpret_cast<uintptr_t>(block_dev) & 15) == 0,
+                "cmw_search_finish: block_dev must be a 16-byte aligned device pointer");
+    SearchPlan pl;
+    // the same arguments as the filter half -> the same workspace layout: the pools are where it left them
+    int rc = make_plan(pl, h, queries_dev, batch, k, metric, mode, ws_dev, ws_bytes, "cmw_search_finish");
+    if (rc) return rc;
+    const ShardBlock lay = shard_block(batch, k);
+    uint8_t* blk = reinterpret_cast<uint8_t*>(block_dev);
+    return run_finish_half(pl, queries_dev, global_kth_dev, nullptr, reinterpret_cast<int64_t*>(blk + lay.ids),
+                           reinterpret_cast<double*>(blk + lay.scores), reinterpret_cast<int32_t*>(blk + lay.flags),
+                           reinterpret_cast<double*>(blk + lay.aux), (cudaStream_t)stream_v);
+}
+
+size_t cmw_shard_block_bytes(int batch, int k) {
+    if (batch < 1 || k < 1) return 0;
+    return shard_block(batch, k).total;
+}
+
+int cmw_shard_kth(const float* filter_topk_gathered_dev, int G, int B, int k, float* out_kth_dev, void* stream) {
+    CMW_REQUIRE(filter_topk_gathered_dev && out_kth_dev, "cmw_shard_kth: NULL argument");
+    CMW_REQUIRE(G >= 1 && B >= 0 && k >= 1, "cmw_shard_kth: bad sizes");
+    if (B == 0) return 0;
+    PhaseTimer t(4, (cudaStream_t)stream);
+    return launch_shard_kth(filter_topk_gathered_dev, G, B, k, out_kth_dev, (cudaStream_t)stream);
+}
+
+int cmw_shard_merge(const void* blocks_dev, int G, int B, int k, int k_out, float* out_scores_dev,
+                    int64_t* out_ids_dev, double* out_scores64_dev, int32_t* out_flags_dev, void* stream) {
+    CMW_REQUIRE(blocks_dev && out_scores_dev && out_ids_dev, "cmw_shard_merge: NULL argument");
+    CMW_REQUIRE(G >= 1 && B >= 0 && k >= 1 && k_out >= 1, "cmw_shard_merge: bad sizes");
+    if (B == 0) return 0;
+    PhaseTimer t(5, (cudaStream_t)stream);
+    return launch_shard_merge(blocks_dev, G, B, k, k_out, out_scores_dev, out_ids_dev, out_scores64_dev,
+                              out_flags_dev, (cudaStream_t)stream);
 }
 
 int cmw_search_host(cmw_store* h, const float* queries_host, int batch, int k, int metric, int mode,

@@ -13,6 +13,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/cmw_dense.h"
 
@@ -59,6 +60,7 @@ constexpr int kMaxKPrime = 1024;
 constexpr int kWideDenseRows = 65536;
 constexpr int kWideSegments = kWideDenseRows / kPoolCap;
 constexpr int kWideDenseMaxBatch = 32;
+constexpr int kScanMaxQueries = 4;  // queries K1 scores per pass over the corpus
 
 struct Pool {
     float* scores;   // [B, kPoolCap]
@@ -109,7 +111,14 @@ struct Store {
     float* live = nullptr;           // [cap4] 1.0   (NaN when tombstoned)
     double* norm64 = nullptr;        // [capacity] |c| in fp64
     int32_t* kb_gid = nullptr;       // [capacity]
-    uint32_t* maxnorm_bits = nullptr;  // device scalars: [0] max |c| as float bits, [1] max |c/|c||_4
+    // device scalars (float bits, rounded up): [0] max |c|, [1] max |c/|c||_4, [2] max |c/|c| - bf16(c/|c|)|_2
+    // (the rounding residual of the bf16 tiles: rigorous certificate); [16..17] tombstone counter
+    uint32_t* maxnorm_bits = nullptr;
+    // tombstones per block of 256 rows, as the device counted them (dead_blk) and as a host prefix sum
+    // (dead_prefix[i] = dead rows among the first 256*i): the slab schedule needs the number of LIVE rows a
+    // slab has seen, not the number of rows
+    uint32_t* dead_blk = nullptr;          // device [capacity / 256 + 1]
+    std::vector<int64_t> dead_prefix;      // host   [capacity / 256 + 2]; empty = no tombstones
     // host-API resources (cmw_search_host / *_host variants)
     cudaStream_t stream = nullptr;
     void* pinned = nullptr;
@@ -130,15 +139,23 @@ struct Store {
 
 // options (cmw_set_option)
 struct Options {
-    // Certificate bound on |bf16 filter score - exact score| (cosine units).  0 = automatic: the rounding
-    // errors of the two bf16 operands are independent with relative size <= u = 2^-9, so the error of a
-    // dot product has sigma <= u * sqrt(2/3) * |q|_4 * |c|_4 (Cauchy-Schwarz on the squared products);
-    // eps = bf16_sigmas * that bound with |c|_4 the maximum over the stored rows, capped by the rigorous
-    // 4.1e-3.  For dense 1536-d unit vectors this is ~6e-4; it grows as 1/sqrt(D) for smaller D and for
-    // concentrated (sparse-ish) vectors.  > 0 = fixed override.
+    // Certificate behind the bf16 tensor-core filter: a bound eps on |filter score - exact score| (cosine units).
+    //   strict_certificate = 1 (default): RIGOROUS.  With q^ = q/|q|, c^ = c/|c| and q~, c~ their bf16 tiles,
+    //       |q^.c^ - q~.c~| <= |q^ - q~| |c^| + |q~| |c^ - c~|  <=  r_q + (1 + r_q) R_c
+    //     where r_q = |q^ - q~|_2 is computed per query by the prep kernel and R_c = max over the stored rows of
+    //     |c^ - c~|_2 is tracked at ingest (both in fp64 from the values actually written), plus D * 2^-23 for
+    //     the fp32 accumulation of the tensor pipe whatever its order and rounding mode.  Round-to-nearest bf16
+    //     has unit round-off 2^-8, so r <= 2^-8 always; for dense embeddings r ~ 0.42 * 2^-8 and eps ~ 3.5e-3.
+    //   strict_certificate = 0: STATISTICAL.  The rounding errors of the two operands are taken as independent,
+    //     relative size <= u = 2^-8 each: sigma <= u sqrt(2/3) |q^|_4 |c^|_4, eps = bf16_sigmas * sigma.  ~4x
+    //     tighter (fewer rows rescored) but a probabilistic statement that adversarially aligned roundings break.
+    //   bf16_eps > 0: fixed override of either.
     double bf16_eps = 0;
     double bf16_sigmas = 8;
-    double f32_eps = 4e-6;    // same for the fp32 FMA filter
+    double strict_certificate = 1;
+    // fp32 FMA filter (K1): 0 = automatic, (D/32 + 12) * 2^-24 -- the length of one lane's FMA chain plus the
+    // shuffle tree, the query scaling and the row multiplier, each one rounding of 2^-24 on |q||c| <= 1
+    double f32_eps = 0;
     double kprime = 0;        // 0 = automatic
     // Batches up to this use K1 (scan), larger ones K2 (GEMM).  0 = K2 for every batch size: even at
     // batch 1 the tensor-core filter reads the bf16 tiles (half the bytes of the fp32 scan) and the
@@ -149,9 +166,6 @@ struct Options {
     double gemm_2cta = 1;            // CTA-pair (cta_group::2) K2 kernel for large batches
     double gemm_2cta_min_batch = 128;  // padded batches of 128 / 192 gain 2-5 % from the halved query-operand traffic
     double gemm_clc = 1;             // CTA-pair kernel: dynamic item scheduling through cluster launch control
-    // 1 = rigorous certificate behind the bf16 filter: eps = 2u(1+u) + fp32 accumulation slack = 4.1e-3
-    // (Cauchy-Schwarz over unit vectors, u = 2^-9) and K' = max(512, 4k); ~17 % slower at B=4096
-    double strict_certificate = 0;
     // host API repair chain for flagged queries: 0 = off (flags are only reported), 1 = stage 1 only (same
     // filter, K' = 1024, overflow-proof slabs), 2 = also stage 2 (fp32 scan filter).  Exact ties larger than
     // K' - k straddling the k-th place stay flagged whatever the stage -- the ids are still the lowest of
@@ -179,7 +193,7 @@ struct ScanArgs {
     const float* row_mul;  // per-row multiplier (indexed by LOCAL row)
     int64_t row_begin, row_end;
     const float* q;        // [nq, dim] prepared fp32 queries
-    int nq;                // 1 or 2
+    int nq;                // 1 .. kScanMaxQueries
     Pool pool;             // already offset to the first of the nq queries
     int dense;             // 1 = write every row at slot (row - row_begin)
     float* wide_scores;    // dense only: scratch [nq, wide_stride] for the wide first slab (NULL = the pools)
@@ -201,22 +215,31 @@ struct GemmArgs {
     float* wide_scores;           // dense only: scratch [batch, wide_stride] (NULL = the pools)
     int32_t* wide_ids;
     int wide_stride;
+    const Options* opt;           // the options snapshot of this search (never g_opt: it may change mid-search)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 bool gemm_supported(const Store* s);
+bool gemm_scan_permuted(const Store* s, const Options& o, int bpad);
 
 int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64, double* q4,
-                        float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count, Pool seg, int wide_rows,
-                        cudaStream_t stream);
+                        double* qres, float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count, Pool seg,
+                        int wide_rows, cudaStream_t stream);
 
 // how the certificate / rescoring cut bound is obtained (see Options::bf16_eps)
+enum CertKind : int { CERT_FIXED = 0, CERT_STATISTICAL = 1, CERT_RIGOROUS = 2 };
 struct CertParams {
-    double eps_fixed;       // used when sigmas == 0
-    double sigmas;          // > 0: statistical bf16 bound from q4 and the store's max row 4-norm
+    int kind;
+    double eps_fixed;       // CERT_FIXED: the bound itself (cosine units)
+    double sigmas;          // CERT_STATISTICAL: multiples of the sigma bound from q4 and the store's max row 4-norm
+    double acc_slack;       // CERT_RIGOROUS / STATISTICAL: fp32 accumulation slack of the filter, D * 2^-23
     const double* q4;       // [B] |q/|q||_4
+    const double* qres;     // [B] |q^ - bf16(q^)|_2 relative to |q^| (the query tile's rounding residual)
     const double* qn64;     // [B] |q|
-    const uint32_t* norms;  // store scalars: [0] max |c| bits, [1] max 4-norm bits
+    const uint32_t* norms;  // store scalars: [0] max |c|, [1] max 4-norm, [2] max bf16 residual (float bits)
     int metric;
+    // row-sharded searches: per-query rescoring cut handed in from outside (the k-th best filter score over ALL
+    // shards minus 2 eps); NULL = this store's own k-th filter score
+    const float* global_kth;
 };
 int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_t stream);
 // wide first slab: the best kprime (and ties) of the 16 scratch segments of every query -> its pool
@@ -226,11 +249,32 @@ int launch_wide_select(Pool seg, Pool pool, int batch, int kprime, int final, cu
 int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprime, int metric,
                           const float* q_raw, const CertParams& cert, double* exact_ws,
                           float* out_scores, int64_t* out_ids, double* out_scores64,
-                          int32_t* out_flags, cudaStream_t stream);
+                          int32_t* out_flags, double* out_aux, cudaStream_t stream);
 // bf16 mode: emit the pool's best k as they are
 int launch_pool_emit(const Store* s, Pool pool, int batch, int k, float* out_scores,
-                     int64_t* out_ids, double* out_scores64, int32_t* out_flags,
+                     int64_t* out_ids, double* out_scores64, int32_t* out_flags, double* out_aux,
                      cudaStream_t stream);
+
+// row-sharded search (pool.cu)
+// packed per-shard result block (what all-gather 2 moves): f64 scores [B,k] | i64 ids [B,k] | f64 aux [B,2] |
+// i32 flags [B]
+struct ShardBlock {
+    size_t scores, ids, aux, flags, total;
+};
+__host__ __device__ inline ShardBlock shard_block(int B, int k) {
+    ShardBlock s;
+    s.scores = 0;
+    s.ids = (size_t)B * k * 8;
+    s.aux = s.ids + (size_t)B * k * 8;
+    s.flags = s.aux + (size_t)B * 16;
+    s.total = (s.flags + (size_t)B * 4 + 255) / 256 * 256;
+    return s;
+}
+
+int launch_pool_topk_scores(Pool pool, int batch, int k, float* out, cudaStream_t stream);
+int launch_shard_kth(const float* gathered, int G, int B, int k, float* out_kth, cudaStream_t stream);
+int launch_shard_merge(const void* blocks, int G, int B, int k, int k_out, float* out_scores, int64_t* out_ids,
+                       double* out_scores64, int32_t* out_flags, cudaStream_t stream);
 
 // host-API resources (store.cu)
 int ensure_pinned(Store* s, size_t bytes);
@@ -279,12 +323,21 @@ __device__ __forceinline__ uint64_t f64_orderable(double d) {
 __device__ __forceinline__ double f64_from_orderable(uint64_t u) {
     return __longlong_as_double((long long)((u >> 63) ? (u & 0x7fffffffffffffffull) : ~u));
 }
+// bound on |filter score - exact score| for query b and ANY stored row (see Options::strict_certificate)
 __device__ __forceinline__ double cert_eps(const CertParams& c, int b) {
     double e = c.eps_fixed;
-    if (c.sigmas > 0.0) {
-        const double bound = c.sigmas * (1.0 / 512.0) * 0.816496580927726 * c.q4[b] *
-                             (double)__uint_as_float(c.norms[1]);
-        e = (bound < 4.1e-3 ? bound : 4.1e-3) + 2e-5;  // + fp32 accumulation slack of the tensor pipe
+    if (c.kind != CERT_FIXED) {
+        const double rq = c.qres[b];
+        const double rc = (double)__uint_as_float(c.norms[2]);
+        const double rigorous = rq + (1.0 + rq) * rc;  // Cauchy-Schwarz on the two rounding residuals
+        e = rigorous;
+        if (c.kind == CERT_STATISTICAL) {
+            // u = 2^-8 (bf16 keeps 8 significand bits), independent roundings
+            const double bound = c.sigmas * (1.0 / 256.0) * 0.816496580927726 * c.q4[b] *
+                                 (double)__uint_as_float(c.norms[1]);
+            if (bound < e) e = bound;
+        }
+        e += c.acc_slack * (1.0 + rq) * (1.0 + rc) + 4e-7;
     }
     if (c.metric == CMW_METRIC_IP) e *= c.qn64[b] * (double)__uint_as_float(c.norms[0]);
     return e;

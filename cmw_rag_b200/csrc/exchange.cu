@@ -10,9 +10,14 @@
 // (a rank can only reach epoch n+2 after all peers have published n+1, i.e. finished reading n).
 // The reference has no counterpart (single Chroma server).
 //
+// The merge kernel's wait is BOUNDED (a dead, late or out-of-step peer must not hang this GPU): it polls with
+// __nanosleep back-off against %globaltimer and gives up after `timeout_ns`, marking every query
+// CMW_FLAG_PEER_TIMEOUT; each sender also publishes the (B, k) it sent, and a mismatch is reported the same way.
+//
 // Peer buffer layout (one per rank, allocated by cmw_peer_alloc, zero-initialised):
-//   [0, 1024)            header: uint32 flags[2][64] (parity, source rank), uint32 done[2]
-//   [1024, ...)          2 parities x { f64 scores [G, Bmax, kmax] ; i64 ids [G, Bmax, kmax] }
+//   [0, 2048)            header: uint32 flags[2][64] (parity, source rank), uint32 done[2], then at uint32
+//                        offset 256: uint32 shape[2][64] = (B << 12 | k) as published by each source rank
+//   [2048, ...)          2 parities x { f64 scores [G, Bmax, kmax] ; i64 ids [G, Bmax, kmax] ; i32 flags [G, Bmax] }
 #include <string.h>
 
 #include "common.cuh"
@@ -20,7 +25,7 @@
 namespace cmw {
 
 constexpr int kXMaxRanks = 64;
-constexpr size_t kXHeaderBytes = 1024;
+constexpr size_t kXHeaderBytes = 2048;
 
 struct XPeers {
     uint8_t* buf[kXMaxRanks];
@@ -32,19 +37,30 @@ __device__ __forceinline__ uint32_t* x_flags(uint8_t* base, int parity) {
 __device__ __forceinline__ uint32_t* x_done(uint8_t* base, int parity) {
     return reinterpret_cast<uint32_t*>(base) + 2 * kXMaxRanks + parity;
 }
+__device__ __forceinline__ uint32_t* x_shape(uint8_t* base, int parity) {
+    return reinterpret_cast<uint32_t*>(base) + 256 + parity * kXMaxRanks;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __global__ void __launch_bounds__(256)
 exchange_send_kernel(XPeers peers, int G, int rank, int B, int k, size_t slot_elems, size_t parity_bytes, int parity,
-                     uint32_t epoch, const double* __restrict__ scores, const int64_t* __restrict__ ids) {
+                     uint32_t epoch, const double* __restrict__ scores, const int64_t* __restrict__ ids,
+                     const int32_t* __restrict__ flags, int max_batch) {
     const size_t n = (size_t)B * k;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (int g = 0; g < G; ++g) {
         uint8_t* base = peers.buf[g] + kXHeaderBytes + (size_t)parity * parity_bytes;
         double* ds = reinterpret_cast<double*>(base) + (size_t)rank * slot_elems;
         int64_t* di = reinterpret_cast<int64_t*>(base + (size_t)G * slot_elems * sizeof(double)) + (size_t)rank * slot_elems;
+        int32_t* df = reinterpret_cast<int32_t*>(base + (size_t)G * slot_elems * 16) + (size_t)rank * max_batch;
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
             ds[i] = scores[i];
             di[i] = ids[i];
+            if (i < (size_t)B) df[i] = flags != nullptr ? flags[i] : 0;
         }
     }
     // publish: every block fences its peer stores system-wide; the last one to finish raises the flags
@@ -55,6 +71,9 @@ exchange_send_kernel(XPeers peers, int G, int rank, int B, int k, size_t slot_el
         const uint32_t prev = atomicAdd(done, 1u);
         if (prev == gridDim.x - 1) {
             *done = 0;  // ready for the next use of this parity
+            __threadfence_system();
+            const uint32_t shape = ((uint32_t)B << 12) | (uint32_t)k;
+            for (int g = 0; g < G; ++g) *(volatile uint32_t*)(x_shape(peers.buf[g], parity) + rank) = shape;
             __threadfence_system();
             for (int g = 0; g < G; ++g) {
                 volatile uint32_t* f = x_flags(peers.buf[g], parity) + rank;
@@ -67,18 +86,54 @@ exchange_send_kernel(XPeers peers, int G, int rank, int B, int k, size_t slot_el
 
 __global__ void __launch_bounds__(256)
 exchange_merge_kernel(uint8_t* self, int G, int B, int k, int k_out, size_t slot_elems, size_t parity_bytes,
-                      int parity, uint32_t epoch, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
-                      double* __restrict__ out_scores64) {
+                      int parity, uint32_t epoch, uint64_t timeout_ns, float* __restrict__ out_scores,
+                      int64_t* __restrict__ out_ids, double* __restrict__ out_scores64,
+                      int32_t* __restrict__ out_flags, int max_batch) {
     extern __shared__ __align__(16) uint8_t x_smem[];
-    // wait until every source rank has published this epoch
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    // wait -- for a bounded time -- until every source rank has published this epoch
     if (threadIdx.x < G) {
         volatile uint32_t* f = x_flags(self, parity) + threadIdx.x;
+        const uint64_t t0 = global_timer_ns();
+        unsigned ns = 32;
+        bool ok = true;
         while (*f != epoch) {
+            if (global_timer_ns() - t0 > timeout_ns) {
+                ok = false;
+                break;
+            }
+            __nanosleep(ns);
+            if (ns < 2048) ns <<= 1;
         }
+        if (ok) {
+            __threadfence_system();
+            const uint32_t shape = *(volatile uint32_t*)(x_shape(self, parity) + threadIdx.x);
+            ok = shape == (((uint32_t)B << 12) | (uint32_t)k);  // every rank must exchange the same (B, k)
+        }
+        if (!ok) atomicExch(&bad, 1);
     }
     __syncthreads();
     __threadfence_system();
     const int b = blockIdx.x;
+    if (bad) {
+        for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
+            out_scores[(size_t)b * k_out + j] = -INFINITY;
+            out_ids[(size_t)b * k_out + j] = -1;
+            if (out_scores64 != nullptr) out_scores64[(size_t)b * k_out + j] = -INFINITY;
+        }
+        if (threadIdx.x == 0 && out_flags != nullptr) out_flags[b] = CMW_FLAG_PEER_TIMEOUT;
+        return;
+    }
+    if (threadIdx.x == 0 && out_flags != nullptr) {
+        // OR of the shards' own flags (they travelled with the candidates)
+        const int32_t* gf = reinterpret_cast<const int32_t*>(self + kXHeaderBytes + (size_t)parity * parity_bytes +
+                                                             (size_t)G * slot_elems * 16);
+        int f = 0;
+        for (int g = 0; g < G; ++g) f |= *reinterpret_cast<const volatile int32_t*>(gf + (size_t)g * max_batch + b);
+        out_flags[b] = f;
+    }
     const int n = G * k;
     const int m = next_pow2(n < 2 ? 2 : n);
     uint64_t* hi = reinterpret_cast<uint64_t*>(x_smem);
@@ -124,7 +179,7 @@ extern "C" {
 
 size_t cmw_peer_buffer_bytes(int G, int max_batch, int max_k) {
     if (G < 1 || G > kXMaxRanks || max_batch < 1 || max_k < 1) return 0;
-    return kXHeaderBytes + 2 * (size_t)G * max_batch * max_k * 16;
+    return kXHeaderBytes + 2 * ((size_t)G * max_batch * max_k * 16 + (size_t)G * max_batch * 4 + 256);
 }
 
 int cmw_peer_alloc(int device, size_t bytes, void** dev_ptr, void* ipc_handle_out) {
@@ -171,10 +226,21 @@ int cmw_peer_free(void* dev_ptr) {
 int cmw_exchange_merge(void* const* peer_bufs_host, int G, int rank, int max_batch, int max_k, int B, int k,
                        int k_out, uint32_t epoch, const double* scores64_local_dev, const int64_t* ids_local_dev,
                        float* out_scores_dev, int64_t* out_ids_dev, double* out_scores64_dev, void* stream_v) {
+    return cmw_exchange_merge_ex(peer_bufs_host, G, rank, max_batch, max_k, B, k, k_out, epoch, scores64_local_dev,
+                                 ids_local_dev, nullptr, out_scores_dev, out_ids_dev, out_scores64_dev, nullptr, 0,
+                                 stream_v);
+}
+
+int cmw_exchange_merge_ex(void* const* peer_bufs_host, int G, int rank, int max_batch, int max_k, int B, int k,
+                          int k_out, uint32_t epoch, const double* scores64_local_dev, const int64_t* ids_local_dev,
+                          const int32_t* flags_local_dev, float* out_scores_dev, int64_t* out_ids_dev,
+                          double* out_scores64_dev, int32_t* out_flags_dev, int timeout_ms, void* stream_v) {
     CMW_REQUIRE(peer_bufs_host && scores64_local_dev && ids_local_dev && out_scores_dev && out_ids_dev,
                 "cmw_exchange_merge: NULL argument");
     CMW_REQUIRE(G >= 1 && G <= kXMaxRanks && rank >= 0 && rank < G, "cmw_exchange_merge: bad rank/world");
     CMW_REQUIRE(B >= 1 && B <= max_batch && k >= 1 && k <= max_k && k_out >= 1, "cmw_exchange_merge: bad sizes");
+    CMW_REQUIRE(B < (1 << 20) && k < (1 << 12), "cmw_exchange_merge: B or k too large for the shape word");
+    const uint64_t timeout_ns = (uint64_t)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
     CMW_REQUIRE(epoch != 0, "cmw_exchange_merge: epoch must be non-zero");
     const int n = G * k;
     CMW_REQUIRE(n <= 8192, "cmw_exchange_merge: G*k = %d exceeds 8192", n);
@@ -185,13 +251,13 @@ int cmw_exchange_merge(void* const* peer_bufs_host, int G, int rank, int max_bat
         peers.buf[g] = reinterpret_cast<uint8_t*>(peer_bufs_host[g]);
     }
     const size_t slot_elems = (size_t)max_batch * max_k;
-    const size_t parity_bytes = (size_t)G * slot_elems * 16;
+    const size_t parity_bytes = (size_t)G * slot_elems * 16 + (size_t)G * max_batch * 4 + 256;
     const int parity = (int)(epoch & 1u);
     const size_t total = (size_t)B * k;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 296) blocks = 296;
     exchange_send_kernel<<<blocks, 256, 0, stream>>>(peers, G, rank, B, k, slot_elems, parity_bytes, parity, epoch,
-                                                     scores64_local_dev, ids_local_dev);
+                                                     scores64_local_dev, ids_local_dev, flags_local_dev, max_batch);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     const size_t smem = (size_t)next_pow2_host(n < 2 ? 2 : n) * 16;
@@ -201,7 +267,8 @@ int cmw_exchange_merge(void* const* peer_bufs_host, int G, int rank, int max_bat
         smem_set.done(smem);
     }
     exchange_merge_kernel<<<B, 256, smem, stream>>>(peers.buf[rank], G, B, k, k_out, slot_elems, parity_bytes, parity,
-                                                    epoch, out_scores_dev, out_ids_dev, out_scores64_dev);
+                                                    epoch, timeout_ns, out_scores_dev, out_ids_dev, out_scores64_dev,
+                                                    out_flags_dev, max_batch);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;

@@ -239,7 +239,7 @@ void set_scan_order(GemmParams& p, const GemmArgs& a, int tile_rows) {
     p.perm_mul = 0;
     p.perm_tiles = (s->rows + tile_rows - 1) / tile_rows;
     const bool whole = a.row_begin == 0 && a.row_end >= s->rows;
-    if (g_opt.scan_permute == 0 || whole || p.perm_tiles < 64) return;
+    if (a.opt->scan_permute == 0 || whole || p.perm_tiles < 64) return;
     auto gcd = [](int64_t x, int64_t y) {
         while (y) {
             const int64_t t = x % y;
@@ -255,6 +255,19 @@ void set_scan_order(GemmParams& p, const GemmArgs& a, int tile_rows) {
     p.row_end = s->rows;
 }
 
+// which K2 kernel a padded batch runs on: CTA pairs (cta_group::2) for the tensor-bound batches, single CTAs
+// for the HBM-bound ones
+static bool use_cta_pairs(const Options& o, int bpad) {
+    return o.gemm_2cta != 0 && bpad >= (int)o.gemm_2cta_min_batch && (bpad % 256 == 0 || (bpad < 256 && bpad % 64 == 0));
+}
+
+// true when the slabs of a multi-slab search scan the store's tiles in the stride permutation (set_scan_order),
+// i.e. every slab is a spread sample of the corpus; false = storage order
+bool gemm_scan_permuted(const Store* s, const Options& o, int bpad) {
+    const int tile_rows = use_cta_pairs(o, bpad) ? 2 * kTileM : kTileM;
+    return o.scan_permute != 0 && (s->rows + tile_rows - 1) / tile_rows >= 64;
+}
+
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     const Store* s = a.store;
     CMW_REQUIRE(gemm_supported(s), "launch_gemm: store has no bf16 tiles / TMA descriptor");
@@ -262,10 +275,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     if (a.dense)
         CMW_REQUIRE(a.row_end - a.row_begin <= (a.wide_scores ? a.wide_stride : kPoolCap),
                     "launch_gemm: dense slab larger than its destination");
-    // tensor-bound batches run on CTA pairs (cta_group::2); the HBM-bound ones on single CTAs
-    if (g_opt.gemm_2cta != 0 && a.bpad >= (int)g_opt.gemm_2cta_min_batch && (a.bpad % 256 == 0 || (a.bpad < 256 && a.bpad % 64 == 0)) &&
-        (a.row_begin % (2 * kTileM)) == 0)
-        return launch_gemm_2cta(a, stream);
+    CMW_REQUIRE((a.row_begin % (2 * kTileM)) == 0, "launch_gemm: slab start must be a multiple of %d rows", 2 * kTileM);
+    if (use_cta_pairs(*a.opt, a.bpad)) return launch_gemm_2cta(a, stream);
     GemmParams p;
     p.dim = s->dim;
     p.num_kb = (s->dim + kBlockK - 1) / kBlockK;

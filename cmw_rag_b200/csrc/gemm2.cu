@@ -377,7 +377,7 @@ int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
     int clusters = s->sm_count / 2;
     if (n_items < clusters) clusters = n_items;
     // dynamic scheduling (cluster launch control): one pair per item in the grid, the resident pairs steal the rest
-    p.dynamic = (g_opt.gemm_clc != 0 && n_items > clusters) ? 1 : 0;
+    p.dynamic = (a.opt->gemm_clc != 0 && n_items > clusters) ? 1 : 0;
     if (p.dynamic) clusters = n_items;
     gemm_topk_kernel_2cta<<<2 * clusters, kGemm2Threads, smem, stream>>>(s->tmap_bf16, tmap_b, p);
     CMW_LAUNCHED();

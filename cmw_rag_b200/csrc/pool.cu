@@ -14,8 +14,9 @@ namespace cmw {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, int metric,
-                    double* __restrict__ qn64, double* __restrict__ q4, float* __restrict__ q_f32,
-                    __nv_bfloat16* __restrict__ q_bf16, Pool pool, int dense_count, Pool seg, int wide_rows) {
+                    double* __restrict__ qn64, double* __restrict__ q4, double* __restrict__ qres,
+                    float* __restrict__ q_f32, __nv_bfloat16* __restrict__ q_bf16, Pool pool, int dense_count,
+                    Pool seg, int wide_rows) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= bpad) return;
@@ -71,25 +72,39 @@ prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, i
         if (lane == 0) q4[b] = sqrt(sqrt(s4));
     }
     float4* of = reinterpret_cast<float4*>(q_f32 + (size_t)b * dim);
+    double res2 = 0.0;  // |scaled query - its bf16 tile|^2, from the values actually written
     for (int c = lane; c < nvec; c += 32) {
         float4 v = __ldg(in + c);
-        float4 w = make_float4((float)((double)v.x * scale), (float)((double)v.y * scale),
-                               (float)((double)v.z * scale), (float)((double)v.w * scale));
+        const double ex = (double)v.x * scale, ey = (double)v.y * scale, ez = (double)v.z * scale,
+                     ew = (double)v.w * scale;
+        float4 w = make_float4((float)ex, (float)ey, (float)ez, (float)ew);
         of[c] = w;
         if (q_bf16 != nullptr) {
             __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(q_bf16 + (size_t)b * dim);
-            ob[2 * c] = __floats2bfloat162_rn(w.x, w.y);
-            ob[2 * c + 1] = __floats2bfloat162_rn(w.z, w.w);
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
+            ob[2 * c] = lo;
+            ob[2 * c + 1] = hi;
+            const double dx = ex - (double)__low2float(lo), dy = ey - (double)__high2float(lo);
+            const double dz = ez - (double)__low2float(hi), dw = ew - (double)__high2float(hi);
+            res2 += dx * dx + dy * dy + dz * dz + dw * dw;
         }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) res2 += __shfl_xor_sync(0xffffffffu, res2, o);
+    if (lane == 0) {
+        // relative to the scaled query's norm (1 for cosine, |q| for inner product), rounded up a little
+        const double ref = (metric == CMW_METRIC_COSINE) ? 1.0 : nrm;
+        qres[b] = ref > 0.0 ? sqrt(res2) / ref * (1.0 + 1e-9) + 1e-12 : 0.0;
     }
 }
 
 int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64, double* q4,
-                        float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count, Pool seg, int wide_rows,
-                        cudaStream_t stream) {
+                        double* qres, float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count, Pool seg,
+                        int wide_rows, cudaStream_t stream) {
     const int wpb = 8;
-    prep_queries_kernel<<<(bpad + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, batch, bpad, dim, metric, qn64, q4, q_f32,
-                                                                        q_bf16, pool, dense_count, seg, wide_rows);
+    prep_queries_kernel<<<(bpad + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, batch, bpad, dim, metric, qn64, q4, qres,
+                                                                        q_f32, q_bf16, pool, dense_count, seg,
+                                                                        wide_rows);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
@@ -104,22 +119,152 @@ int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric
 // compacted to the front (all ties at T are kept, so the `score >= thr` admission rule and the pool
 // stay consistent) and thr is raised to T.  The last call (final = 1) also sorts the survivors by
 // (score desc, id asc) and truncates to kprime -- the order K3 / the bf16 emit rely on.
+//
+// Entries whose score is -inf are ABSENT: that is what the dense first slab writes for tombstoned rows and
+// for the slots past the end of the store.  They never count towards kprime and never survive, so a slab of
+// dead rows leaves the pool empty and thr at -inf instead of filling the pool with 4096 placeholders (which
+// made every later admission fall off the end of the pool).
 constexpr int kCompactThreads = 256;
 constexpr int kCompactPer = kPoolCap / kCompactThreads;  // 16 entries per thread, in registers
 
+struct SelectShared {
+    int hist[256];
+    int warp_sums[kCompactThreads / 32];
+    int sel_digit, sel_below;
+};
+
+// key of one pool entry (ascending = better); returns false for an absent entry
+__device__ __forceinline__ bool load_entry(float score, int32_t row, uint32_t& key, int32_t& rid) {
+    key = 0xffffffffu;
+    rid = -1;
+    if (!(score > -INFINITY)) return false;  // -inf and NaN: absent
+    key = (uint32_t)(desc_key(score, 0u) >> 32);
+    rid = row;
+    return true;
+}
+
+// exclusive prefix of `mine` over the CTA and the CTA-wide total (two barriers)
+__device__ __forceinline__ int block_exclusive_scan(int mine, int& total, SelectShared& sm) {
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    int v = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    __syncthreads();  // warp_sums may still be read by the previous use
+    if (lane == 31) sm.warp_sums[w] = v;
+    __syncthreads();
+    int base = 0;
+    total = 0;
+#pragma unroll
+    for (int ww = 0; ww < kCompactThreads / 32; ++ww) {
+        const int x = sm.warp_sums[ww];
+        if (ww < w) base += x;
+        total += x;
+    }
+    return base + v - mine;
+}
+
+// The selection shared by the compaction kernel and the merge kernel of the wide first slab.  Every thread
+// holds kCompactPer entries in registers (rid < 0 = absent).  Keeps the best kprime (and every tie at the
+// cut), writes them to dst_sc / dst_id -- unordered, or for final != 0 sorted by (score desc, id asc) and
+// truncated to kprime -- and publishes cnt / thr / ovf of pool slot `b`.
+__device__ __forceinline__ void select_and_compact(uint32_t (&key)[kCompactPer], int32_t (&rid)[kCompactPer],
+                                                   int kprime, int final, bool overflowed, Pool pool, int b,
+                                                   uint64_t* sort_keys, SelectShared& sm) {
+    const int t = threadIdx.x;
+    float* sc = pool.scores + (size_t)b * kPoolCap;
+    int32_t* id = pool.ids + (size_t)b * kPoolCap;
+    int valid_mine = 0;
+#pragma unroll
+    for (int j = 0; j < kCompactPer; ++j) valid_mine += rid[j] >= 0 ? 1 : 0;
+    int valid;
+    block_exclusive_scan(valid_mine, valid, sm);
+    uint32_t T = 0xffffffffu;  // keep everything that is present
+    const bool select = valid > kprime;
+    if (select) {
+        uint32_t prefix = 0, mask = 0;
+        int remaining = kprime;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            sm.hist[t] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < kCompactPer; ++j) {
+                if (rid[j] >= 0 && (key[j] & mask) == prefix) atomicAdd(&sm.hist[(key[j] >> shift) & 255u], 1);
+            }
+            __syncthreads();
+            // inclusive scan of the 256 bins (one per thread)
+            const int h = sm.hist[t];
+            int total;
+            const int cum = block_exclusive_scan(h, total, sm) + h;
+            if (cum >= remaining && cum - h < remaining) {
+                sm.sel_digit = t;
+                sm.sel_below = cum - h;
+            }
+            __syncthreads();
+            prefix |= (uint32_t)sm.sel_digit << shift;
+            mask |= 0xffu << shift;
+            remaining -= sm.sel_below;
+        }
+        T = prefix;
+    }
+    // stream compaction of the kept entries (every entry is in registers)
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < kCompactPer; ++j) mine += (rid[j] >= 0 && key[j] <= T) ? 1 : 0;
+    int total;
+    int pos = block_exclusive_scan(mine, total, sm);
+    if (!final) {
+#pragma unroll
+        for (int j = 0; j < kCompactPer; ++j) {
+            if (rid[j] >= 0 && key[j] <= T) {
+                sc[pos] = f32_from_orderable(~key[j]);
+                id[pos] = rid[j];
+                ++pos;
+            }
+        }
+        if (t == 0) {
+            pool.cnt[b] = total;
+            if (select) pool.thr[b] = f32_from_orderable(~T);
+            if (overflowed) pool.ovf[b] = 1;
+        }
+        return;
+    }
+    // final: sort the survivors by (score desc, id asc), keep kprime
+    const int m = next_pow2(total < 2 ? 2 : total);
+    for (int i = total + t; i < m; i += kCompactThreads) sort_keys[i] = ~0ull;
+#pragma unroll
+    for (int j = 0; j < kCompactPer; ++j) {
+        if (rid[j] >= 0 && key[j] <= T) {
+            sort_keys[pos] = ((uint64_t)key[j] << 32) | (uint64_t)(uint32_t)rid[j];
+            ++pos;
+        }
+    }
+    bitonic_sort_u64(sort_keys, m);
+    const int keep = total < kprime ? total : kprime;
+    for (int i = t; i < keep; i += kCompactThreads) {
+        const uint64_t k = sort_keys[i];
+        sc[i] = desc_key_score(k);
+        id[i] = (int32_t)(uint32_t)k;
+    }
+    if (t == 0) {
+        pool.cnt[b] = keep;
+        if (total >= kprime) pool.thr[b] = desc_key_score(sort_keys[kprime - 1]);
+        if (overflowed) pool.ovf[b] = 1;
+    }
+}
+
 __global__ void __launch_bounds__(kCompactThreads, 5) pool_compact_kernel(Pool pool, int kprime, int final) {
     extern __shared__ __align__(16) uint8_t cmp_smem[];
-    __shared__ int hist[256];
-    __shared__ int warp_sums[32];
-    __shared__ int sel_digit, sel_below;
+    __shared__ SelectShared sm;
     const int b = blockIdx.x;
     const int t = threadIdx.x;
     const int n_in = pool.cnt[b];
     const int n = n_in < kPoolCap ? n_in : kPoolCap;
-    float* sc = pool.scores + (size_t)b * kPoolCap;
-    int32_t* id = pool.ids + (size_t)b * kPoolCap;
-
-    // ascending key = better score
+    const float* sc = pool.scores + (size_t)b * kPoolCap;
+    const int32_t* id = pool.ids + (size_t)b * kPoolCap;
     uint32_t key[kCompactPer];
     int32_t rid[kCompactPer];
 #pragma unroll
@@ -127,112 +272,10 @@ __global__ void __launch_bounds__(kCompactThreads, 5) pool_compact_kernel(Pool p
         const int i = t + j * kCompactThreads;
         key[j] = 0xffffffffu;
         rid[j] = -1;
-        if (i < n) {
-            key[j] = (uint32_t)(desc_key(sc[i], 0u) >> 32);
-            rid[j] = id[i];
-        }
+        if (i < n) load_entry(sc[i], id[i], key[j], rid[j]);
     }
-    uint32_t T = 0xffffffffu;  // keep everything
-    const bool select = n > kprime;
-    if (select) {
-        uint32_t prefix = 0, mask = 0;
-        int remaining = kprime;
-        for (int pass = 0; pass < 4; ++pass) {
-            const int shift = 24 - 8 * pass;
-            hist[t] = 0;
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < kCompactPer; ++j) {
-                if (rid[j] >= 0 && (key[j] & mask) == prefix) atomicAdd(&hist[(key[j] >> shift) & 255u], 1);
-            }
-            __syncthreads();
-            // inclusive scan of the 256 bins (one per thread)
-            const int h = hist[t];
-            int v = h;
-            const int lane = t & 31, w = t >> 5;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int u = __shfl_up_sync(0xffffffffu, v, o);
-                if (lane >= o) v += u;
-            }
-            if (lane == 31) warp_sums[w] = v;
-            __syncthreads();
-            int base = 0;
-            for (int ww = 0; ww < w; ++ww) base += warp_sums[ww];
-            const int cum = base + v;
-            if (cum >= remaining && cum - h < remaining) {
-                sel_digit = t;
-                sel_below = cum - h;
-            }
-            __syncthreads();
-            prefix |= (uint32_t)sel_digit << shift;
-            mask |= 0xffu << shift;
-            remaining -= sel_below;
-            __syncthreads();
-        }
-        T = prefix;
-    } else {
-        __syncthreads();
-    }
-    // stream compaction of the kept entries (every entry was read into registers above)
-    int mine = 0;
-#pragma unroll
-    for (int j = 0; j < kCompactPer; ++j) mine += (rid[j] >= 0 && key[j] <= T) ? 1 : 0;
-    {
-        const int lane = t & 31, w = t >> 5;
-        int v = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int u = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v += u;
-        }
-        if (lane == 31) warp_sums[w] = v;
-        __syncthreads();
-        int base = 0;
-        for (int ww = 0; ww < w; ++ww) base += warp_sums[ww];
-        int total = 0;
-        for (int ww = 0; ww < kCompactThreads / 32; ++ww) total += warp_sums[ww];
-        int pos = base + v - mine;
-        if (!final) {
-#pragma unroll
-            for (int j = 0; j < kCompactPer; ++j) {
-                if (rid[j] >= 0 && key[j] <= T) {
-                    sc[pos] = f32_from_orderable(~key[j]);
-                    id[pos] = rid[j];
-                    ++pos;
-                }
-            }
-            if (t == 0) {
-                pool.cnt[b] = total;
-                if (select) pool.thr[b] = f32_from_orderable(~T);
-                if (n_in > kPoolCap) pool.ovf[b] = 1;
-            }
-            return;
-        }
-        // final: sort the survivors by (score desc, id asc), keep kprime
-        uint64_t* keys = reinterpret_cast<uint64_t*>(cmp_smem);
-        const int m = next_pow2(total < 2 ? 2 : total);
-        for (int i = total + t; i < m; i += kCompactThreads) keys[i] = ~0ull;
-#pragma unroll
-        for (int j = 0; j < kCompactPer; ++j) {
-            if (rid[j] >= 0 && key[j] <= T) {
-                keys[pos] = ((uint64_t)key[j] << 32) | (uint64_t)(uint32_t)rid[j];
-                ++pos;
-            }
-        }
-        bitonic_sort_u64(keys, m);
-        const int keep = total < kprime ? total : kprime;
-        for (int i = t; i < keep; i += kCompactThreads) {
-            const uint64_t k = keys[i];
-            sc[i] = desc_key_score(k);
-            id[i] = (int32_t)(uint32_t)k;
-        }
-        if (t == 0) {
-            pool.cnt[b] = keep;
-            if (total >= kprime) pool.thr[b] = desc_key_score(keys[kprime - 1]);
-            if (n_in > kPoolCap) pool.ovf[b] = 1;
-        }
-    }
+    // (the barriers of the first block scan inside separate these loads from the in-place write-back)
+    select_and_compact(key, rid, kprime, final, n_in > kPoolCap, pool, b, reinterpret_cast<uint64_t*>(cmp_smem), sm);
 }
 
 int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_t stream) {
@@ -247,16 +290,14 @@ int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_
 // Wide first slab (small batches): the filter wrote the scores and ids of up to 65536 rows into a scratch
 // matrix laid out as 16 pool-sized segments per query.  Level 1 = the ordinary compaction kernel over the
 // batch * 16 segments (each keeps its best kprime and ties, in parallel on as many SMs); level 2 = this
-// kernel: one CTA per query gathers the segments' survivors (<= 16 * kprime + ties), selects the kprime-th
-// best of them exactly like the compaction kernel, moves those entries into the query's pool and publishes
-// thr.  An entry that is among the best kprime overall is among the best kprime of its segment, so the cut
-// is exact; ties at the cut survive level 1 for the same reason.
+// kernel: one CTA per query gathers the segments' survivors (<= 16 * kprime + ties), runs the same selection
+// on them, moves the kept entries into the query's pool and publishes thr.  An entry that is among the best
+// kprime overall is among the best kprime of its segment, so the cut is exact; ties at the cut survive level
+// 1 for the same reason.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCompactThreads, 5) wide_merge_kernel(Pool seg, Pool pool, int kprime, int final) {
     extern __shared__ __align__(16) uint8_t wm_smem[];
-    __shared__ int hist[256];
-    __shared__ int warp_sums[32];
-    __shared__ int sel_digit, sel_below;
+    __shared__ SelectShared sm;
     __shared__ int seg_off[kWideSegments + 1];
     __shared__ int seg_flag;
     const int b = blockIdx.x;
@@ -290,110 +331,11 @@ __global__ void __launch_bounds__(kCompactThreads, 5) wide_merge_kernel(Pool seg
 #pragma unroll
             for (int q = 1; q < kWideSegments; ++q) sgm += (i >= seg_off[q]) ? 1 : 0;
             const size_t src = ((size_t)b * kWideSegments + sgm) * kPoolCap + (size_t)(i - seg_off[sgm]);
-            key[j] = (uint32_t)(desc_key(seg.scores[src], 0u) >> 32);
-            rid[j] = seg.ids[src];
+            load_entry(seg.scores[src], seg.ids[src], key[j], rid[j]);
         }
     }
-    uint32_t T = 0xffffffffu;
-    const bool select = n > kprime;
-    if (select) {
-        uint32_t prefix = 0, mask = 0;
-        int remaining = kprime;
-        for (int pass = 0; pass < 4; ++pass) {
-            const int shift = 24 - 8 * pass;
-            hist[t] = 0;
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < kCompactPer; ++j) {
-                if (rid[j] >= 0 && (key[j] & mask) == prefix) atomicAdd(&hist[(key[j] >> shift) & 255u], 1);
-            }
-            __syncthreads();
-            const int h = hist[t];
-            int v = h;
-            const int lane = t & 31, w = t >> 5;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int u = __shfl_up_sync(0xffffffffu, v, o);
-                if (lane >= o) v += u;
-            }
-            if (lane == 31) warp_sums[w] = v;
-            __syncthreads();
-            int base = 0;
-            for (int ww = 0; ww < w; ++ww) base += warp_sums[ww];
-            const int cum = base + v;
-            if (cum >= remaining && cum - h < remaining) {
-                sel_digit = t;
-                sel_below = cum - h;
-            }
-            __syncthreads();
-            prefix |= (uint32_t)sel_digit << shift;
-            mask |= 0xffu << shift;
-            remaining -= sel_below;
-            __syncthreads();
-        }
-        T = prefix;
-    }
-    int mine = 0;
-#pragma unroll
-    for (int j = 0; j < kCompactPer; ++j) mine += (rid[j] >= 0 && key[j] <= T) ? 1 : 0;
-    const int lane = t & 31, w = t >> 5;
-    int v = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int u = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += u;
-    }
-    __syncthreads();
-    if (lane == 31) warp_sums[w] = v;
-    __syncthreads();
-    int base = 0, total = 0;
-    for (int ww = 0; ww < kCompactThreads / 32; ++ww) {
-        if (ww < w) base += warp_sums[ww];
-        total += warp_sums[ww];
-    }
-    int pos = base + v - mine;
-    float* sc = pool.scores + (size_t)b * kPoolCap;
-    int32_t* id = pool.ids + (size_t)b * kPoolCap;
-    if (!final) {
-#pragma unroll
-        for (int j = 0; j < kCompactPer; ++j) {
-            if (rid[j] >= 0 && key[j] <= T) {
-                sc[pos] = f32_from_orderable(~key[j]);
-                id[pos] = rid[j];
-                ++pos;
-            }
-        }
-        if (t == 0) {
-            pool.cnt[b] = total;
-            if (select) pool.thr[b] = f32_from_orderable(~T);
-            if (n_in > kPoolCap || seg_flag) pool.ovf[b] = 1;
-        }
-        return;
-    }
-    // the wide slab was the whole corpus: sort the survivors by (score desc, id asc) and keep kprime, exactly
-    // like the final call of the compaction kernel
-    uint64_t* keys = reinterpret_cast<uint64_t*>(wm_smem);
-    const int m = next_pow2(total < 2 ? 2 : total);
-    for (int i = total + t; i < m; i += kCompactThreads) keys[i] = ~0ull;
-#pragma unroll
-    for (int j = 0; j < kCompactPer; ++j) {
-        if (rid[j] >= 0 && key[j] <= T) {
-            keys[pos] = ((uint64_t)key[j] << 32) | (uint64_t)(uint32_t)rid[j];
-            ++pos;
-        }
-    }
-    bitonic_sort_u64(keys, m);
-    const int keep = total < kprime ? total : kprime;
-    for (int i = t; i < keep; i += kCompactThreads) {
-        const uint64_t kk = keys[i];
-        sc[i] = desc_key_score(kk);
-        id[i] = (int32_t)(uint32_t)kk;
-    }
-    if (t == 0) {
-        pool.cnt[b] = keep;
-        if (total >= kprime) pool.thr[b] = desc_key_score(keys[kprime - 1]);
-        if (n_in > kPoolCap || seg_flag) pool.ovf[b] = 1;
-    }
+    select_and_compact(key, rid, kprime, final, n_in > kPoolCap || seg_flag != 0, pool, b,
+                       reinterpret_cast<uint64_t*>(wm_smem), sm);
 }
 
 int launch_wide_select(Pool seg, Pool pool, int batch, int kprime, int final, cudaStream_t stream) {
@@ -423,8 +365,11 @@ rescore_kernel(const float* __restrict__ f32, const double* __restrict__ norm64,
     // The pool is sorted by filter score.  With a_k its k-th filter score, every row whose filter score
     // is below a_k - 2*eps has an exact score below a_k - eps <= (k-th exact score): it cannot be in the
     // exact top-k, so it is not rescored (its slot gets -inf and sorts last).
+    // Row shards: the k-th best filter score over ALL shards is handed in (cert.global_kth); the k rows behind it
+    // have exact scores >= that - eps wherever they live, so the same cut holds against the global k-th exact score.
     double cut = -INFINITY;
-    if (n > k) cut = (double)pool.scores[(size_t)b * kPoolCap + (k - 1)] - 2.0 * cert_eps(cert, b);
+    if (cert.global_kth != nullptr) cut = (double)cert.global_kth[b] - 2.0 * cert_eps(cert, b);
+    else if (n > k) cut = (double)pool.scores[(size_t)b * kPoolCap + (k - 1)] - 2.0 * cert_eps(cert, b);
     const float4* qv = reinterpret_cast<const float4*>(q_raw + (size_t)b * dim);
     const int nvec = dim >> 2;
     // gridDim.x blocks share a query (many for small batches, one for large ones); a warp walks its
@@ -484,7 +429,7 @@ rescore_kernel(const float* __restrict__ f32, const double* __restrict__ norm64,
 __global__ void __launch_bounds__(256)
 select_kernel(Pool pool, int k, int kprime, const double* __restrict__ exact, const CertParams cert,
               int64_t id_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
-              double* __restrict__ out_scores64, int32_t* __restrict__ out_flags) {
+              double* __restrict__ out_scores64, int32_t* __restrict__ out_flags, double* __restrict__ out_aux) {
     extern __shared__ __align__(16) uint8_t sel_smem[];
     const int b = blockIdx.x;
     const int n = pool.cnt[b] < kprime ? pool.cnt[b] : kprime;
@@ -510,14 +455,21 @@ select_kernel(Pool pool, int k, int kprime, const double* __restrict__ exact, co
             s = f64_from_orderable(~hi[j]);
             id = (int64_t)lo[j] + id_offset;
         }
-        out_scores[(size_t)b * k + j] = (float)s;
+        if (out_scores != nullptr) out_scores[(size_t)b * k + j] = (float)s;
         out_ids[(size_t)b * k + j] = id;
         if (out_scores64 != nullptr) out_scores64[(size_t)b * k + j] = s;
+    }
+    if (threadIdx.x == 0 && out_aux != nullptr) {
+        // row shards: what the cross-shard certificate needs from this shard -- every row outside this pool has
+        // filter score <= t (none, if the pool never filled), and eps with this shard's own residual bound
+        out_aux[2 * b] = (n >= kprime) ? (double)pool.thr[b] : -INFINITY;
+        out_aux[2 * b + 1] = cert_eps(cert, b);
     }
     if (threadIdx.x == 0 && out_flags != nullptr) {
         int flag = 0;
         if (pool.ovf[b]) flag = CMW_FLAG_UNCERTIFIED;
-        if (n >= kprime) {
+        // (a shard of a row-sharded search cannot certify anything by itself: cmw_shard_merge does)
+        if (n >= kprime && cert.global_kth == nullptr) {
             // rows outside the pool have filter score <= t, hence exact score <= t + eps
             const double t = (double)pool.thr[b];
             const double e = cert_eps(cert, b);
@@ -535,7 +487,7 @@ select_kernel(Pool pool, int k, int kprime, const double* __restrict__ exact, co
 int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprime, int metric,
                           const float* q_raw, const CertParams& cert, double* exact_ws,
                           float* out_scores, int64_t* out_ids, double* out_scores64,
-                          int32_t* out_flags, cudaStream_t stream) {
+                          int32_t* out_flags, double* out_aux, cudaStream_t stream) {
     CMW_REQUIRE(s->f32 != nullptr, "CMW_MODE_F32_EXACT needs a store created with CMW_STORE_F32");
     const int wpb = 8;
     // enough blocks to fill the GPU a few times over, at most one warp per candidate
@@ -550,7 +502,7 @@ int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprim
     CMW_CUDA_OK(cudaGetLastError());
     const size_t smem = (size_t)next_pow2_host(kprime) * 16;
     select_kernel<<<batch, 256, smem, stream>>>(pool, k, kprime, exact_ws, cert, s->id_offset, out_scores,
-                                               out_ids, out_scores64, out_flags);
+                                               out_ids, out_scores64, out_flags, out_aux);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
@@ -559,7 +511,7 @@ int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprim
 // bf16 mode: the pool is already sorted by the last compaction; emit its best k.
 __global__ void pool_emit_kernel(Pool pool, int k, int64_t id_offset, float* __restrict__ out_scores,
                                  int64_t* __restrict__ out_ids, double* __restrict__ out_scores64,
-                                 int32_t* __restrict__ out_flags) {
+                                 int32_t* __restrict__ out_flags, double* __restrict__ out_aux) {
     const int b = blockIdx.x;
     const int n = pool.cnt[b];
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
@@ -572,18 +524,22 @@ __global__ void pool_emit_kernel(Pool pool, int k, int64_t id_offset, float* __r
                 id = (int64_t)pool.ids[(size_t)b * kPoolCap + j] + id_offset;
             }
         }
-        out_scores[(size_t)b * k + j] = s;
+        if (out_scores != nullptr) out_scores[(size_t)b * k + j] = s;
         out_ids[(size_t)b * k + j] = id;
         if (out_scores64 != nullptr) out_scores64[(size_t)b * k + j] = (double)s;
     }
     if (threadIdx.x == 0 && out_flags != nullptr) out_flags[b] = pool.ovf[b] ? CMW_FLAG_UNCERTIFIED : 0;
+    if (threadIdx.x == 0 && out_aux != nullptr) {  // approximate mode: nothing to certify across shards
+        out_aux[2 * b] = -INFINITY;
+        out_aux[2 * b + 1] = 0.0;
+    }
 }
 
 int launch_pool_emit(const Store* s, Pool pool, int batch, int k, float* out_scores,
-                     int64_t* out_ids, double* out_scores64, int32_t* out_flags,
+                     int64_t* out_ids, double* out_scores64, int32_t* out_flags, double* out_aux,
                      cudaStream_t stream) {
     pool_emit_kernel<<<batch, 128, 0, stream>>>(pool, k, s->id_offset, out_scores, out_ids,
-                                               out_scores64, out_flags);
+                                               out_scores64, out_flags, out_aux);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
@@ -631,6 +587,107 @@ merge_kernel(const double* __restrict__ scores, const int64_t* __restrict__ ids,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Row-sharded search: the three small kernels either side of the two all-gathers.
+// ---------------------------------------------------------------------------------------------
+// after the filter half: the best k FILTER scores of every pool (sorted by the final compaction), -inf padded
+__global__ void pool_topk_scores_kernel(Pool pool, int k, float* __restrict__ out) {
+    const int b = blockIdx.x;
+    const int n = pool.cnt[b];
+    for (int j = threadIdx.x; j < k; j += blockDim.x)
+        out[(size_t)b * k + j] = j < n ? pool.scores[(size_t)b * kPoolCap + j] : -INFINITY;
+}
+
+int launch_pool_topk_scores(Pool pool, int batch, int k, float* out, cudaStream_t stream) {
+    pool_topk_scores_kernel<<<batch, 128, 0, stream>>>(pool, k, out);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// after all-gather 1: the k-th best filter score over all shards, per query (-inf when fewer than k exist)
+__global__ void __launch_bounds__(256)
+shard_kth_kernel(const float* __restrict__ gathered, int G, int B, int k, float* __restrict__ out_kth) {
+    extern __shared__ __align__(16) uint8_t kth_smem[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(kth_smem);
+    const int b = blockIdx.x;
+    const int n = G * k;
+    const int m = next_pow2(n < 2 ? 2 : n);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        uint64_t key = ~0ull;
+        if (i < n) {
+            const int g = i / k, j = i - g * k;
+            const float v = gathered[((size_t)g * B + b) * k + j];
+            if (v > -INFINITY) key = desc_key(v, 0u);
+        }
+        keys[i] = key;
+    }
+    bitonic_sort_u64(keys, m);
+    if (threadIdx.x == 0) out_kth[b] = (keys[k - 1] != ~0ull) ? desc_key_score(keys[k - 1]) : -INFINITY;
+}
+
+// after all-gather 2: G blocks -> the global top k_out by (exact score desc, id asc) and the cross-shard
+// certificate: every row outside shard g's pool has filter score <= t_g, hence exact score <= t_g + eps_g; rows
+// inside a pool that were not rescored lie below the global cut (see rescore_kernel).  So the merged ids are the
+// oracle's as soon as the k-th merged exact score exceeds max_g (t_g + eps_g).
+__global__ void __launch_bounds__(256)
+shard_merge_kernel(const uint8_t* __restrict__ blocks, int G, int B, int k, int k_out,
+                   float* __restrict__ out_scores, int64_t* __restrict__ out_ids, double* __restrict__ out_scores64,
+                   int32_t* __restrict__ out_flags) {
+    extern __shared__ __align__(16) uint8_t sm_smem[];
+    const int b = blockIdx.x;
+    const int n = G * k;
+    const int m = next_pow2(n < 2 ? 2 : n);
+    uint64_t* hi = reinterpret_cast<uint64_t*>(sm_smem);
+    uint64_t* lo = hi + m;
+    const ShardBlock lay = shard_block(B, k);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        uint64_t h = ~0ull, l = ~0ull;
+        if (i < n) {
+            const int g = i / k, j = i - g * k;
+            const uint8_t* blk = blocks + (size_t)g * lay.total;
+            const int64_t id = reinterpret_cast<const int64_t*>(blk + lay.ids)[(size_t)b * k + j];
+            const double s = reinterpret_cast<const double*>(blk + lay.scores)[(size_t)b * k + j];
+            if (id >= 0 && s == s) {
+                h = ~f64_orderable(s);
+                l = (uint64_t)id;
+            }
+        }
+        hi[i] = h;
+        lo[i] = l;
+    }
+    bitonic_sort_u128(hi, lo, m);
+    for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
+        double s = -INFINITY;
+        int64_t id = -1;
+        if (j < n && !(hi[j] == ~0ull && lo[j] == ~0ull)) {
+            s = f64_from_orderable(~hi[j]);
+            id = (int64_t)lo[j];
+        }
+        out_scores[(size_t)b * k_out + j] = (float)s;
+        out_ids[(size_t)b * k_out + j] = id;
+        if (out_scores64 != nullptr) out_scores64[(size_t)b * k_out + j] = s;
+    }
+    if (threadIdx.x == 0 && out_flags != nullptr) {
+        int flag = 0;
+        double bar = -INFINITY;  // max over shards of t_g + eps_g
+        for (int g = 0; g < G; ++g) {
+            const uint8_t* blk = blocks + (size_t)g * lay.total;
+            flag |= reinterpret_cast<const int32_t*>(blk + lay.flags)[b];
+            const double* aux = reinterpret_cast<const double*>(blk + lay.aux) + 2 * (size_t)b;
+            if (aux[0] > -INFINITY && aux[0] + aux[1] > bar) bar = aux[0] + aux[1];
+        }
+        if (bar > -INFINITY) {
+            const int kk = k_out <= n ? k_out : n;
+            double kth = -INFINITY;
+            if (!(hi[kk - 1] == ~0ull && lo[kk - 1] == ~0ull)) kth = f64_from_orderable(~hi[kk - 1]);
+            if (!(kth > bar)) flag |= CMW_FLAG_UNCERTIFIED;
+        }
+        out_flags[b] = flag;
+    }
+}
+
 }  // namespace cmw
 
 using namespace cmw;
@@ -656,3 +713,39 @@ extern "C" int cmw_merge_topk(const double* scores_dev, const int64_t* ids_dev, 
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
 }
+
+namespace cmw {
+
+int launch_shard_kth(const float* gathered, int G, int B, int k, float* out_kth, cudaStream_t stream) {
+    const int n = G * k;
+    CMW_REQUIRE(n <= 16384, "cmw_shard_kth: G*k = %d exceeds 16384", n);
+    const size_t smem = (size_t)next_pow2_host(n < 2 ? 2 : n) * 8;
+    static SmemAttrCache smem_set;
+    if (smem > 48 * 1024 && smem_set.needs(smem)) {
+        CMW_CUDA_OK(cudaFuncSetAttribute(shard_kth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set.done(smem);
+    }
+    shard_kth_kernel<<<B, 256, smem, stream>>>(gathered, G, B, k, out_kth);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_shard_merge(const void* blocks, int G, int B, int k, int k_out, float* out_scores, int64_t* out_ids,
+                       double* out_scores64, int32_t* out_flags, cudaStream_t stream) {
+    const int n = G * k;
+    CMW_REQUIRE(n <= 8192, "cmw_shard_merge: G*k = %d exceeds 8192", n);
+    const size_t smem = (size_t)next_pow2_host(n < 2 ? 2 : n) * 16;
+    static SmemAttrCache smem_set;
+    if (smem > 48 * 1024 && smem_set.needs(smem)) {
+        CMW_CUDA_OK(cudaFuncSetAttribute(shard_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set.done(smem);
+    }
+    shard_merge_kernel<<<B, 256, smem, stream>>>(reinterpret_cast<const uint8_t*>(blocks), G, B, k, k_out, out_scores,
+                                                out_ids, out_scores64, out_flags);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cmw

@@ -1,4 +1,4 @@
-// scan.cu -- K1: streaming dot-product filter for batch 1-2 per pass (HBM-bound regime).
+// scan.cu -- K1: streaming dot-product filter, 1-4 queries per pass over the corpus (HBM-bound regime).
 //
 // Stands in for the HNSW walk behind collection.query() (rag_engine/storage/vector_store.py:59-63
 // of the reference) for single queries -- but exact: every live row is scored.
@@ -262,6 +262,10 @@ static int launch_one(const ScanParams& p, int grid, size_t smem, cudaStream_t s
 template <typename ELT, int NQ>
 static int dispatch_chunks(const ScanParams& p, int grid, size_t smem, cudaStream_t stream) {
     constexpr int PV = EltTraits<ELT>::kPerVec;
+    // 3-4 queries: NQ * D / 32 query floats per lane no longer fit the register file next to the row vectors
+    // (ptxas spills from NQ = 3 at D = 1536), so the queries are read from shared memory: ~30 KB of LDS per
+    // 6 KB row, still just inside the SM's shared-memory bandwidth at the HBM feed rate
+    if (NQ > 2) return launch_one<ELT, NQ, 0>(p, grid, smem, stream);
     if (p.dim == 1536) {
         return launch_one<ELT, NQ, 1536 / (32 * PV)>(p, grid, smem, stream);
     }
@@ -271,7 +275,7 @@ static int dispatch_chunks(const ScanParams& p, int grid, size_t smem, cudaStrea
 }
 
 int launch_scan(const ScanArgs& a, cudaStream_t stream) {
-    CMW_REQUIRE(a.nq == 1 || a.nq == 2, "launch_scan: nq must be 1 or 2");
+    CMW_REQUIRE(a.nq >= 1 && a.nq <= kScanMaxQueries, "launch_scan: nq must be in [1, %d]", kScanMaxQueries);
     CMW_REQUIRE(a.row_begin % 4 == 0, "launch_scan: slab start must be a multiple of 4");
     if (a.row_end <= a.row_begin) return 0;
     ScanParams p;
@@ -308,11 +312,19 @@ int launch_scan(const ScanArgs& a, cudaStream_t stream) {
     int grid = a.sm_count;
     if ((int64_t)grid > total_stages) grid = (int)total_stages;
     if (a.elt_bytes == 4) {
-        return a.nq == 1 ? dispatch_chunks<float, 1>(p, grid, smem, stream)
-                         : dispatch_chunks<float, 2>(p, grid, smem, stream);
+        switch (a.nq) {
+            case 1: return dispatch_chunks<float, 1>(p, grid, smem, stream);
+            case 2: return dispatch_chunks<float, 2>(p, grid, smem, stream);
+            case 3: return dispatch_chunks<float, 3>(p, grid, smem, stream);
+            default: return dispatch_chunks<float, 4>(p, grid, smem, stream);
+        }
     }
-    return a.nq == 1 ? dispatch_chunks<__nv_bfloat16, 1>(p, grid, smem, stream)
-                     : dispatch_chunks<__nv_bfloat16, 2>(p, grid, smem, stream);
+    switch (a.nq) {
+        case 1: return dispatch_chunks<__nv_bfloat16, 1>(p, grid, smem, stream);
+        case 2: return dispatch_chunks<__nv_bfloat16, 2>(p, grid, smem, stream);
+        case 3: return dispatch_chunks<__nv_bfloat16, 3>(p, grid, smem, stream);
+        default: return dispatch_chunks<__nv_bfloat16, 4>(p, grid, smem, stream);
+    }
 }
 
 }  // namespace cmw

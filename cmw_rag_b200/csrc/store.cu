@@ -66,14 +66,23 @@ ingest_kernel(const float* __restrict__ src, const int32_t* __restrict__ gid_src
             float4* out = reinterpret_cast<float4*>(f32 + dst * dim);
             for (int c = lane; c < nvec; c += 32) out[c] = __ldg(in + c);
         }
+        double res2 = 0.0;  // |c/|c| - its bf16 tile|^2 from the values actually written (rigorous certificate)
         if (bf16 != nullptr) {
             __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(bf16 + dst * dim);
             for (int c = lane; c < nvec; c += 32) {
                 float4 v = __ldg(in + c);
-                out[2 * c] = __floats2bfloat162_rn((float)((double)v.x * inv), (float)((double)v.y * inv));
-                out[2 * c + 1] =
-                    __floats2bfloat162_rn((float)((double)v.z * inv), (float)((double)v.w * inv));
+                const double ex = (double)v.x * inv, ey = (double)v.y * inv, ez = (double)v.z * inv,
+                             ew = (double)v.w * inv;
+                const __nv_bfloat162 lo = __floats2bfloat162_rn((float)ex, (float)ey);
+                const __nv_bfloat162 hi = __floats2bfloat162_rn((float)ez, (float)ew);
+                out[2 * c] = lo;
+                out[2 * c + 1] = hi;
+                const double dx = ex - (double)__low2float(lo), dy = ey - (double)__high2float(lo);
+                const double dz = ez - (double)__low2float(hi), dw = ew - (double)__high2float(hi);
+                res2 += dx * dx + dy * dy + dz * dz + dw * dw;
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) res2 += __shfl_xor_sync(0xffffffffu, res2, o);
         }
         // 4-norm of the normalised row (certificate bound of the bf16 filter, Options::bf16_eps)
         double s4 = 0.0;
@@ -86,6 +95,8 @@ ingest_kernel(const float* __restrict__ src, const int32_t* __restrict__ gid_src
         for (int o = 16; o > 0; o >>= 1) s4 += __shfl_xor_sync(0xffffffffu, s4, o);
         if (lane == 0) {
             atomicMax(maxnorm_bits + 1, __float_as_uint((float)sqrt(sqrt(s4))) + 1u);
+            // rounded up, and a hair more for the fp64 arithmetic above (positive floats order like their bits)
+            atomicMax(maxnorm_bits + 2, __float_as_uint(__double2float_ru(sqrt(res2) * (1.0 + 1e-9) + 1e-12)));
             inv_norm[dst] = (float)inv;
             norm[dst] = (float)nrm;
             live[dst] = 1.0f;
@@ -98,7 +109,7 @@ ingest_kernel(const float* __restrict__ src, const int32_t* __restrict__ gid_src
 
 __global__ void tombstone_kernel(const int64_t* __restrict__ rows, int64_t n, int64_t nrows,
                                  float* inv_norm, float* norm, float* live,
-                                 unsigned long long* newly_dead) {
+                                 unsigned long long* newly_dead, uint32_t* dead_blk) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int64_t r = rows[i];
@@ -110,6 +121,7 @@ __global__ void tombstone_kernel(const int64_t* __restrict__ rows, int64_t n, in
         inv_norm[r] = qnan;
         norm[r] = qnan;
         atomicAdd(newly_dead, 1ull);
+        atomicAdd(dead_blk + (r >> 8), 1u);
     }
 }
 
@@ -297,9 +309,12 @@ int cmw_store_create(int device, int dim, int64_t capacity_rows, uint32_t flags,
     if (!rc) rc = alloc((void**)&s->norm64, capacity_rows * sizeof(double));
     if (!rc) rc = alloc((void**)&s->kb_gid, capacity_rows * sizeof(int32_t));
     if (!rc) rc = alloc((void**)&s->maxnorm_bits, 256);
+    const size_t dead_blk_bytes = (size_t)(capacity_rows / 256 + 1) * sizeof(uint32_t);
+    if (!rc) rc = alloc((void**)&s->dead_blk, dead_blk_bytes);
     if (!rc) rc = ensure_stream(s);
     if (!rc) {
         cudaError_t e2 = cudaMemsetAsync(s->maxnorm_bits, 0, 256, s->stream);
+        if (e2 == cudaSuccess) e2 = cudaMemsetAsync(s->dead_blk, 0, dead_blk_bytes, s->stream);
         if (e2 == cudaSuccess) e2 = cudaMemsetAsync(s->inv_norm, 0xff, cap4 * sizeof(float), s->stream);
         if (e2 == cudaSuccess) e2 = cudaMemsetAsync(s->norm, 0xff, cap4 * sizeof(float), s->stream);
         if (e2 == cudaSuccess) e2 = cudaMemsetAsync(s->live, 0xff, cap4 * sizeof(float), s->stream);
@@ -349,6 +364,7 @@ int cmw_store_destroy(cmw_store* h) {
     cudaFree(s->norm64);
     cudaFree(s->kb_gid);
     cudaFree(s->maxnorm_bits);
+    cudaFree(s->dead_blk);
     cudaFree(s->dev_io);
     cudaFree(s->ws);
     if (s->pinned) cudaFreeHost(s->pinned);
@@ -456,13 +472,21 @@ int cmw_store_tombstone(cmw_store* h, const int64_t* rows_dev, int64_t n, void* 
     cudaStream_t st = (cudaStream_t)stream;
     CMW_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     tombstone_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows_dev, n, s->rows, s->inv_norm,
-                                                                 s->norm, s->live, counter);
+                                                                 s->norm, s->live, counter, s->dead_blk);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     unsigned long long host_count = 0;
     CMW_CUDA_OK(cudaMemcpyAsync(&host_count, counter, sizeof(host_count), cudaMemcpyDeviceToHost, st));
+    // where the dead rows are: per-block counts -> host prefix sums for the slab schedule (api.cu)
+    const size_t nblk = (size_t)(s->rows / 256 + 1);
+    std::vector<uint32_t> blk(nblk);
+    CMW_CUDA_OK(cudaMemcpyAsync(blk.data(), s->dead_blk, nblk * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CMW_CUDA_OK(cudaStreamSynchronize(st));
     s->dead += (int64_t)host_count;
+    if (s->dead > 0) {
+        s->dead_prefix.assign(nblk + 1, 0);
+        for (size_t i = 0; i < nblk; ++i) s->dead_prefix[i + 1] = s->dead_prefix[i] + (int64_t)blk[i];
+    }
     return 0;
 }
 

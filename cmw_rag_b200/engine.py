@@ -193,6 +193,43 @@ class DenseStore:
         )
         return (scores, ids, flags, s64) if return_scores64 else (scores, ids, flags)
 
+    # -- row-sharded search: the two halves of a search around the cross-shard exchange (sharded.py) -------
+    def search_filter(self, queries, k: int, metric="cosine", mode="f32", algo=None, ws_slot: int = 0):
+        """First half (prep + filter + compaction).  Returns the best k FILTER scores f32[B,k] of this
+        shard; the candidate pools stay in the workspace of ``ws_slot`` for :meth:`search_finish`."""
+        torch = _torch()
+        assert queries.is_cuda and queries.dtype == torch.float32 and queries.dim() == 2
+        q = queries.contiguous()
+        b = q.shape[0]
+        m = self._mode(mode, algo)
+        ftop = torch.empty((b, k), dtype=torch.float32, device=q.device)
+        if b:
+            ws = self._workspace(b, k, m, ws_slot)
+            N.check(N.lib().cmw_search_filter(self._h, q.data_ptr(), b, k, N.METRICS[metric], m, ftop.data_ptr(),
+                                              ws.data_ptr(), ws.numel(),
+                                              torch.cuda.current_stream(q.device).cuda_stream), "cmw_search_filter")
+        return ftop
+
+    def search_finish(self, queries, k: int, global_kth=None, metric="cosine", mode="f32", algo=None,
+                      ws_slot: int = 0, block=None):
+        """Second half: rescoring (restricted by the cross-shard k-th filter score ``global_kth`` f32[B] when
+        given) + selection into one packed uint8 block (cmw_shard_block_bytes) for the all-gather."""
+        torch = _torch()
+        q = queries.contiguous()
+        b = q.shape[0]
+        m = self._mode(mode, algo)
+        nbytes = int(N.lib().cmw_shard_block_bytes(max(b, 1), k))
+        if block is None:
+            block = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+        assert block.numel() >= nbytes and block.is_cuda
+        if b:
+            ws = self._workspace(b, k, m, ws_slot)
+            N.check(N.lib().cmw_search_finish(self._h, q.data_ptr(), b, k, N.METRICS[metric], m,
+                                              global_kth.data_ptr() if global_kth is not None else None,
+                                              block.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              torch.cuda.current_stream(q.device).cuda_stream), "cmw_search_finish")
+        return block
+
     def search_host(self, queries, k: int, metric="cosine", mode="f32", algo=None, out=None):
         """End-to-end form with HOST buffers (numpy in, numpy out): H2D, kernels, D2H, synchronised.
         This is the call that stands in for one HTTP round trip to Chroma.  Pageable arrays go through
@@ -340,3 +377,33 @@ def merge_topk(scores64, ids, k_out: int):
             "cmw_merge_topk",
         )
     return out_s, out_i, out_s64
+
+
+def shard_kth(filter_topk_gathered, k: int):
+    """f32[G,B,k] gathered per-shard filter scores -> f32[B]: the k-th best over all shards."""
+    torch = _torch()
+    t = filter_topk_gathered.contiguous()
+    g, b, kk = t.shape
+    assert kk == k and t.dtype == torch.float32 and t.is_cuda
+    out = torch.empty((b,), dtype=torch.float32, device=t.device)
+    if b:
+        N.check(N.lib().cmw_shard_kth(t.data_ptr(), g, b, k, out.data_ptr(),
+                                      torch.cuda.current_stream(t.device).cuda_stream), "cmw_shard_kth")
+    return out
+
+
+def shard_merge(blocks, world: int, batch: int, k: int, k_out: int | None = None):
+    """uint8[G * block_bytes] gathered shard blocks -> (scores f32[B,k_out], ids i64, scores64 f64, flags i32)."""
+    torch = _torch()
+    k_out = k if k_out is None else k_out
+    dev = blocks.device
+    out_s = torch.empty((batch, k_out), dtype=torch.float32, device=dev)
+    out_i = torch.empty((batch, k_out), dtype=torch.int64, device=dev)
+    out_s64 = torch.empty((batch, k_out), dtype=torch.float64, device=dev)
+    flags = torch.zeros((batch,), dtype=torch.int32, device=dev)
+    if batch:
+        assert blocks.numel() >= world * int(N.lib().cmw_shard_block_bytes(batch, k))
+        N.check(N.lib().cmw_shard_merge(blocks.data_ptr(), world, batch, k, k_out, out_s.data_ptr(), out_i.data_ptr(),
+                                        out_s64.data_ptr(), flags.data_ptr(),
+                                        torch.cuda.current_stream(dev).cuda_stream), "cmw_shard_merge")
+    return out_s, out_i, out_s64, flags

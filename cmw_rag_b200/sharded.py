@@ -77,8 +77,10 @@ class PeerExchange:
         self.epoch = 0
         dist.barrier(group=group)
 
-    def exchange_merge(self, s64, ids, k_out: int):
-        """s64 f64[B,k], ids i64[B,k] (CUDA, this rank's candidates) -> merged (scores f32, ids, scores64)."""
+    def exchange_merge(self, s64, ids, k_out: int, flags=None, timeout_ms: int = 0):
+        """s64 f64[B,k], ids i64[B,k] (CUDA, this rank's candidates; ``flags`` i32[B] = its search flags) ->
+        merged (scores f32, ids, scores64); with ``flags`` also the OR of every rank's flags, or
+        FLAG_PEER_TIMEOUT for all queries if a peer did not publish within the bounded wait."""
         import torch
 
         assert s64.is_cuda and s64.dtype == torch.float64 and ids.dtype == torch.int64 and s64.shape == ids.shape
@@ -90,13 +92,21 @@ class PeerExchange:
         out_s = torch.empty((b, k_out), dtype=torch.float32, device=dev)
         out_i = torch.empty((b, k_out), dtype=torch.int64, device=dev)
         out_s64 = torch.empty((b, k_out), dtype=torch.float64, device=dev)
+        out_f = torch.zeros((b,), dtype=torch.int32, device=dev) if flags is not None else None
+        if flags is not None:
+            flags = flags.to(torch.int32).contiguous()
         self.epoch += 1
         stream = torch.cuda.current_stream(dev).cuda_stream
         self._N.check(
-            self._N.lib().cmw_exchange_merge(self._ptrs, self.world, self.rank, self.max_batch, self.max_k, b, k,
-                                             k_out, self.epoch & 0xffffffff or 2, s64.data_ptr(), ids.data_ptr(),
-                                             out_s.data_ptr(), out_i.data_ptr(), out_s64.data_ptr(), stream),
-            "cmw_exchange_merge")
+            self._N.lib().cmw_exchange_merge_ex(self._ptrs, self.world, self.rank, self.max_batch, self.max_k, b, k,
+                                                k_out, self.epoch & 0xffffffff or 2, s64.data_ptr(), ids.data_ptr(),
+                                                flags.data_ptr() if flags is not None else None,
+                                                out_s.data_ptr(), out_i.data_ptr(), out_s64.data_ptr(),
+                                                out_f.data_ptr() if out_f is not None else None, int(timeout_ms),
+                                                stream),
+            "cmw_exchange_merge_ex")
+        if flags is not None:
+            return out_s, out_i, out_s64, out_f
         return out_s, out_i, out_s64
 
     def close(self):
@@ -114,9 +124,46 @@ class PeerExchange:
         self._own, self._opened = None, []
 
 
+class CudaShardBackend:
+    """The four device steps of the two-phase row-sharded search, as implemented by libcmwdense.so for one
+    ``DenseStore`` shard.  (A stand-in with the same four methods is what the gloo CPU tests inject.)"""
+
+    def __init__(self, store):
+        self.store = store
+
+    def filter(self, q, k, **kw):
+        return self.store.search_filter(q, k, **kw)
+
+    def kth(self, gathered, k):
+        from .engine import shard_kth
+
+        return shard_kth(gathered, k)
+
+    def finish(self, q, k, kth, **kw):
+        return self.store.search_finish(q, k, global_kth=kth, **kw)
+
+    def merge(self, blocks, world, batch, k):
+        from .engine import shard_merge
+
+        ms, mi, _, flags = shard_merge(blocks, world, batch, k)
+        return ms, mi, flags
+
+
 class ShardedSearcher:
+    """Search over a corpus row-sharded across the ranks of ``group``; every rank gets the global answer.
+
+    Default (a ``DenseStore`` shard, exact mode) -- the TWO-PHASE search: filter half on every shard, all-gather
+    of the shards' best k filter scores (``4 B k`` bytes per rank), the k-th best over all shards per query, then
+    the finish half: fp64 rescoring of only those local candidates that can still reach the global top-k, one
+    packed block per rank (scores, ids, certificate terms, flags) through a second all-gather, and the merge
+    kernel with the cross-shard certificate.  The rescoring -- the part of a search that does not shrink with the
+    shard -- is thereby shared between the ranks instead of repeated on each.
+    bf16 mode has nothing to rescore: one phase, one all-gather.
+    ``local_search`` / ``merge`` callables or a ``PeerExchange`` select the ONE-PHASE path: local top-k on
+    every rank, one packed exchange, merge."""
+
     def __init__(self, store=None, group=None, local_search: Callable | None = None,
-                 merge: Callable | None = None, exchange: PeerExchange | None = None):
+                 merge: Callable | None = None, exchange: PeerExchange | None = None, backend=None):
         import torch.distributed as dist
 
         self.dist = dist
@@ -124,46 +171,94 @@ class ShardedSearcher:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.store = store
-        if local_search is None:
+        self._one_phase = local_search is not None or merge is not None or exchange is not None
+        if backend is None and not self._one_phase:
             if store is None:
-                raise ValueError("ShardedSearcher needs a DenseStore or a local_search callable")
+                raise ValueError("ShardedSearcher needs a DenseStore, a backend or a local_search callable")
+            backend = CudaShardBackend(store)
+        self._backend = backend
+        if local_search is None and store is not None:
 
             def local_search(q, k, **kw):
                 sc, ids, flags, s64 = store.search(q, k, return_scores64=True, **kw)
                 return s64, ids, flags
 
-        if merge is None:
+        if merge is None and self._one_phase:
             from .engine import merge_topk as merge
         self._local_search = local_search
         self._merge = merge
         self._exchange = exchange
+        self.timings = None  # set to {} to collect CUDA-event pairs per phase (bench.py)
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def _all_gather(self, t):
+        import torch
+
+        out = torch.empty((self.world * t.numel(),), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t.contiguous().view(-1), group=self.group)
+        return out
+
+    def _mark(self, name):
+        """bench.py instrumentation: a CUDA event on the current stream at a phase boundary."""
+        if self.timings is None:
+            return
+        import torch
+
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.timings.setdefault(name, []).append(ev)
 
     def search(self, queries, k: int, **kw):
-        """queries [B, dim] (replicated on every rank) -> (scores f32[B,k], ids i64[B,k], flags),
+        """queries [B, dim] (replicated on every rank) -> (scores f32[B,k], ids i64[B,k], flags i32[B]),
         identical on every rank."""
+        if self._one_phase or self._backend is None:
+            return self._search_one_phase(queries, k, **kw)
+        return self._search_two_phase(queries, k, **kw)
+
+    def _search_two_phase(self, queries, k: int, **kw):
+        be = self._backend
+        b = queries.shape[0]
+        exact = kw.get("mode", "f32") in ("f32", "exact", 0)
+        self._mark("start")
+        ftop = be.filter(queries, k, **kw)
+        self._mark("filter_done")
+        kth = None
+        if exact and self.world > 1:
+            g_ftop = self._all_gather(ftop).view(self.world, b, k)  # rank-major == a [world, B, k] stack
+            self._mark("gather1_done")
+            kth = be.kth(g_ftop, k)
+        else:
+            self._mark("gather1_done")
+        self._mark("kth_done")
+        block = be.finish(queries, k, kth, **kw)
+        self._mark("finish_done")
+        blocks = self._all_gather(block) if self.world > 1 else block
+        self._mark("gather2_done")
+        out = be.merge(blocks, self.world, b, k)
+        self._mark("merge_done")
+        return out
+
+    def _search_one_phase(self, queries, k: int, **kw):
         import torch
 
         s64, ids, flags = self._local_search(queries, k, **kw)
         if self.world == 1:
             ms, mi, _ = self._merge(s64.unsqueeze(0), ids.unsqueeze(0), k)
             return ms, mi, flags
-        if self._exchange is not None:
-            # fused path: peer stores over NVLink + flag-wait + merge, no collective call
-            if flags is not None:
-                flags = flags.clone()
-                self.dist.all_reduce(flags, op=self.dist.ReduceOp.MAX, group=self.group)
-            ms, mi, _ = self._exchange.exchange_merge(s64, ids, k)
-            return ms, mi, flags
         b, kk = s64.shape
-        # rank-major concatenation along dim 0 == a [world, B, k] stack
-        g_s = torch.empty((self.world * b, kk), dtype=s64.dtype, device=s64.device)
-        g_i = torch.empty((self.world * b, kk), dtype=ids.dtype, device=ids.device)
-        self.dist.all_gather_into_tensor(g_s, s64.contiguous(), group=self.group)
-        self.dist.all_gather_into_tensor(g_i, ids.contiguous(), group=self.group)
-        g_s = g_s.view(self.world, b, kk)
-        g_i = g_i.view(self.world, b, kk)
-        if flags is not None:
-            flags = flags.clone()
-            self.dist.all_reduce(flags, op=self.dist.ReduceOp.MAX, group=self.group)
+        if flags is None:
+            flags = torch.zeros((b,), dtype=torch.int32, device=s64.device)
+        if self._exchange is not None:
+            # fused path: peer stores over NVLink + bounded flag-wait + merge; the shards' own flags travel with
+            # the candidates, so no collective call is left on the data path
+            ms, mi, _, fl = self._exchange.exchange_merge(s64, ids, k, flags=flags)
+            return ms, mi, fl
+        # ONE packed all-gather: [B, 2k+1] x 8 bytes = f64 scores | i64 ids (bit-cast) | flags
+        packed = torch.cat([s64.contiguous(), ids.contiguous().view(torch.float64),
+                            flags.to(torch.float64).view(b, 1)], dim=1)
+        g = self._all_gather(packed).view(self.world, b, 2 * kk + 1)
+        g_s = g[:, :, :kk].contiguous()
+        g_i = g[:, :, kk:2 * kk].contiguous().view(torch.int64)
+        flags = g[:, :, 2 * kk].max(dim=0).values.to(torch.int32)
         ms, mi, _ = self._merge(g_s, g_i, k)
         return ms, mi, flags

@@ -20,6 +20,7 @@ Additions over the reference surface: ``search`` (batched, returns ids + scores)
 from __future__ import annotations
 
 import asyncio
+import logging
 import threading
 import uuid
 from dataclasses import dataclass
@@ -29,6 +30,9 @@ import numpy as np
 
 from .engine import DenseStore
 from .kbid import group_key
+
+
+log = logging.getLogger("cmw_rag_b200.store")
 
 
 @dataclass
@@ -117,7 +121,7 @@ class B200Store:
 
         self._executor = concurrent.futures.ThreadPoolExecutor(max_workers=2, thread_name_prefix="b200store")
         self._flush_scheduled = False
-        self.stats = {"searches": 0, "launch_batches": 0, "max_batch": 0}
+        self.stats = {"searches": 0, "launch_batches": 0, "max_batch": 0, "uncertified": 0}
 
     # -- plumbing -----------------------------------------------------------------------------
     def _ensure(self, dim: int) -> DenseStore:
@@ -359,8 +363,21 @@ class B200Store:
                         np.zeros((b,), np.int32))
             if q.shape[1] != self._dim:
                 raise ValueError(f"query dimension {q.shape[1]} does not match the collection's {self._dim}")
-            return self._dense.search_host(self._pad(q), k, metric=self.metric, mode=mode or self.mode,
-                                           algo=algo)
+            out = self._dense.search_host(self._pad(q), k, metric=self.metric, mode=mode or self.mode,
+                                          algo=algo)
+        self._note_flags(out[2])
+        return out
+
+    def _note_flags(self, flags) -> None:
+        """A query still flagged after the library's repair chain (in practice: more exact duplicates of a
+        top-k chunk than the candidate set holds) is answered with the best candidates found, but it is not
+        PROVEN identical to the exact answer: count it and say so -- never pass it on silently."""
+        bad = int(np.count_nonzero(flags))
+        if bad:
+            self.stats["uncertified"] += bad
+            log.warning("B200Store[%s]: %d of %d queries came back CMW_FLAG_UNCERTIFIED after the repair chain "
+                        "(candidate pool overflow or unbreakable ties); results are the best rescored candidates",
+                        self.collection_name, bad, len(flags))
 
     def _docs_for(self, ids_row: np.ndarray) -> list[RetrievedDoc]:
         out = []
@@ -380,12 +397,14 @@ class B200Store:
         res: dict[str, Any] = {"ids": [], "documents": None, "metadatas": None, "distances": None}
         docs, metas, dists = [], [], []
         for b in range(ids.shape[0]):
-            rows = [int(g) - self._id_offset for g in ids[b] if g >= 0]
-            rows = [r for r in rows if 0 <= r < len(self._ids) and self._alive[r]]
+            # ids and distances are filtered by the SAME list of kept slots, so they always line up
+            kept = [j for j, g in enumerate(ids[b].tolist())
+                    if g >= 0 and 0 <= g - self._id_offset < len(self._ids) and self._alive[g - self._id_offset]]
+            rows = [int(ids[b, j]) - self._id_offset for j in kept]
             res["ids"].append([self._ids[r] for r in rows])
             docs.append([self._docs[r] for r in rows])
             metas.append([dict(self._metas[r] or {}) for r in rows])
-            dists.append([float(1.0 - s) for s, g in zip(scores[b], ids[b]) if g >= 0][: len(rows)])
+            dists.append([float(1.0 - scores[b, j]) for j in kept])
         if "documents" in include:
             res["documents"] = docs
         if "metadatas" in include:
@@ -517,9 +536,24 @@ class B200Store:
                 raise RuntimeError("empty collection")
             dev = torch.device(f"cuda:{self._device}")
             t = torch.from_numpy(seg).to(dev)
-            res, scores, ids, _ = self._dense.search_multivector(t, k, prl=prl, limit=limit,
-                                                                 metric=self.metric, mode=self.mode)
+            res, scores, ids, flags = self._dense.search_multivector(t, k, prl=prl, limit=limit,
+                                                                     metric=self.metric, mode=self.mode)
             torch.cuda.synchronize(dev)
+            flags = flags.cpu().numpy().ravel()
+            if flags.any():
+                # the device path has no repair chain: re-run the flagged segments through the host API (which
+                # has), then redo the reduction on the repaired per-segment lists
+                qn, sn, _ = seg.shape
+                bad = np.flatnonzero(flags)
+                sc_r, ids_r, fl_r = self._dense.search_host(self._pad(seg.reshape(qn * sn, -1)[bad]), k,
+                                                            metric=self.metric, mode=self.mode)
+                ids2, sc2 = ids.reshape(qn * sn, k).clone(), scores.reshape(qn * sn, k).clone()
+                ids2[torch.from_numpy(bad).to(dev)] = torch.from_numpy(ids_r).to(dev)
+                sc2[torch.from_numpy(bad).to(dev)] = torch.from_numpy(sc_r).to(dev)
+                ids, scores = ids2.view(qn, sn, k), sc2.view(qn, sn, k)
+                res = self._dense.multivector(ids, scores, prl=prl, limit=limit)
+                torch.cuda.synchronize(dev)
+                self._note_flags(fl_r)
             return res.cpu(), ids.cpu().numpy(), scores.cpu().numpy()
 
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CMW_ABI_VERSION 4
+#define CMW_ABI_VERSION 5
 
 /* metric -- rag_engine/storage/vector_store.py:48-51 fixes the collection to cosine
  * ({"hnsw:space": "cosine"}); inner product is the north star's second metric. */
@@ -37,11 +37,20 @@ extern "C" {
 #define CMW_METRIC_IP 1
 
 /* search mode */
-#define CMW_MODE_F32_EXACT 0 /* ids identical to the exact fp64 oracle (ties -> lower id); fp64-accumulated scores */
+/* F32_EXACT: fp64-accumulated scores from the fp32 rows; a query whose out_flags entry is 0 carries a PROOF that
+ * its ids are those of the exact fp64 oracle (ties -> lower id): every row that was not rescored has a filter
+ * score which, plus a rigorous bound on the filter's error, stays below the k-th exact score.  The bound behind
+ * the bf16 tensor-core filter is r_q + (1 + r_q) R_c + D 2^-23 (rounding residual of the query tile, largest
+ * rounding residual of any stored row, fp32 accumulation), both residuals measured from the values actually
+ * written; behind the fp32 scan filter it is (D/32 + 12) 2^-24.  A query the proof fails for is flagged
+ * CMW_FLAG_UNCERTIFIED (its ids are still the best of the candidates that were rescored); cmw_search_host
+ * re-runs flagged queries through wider / more precise filters by itself.  cmw_set_option("strict_certificate", 0)
+ * trades the proof for a statistical bound (independent roundings, 8 sigma) and ~4 % more throughput. */
+#define CMW_MODE_F32_EXACT 0
 #define CMW_MODE_BF16 1      /* bf16 operands, fp32 accumulation; approximate (reported as recall@k) */
 /* optional algorithm override, OR-ed into `mode` (default: chosen from the batch size) */
 #define CMW_ALGO_AUTO (0 << 8)
-#define CMW_ALGO_SCAN (1 << 8) /* K1: TMA-staged streaming dot product, 1-2 queries per pass (HBM-bound);
+#define CMW_ALGO_SCAN (1 << 8) /* K1: TMA-staged streaming dot product, 1-4 queries per pass (HBM-bound);
                                   F32_EXACT scans the fp32 tiles, BF16 the bf16 tiles */
 #define CMW_ALGO_GEMM (2 << 8) /* K2: tcgen05/TMEM GEMM with fused top-k epilogue */
 /* slab schedule override, OR-ed into `mode`: fixed slabs small enough that the candidate pool can
@@ -55,7 +64,16 @@ extern "C" {
 #define CMW_STORE_BF16 2u /* keep row-major bf16 tiles of the L2-normalised rows */
 
 /* per-query flags written by cmw_search (out_flags) */
-#define CMW_FLAG_UNCERTIFIED 1 /* F32_EXACT only: the exactness certificate could not be established */
+#define CMW_FLAG_UNCERTIFIED 1 /* the exactness certificate could not be established, or a candidate pool overflowed */
+#define CMW_FLAG_PEER_TIMEOUT 2 /* cmw_exchange_merge: a peer never published its candidates (results invalid) */
+
+/* limits (checked, not silent): k <= CMW_MAX_K; cmw_multivector S*k <= CMW_MAX_MULTIVECTOR_ENTRIES;
+ * cmw_merge_topk / cmw_shard_merge / cmw_exchange_merge G*k <= CMW_MAX_MERGE_ENTRIES.  k above ~330 cannot be
+ * certified behind the bf16 filter (its candidate set K' = max(k + 108, 3k + 20) is capped at 1024): those
+ * queries come back flagged from cmw_search and are repaired through the fp32 scan by cmw_search_host. */
+#define CMW_MAX_K 1024
+#define CMW_MAX_MULTIVECTOR_ENTRIES 2048
+#define CMW_MAX_MERGE_ENTRIES 8192
 
 typedef struct cmw_store cmw_store;
 
@@ -154,6 +172,30 @@ int cmw_merge_topk(const double* scores_dev, const int64_t* ids_dev, int G, int 
                    int k_out, float* out_scores_dev, int64_t* out_ids_dev,
                    double* out_scores64_dev, void* stream);
 
+/* ---- row-sharded search: cmw_search cut in two around ONE small exchange, so that the fp64
+ * rescoring -- the part of a search that does not shrink with the shard -- is shared between the shards instead of
+ * repeated on each.  Every rank holds a row shard (store with id_offset = its first row) and the same queries:
+ *   1. cmw_search_filter   prep + filter + compaction; out_filter_topk f32 [batch,k] = the best k FILTER scores
+ *   2. all-gather 1        [G,batch,k] f32                                  (NCCL, or any transport)
+ *   3. cmw_shard_kth       k-th best filter score over all shards, per query -> global_kth f32 [batch]
+ *   4. cmw_search_finish   rescoring of the local candidates that can still reach the GLOBAL top-k (filter score
+ *                          >= global_kth - 2 eps), selection; writes one packed block of cmw_shard_block_bytes:
+ *                          f64 scores [batch,k] | i64 ids [batch,k] | f64 {t, eps} [batch,2] | i32 flags [batch]
+ *   5. all-gather 2        G blocks
+ *   6. cmw_shard_merge     G*k -> k_out by (score desc, id asc) + the cross-shard certificate
+ *                          (k-th merged exact score > max over shards of t + eps)
+ * global_kth_dev may be NULL (each shard then uses its own k-th: steps 2-3 skipped; CMW_MODE_BF16 always does).
+ * filter and finish take the SAME queries / batch / k / metric / mode / workspace; nothing else may use that
+ * workspace in between.  The reference has no counterpart (one Chroma server: vector_store.py:34-42). */
+int cmw_search_filter(cmw_store* s, const float* queries_dev, int batch, int k, int metric, int mode,
+                      float* out_filter_topk_dev, void* ws_dev, size_t ws_bytes, void* stream);
+int cmw_shard_kth(const float* filter_topk_gathered_dev, int G, int B, int k, float* out_kth_dev, void* stream);
+size_t cmw_shard_block_bytes(int batch, int k);
+int cmw_search_finish(cmw_store* s, const float* queries_dev, int batch, int k, int metric, int mode,
+                      const float* global_kth_dev, void* block_dev, void* ws_dev, size_t ws_bytes, void* stream);
+int cmw_shard_merge(const void* blocks_dev, int G, int B, int k, int k_out, float* out_scores_dev,
+                    int64_t* out_ids_dev, double* out_scores64_dev, int32_t* out_flags_dev, void* stream);
+
 /* ---- fused exchange + merge over NVLink peer memory (alternative to all-gather + cmw_merge_topk).
  * Every rank allocates one peer buffer (cmw_peer_alloc: cudaMalloc + cudaIpc handle, zero-initialised,
  * cmw_peer_buffer_bytes bytes), exchanges the 64-byte handles out of band (torch.distributed, MPI, a
@@ -171,6 +213,14 @@ int cmw_peer_free(void* dev_ptr);
 int cmw_exchange_merge(void* const* peer_bufs_host, int G, int rank, int max_batch, int max_k, int B, int k,
                        int k_out, uint32_t epoch, const double* scores64_local_dev, const int64_t* ids_local_dev,
                        float* out_scores_dev, int64_t* out_ids_dev, double* out_scores64_dev, void* stream);
+/* Same, with per-query status.  flags_local_dev i32 [B] (may be NULL): this shard's own search flags, which travel
+ * with the candidates; out_flags_dev i32 [B] (may be NULL) = their OR over all shards, or CMW_FLAG_PEER_TIMEOUT for
+ * every query when a peer's flag did not arrive within `timeout_ms` (0 = the default, 2000 ms; the wait is bounded
+ * so that a dead or out-of-step peer cannot hang this GPU) or when a peer published a different (B, k). */
+int cmw_exchange_merge_ex(void* const* peer_bufs_host, int G, int rank, int max_batch, int max_k, int B, int k,
+                          int k_out, uint32_t epoch, const double* scores64_local_dev, const int64_t* ids_local_dev,
+                          const int32_t* flags_local_dev, float* out_scores_dev, int64_t* out_ids_dev,
+                          double* out_scores64_dev, int32_t* out_flags_dev, int timeout_ms, void* stream);
 
 /* ---- instrumentation ---- */
 /* number of kernels this library has launched since load (all stores, all streams) */
@@ -179,15 +229,17 @@ int64_t cmw_kernel_launches(void);
  * CUDA events on the caller's stream.  cmw_profile_read synchronises those events and returns the
  * accumulated milliseconds since the last enable/read: ms[0] = filter kernels (K1 scan / K2 GEMM),
  * ms[1] = pool compaction, ms[2] = finalisation (K3 rescoring + select, or emit), ms[3] = query
- * preparation; counts[i] = kernels launched in that phase.  n = array length (<= 4). */
+ * preparation, ms[4] = cmw_shard_kth, ms[5] = cmw_shard_merge; counts[i] = kernels launched in that phase.
+ * n = array length (<= 6). */
 int cmw_profile_enable(int on);
 int cmw_profile_read(double* ms, int64_t* counts, int n);
 /* Process-wide tunables (defaults in parentheses):
  *   "scan_max_batch" (0)      batches up to this size use K1 (scan), larger ones K2 (GEMM)
  *   "gemm_enabled" (1), "gemm_2cta" (1), "gemm_2cta_min_batch" (128), "gemm_clc" (1)   K2 kernel selection
  *   "kprime" (0 = automatic)  candidates kept per query between slabs and handed to K3
- *   "bf16_eps" (0 = automatic, dimension-aware), "bf16_sigmas" (8), "f32_eps" (4e-6)   certificate bounds
- *   "strict_certificate" (0)  1 = rigorous Cauchy-Schwarz bound behind the bf16 filter (K' = max(512, 4k))
+ *   "strict_certificate" (1)  1 = rigorous residual bound behind the bf16 filter (K' = max(k + 108, 3k + 20));
+ *                             0 = statistical bound, bf16_sigmas x sigma with u = 2^-8 (K' = max(k + 64, 2k))
+ *   "bf16_eps" (0 = from the bound above), "bf16_sigmas" (8), "f32_eps" (0 = (D/32 + 12) 2^-24)   certificate bounds
  *   "repair" (2)              cmw_search_host repair chain for flagged queries: 0 off, 1 stage 1, 2 both stages
  *   "wide_dense" (1)          batches up to 32: 65536-row first slab through a scratch matrix, then the rest of
  *                             the corpus in one launch when the expected admissions fit the pool

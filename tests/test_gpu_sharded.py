@@ -18,6 +18,7 @@ import numpy as np, torch, torch.distributed as dist
 import synth
 from oracle.cport import exact_topk_c
 from cmw_rag_b200 import DenseStore
+from cmw_rag_b200 import _native as N
 from cmw_rag_b200.sharded import PeerExchange, ShardedSearcher, shard_bounds
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 dev = torch.device(f"cuda:{{local}}"); torch.cuda.set_device(dev)
@@ -25,32 +26,64 @@ dist.init_process_group("nccl", device_id=dev)
 n, d, k = 30011, 256, 50
 c = synth.make_corpus(n, d, seed=4)
 q, _ = synth.make_queries(c, 37, seed=5)
-lo, hi = shard_bounds(n, world)[rank]
+bounds = shard_bounds(n, world)
+# SURVEY 8e verification list: a needle in every shard (query g is planted on a row of shard g)
+for g, (glo, ghi) in enumerate(bounds):
+    if ghi > glo and g < q.shape[0] - 2:
+        v = c[glo + (ghi - glo) // 3] + 0.3 * q[g + 2]
+        q[g + 2] = v / np.linalg.norm(v)
+lo, hi = bounds[rank]
 st = DenseStore(d, max(1, hi - lo), device=local, id_offset=lo)
 st.append(c[lo:hi])
-s = ShardedSearcher(st)
+s = ShardedSearcher(st)                      # two-phase: filter | gather | global k-th | finish | gather | merge
+one = ShardedSearcher(st, merge=None, local_search=lambda qq, kk, **kw: (lambda r: (r[3], r[1], r[2]))(
+    st.search(qq, kk, return_scores64=True, **kw)))   # one-phase: independent local top-k, then the merge kernel
 qd = torch.from_numpy(q).to(dev)
 ref_ids, ref_sc, _ = exact_topk_c(c, q, k)
+for g, (glo, ghi) in enumerate(bounds):
+    if ghi > glo and g < q.shape[0] - 2:
+        assert ref_ids[g + 2, 0] == glo + (ghi - glo) // 3
 for mode in ("f32", "bf16"):
     ms, mi, fl = s.search(qd, k, mode=mode)
+    os_, oi, ofl = one.search(qd, k, mode=mode)
     torch.cuda.synchronize()
     if mode == "f32":
         assert (mi.cpu().numpy() == ref_ids).all(), rank
         assert np.abs(ms.cpu().numpy() - ref_sc).max() <= 1e-5
-        assert int(fl.sum()) == 0
+        assert int(fl.sum()) == 0 and int(ofl.sum()) == 0
+        # the sharded answer equals the merge of independent single-GPU runs over the same shards
+        assert torch.equal(mi, oi) and torch.equal(ms, os_), rank
     else:
         rec = np.mean([len(set(mi[b].tolist()) & set(ref_ids[b])) / k for b in range(37)])
         assert rec >= 0.95, rec
+        assert torch.equal(mi, oi)
+# a failed certificate on ONE shard must flag the merged answer on EVERY rank (and never pass silently)
+old = N.get_option("bf16_eps")
+N.set_option("bf16_eps", 0.5)
+_, _, fl = s.search(qd, k, mode="f32", algo="gemm")
+torch.cuda.synchronize()
+N.set_option("bf16_eps", old)
+assert int(fl.sum()) == q.shape[0], (rank, int(fl.sum()))
 # the fused NVLink peer-memory exchange must give the same answer as all-gather + merge, call after call
 ex = PeerExchange(device=local, max_batch=64, max_k=64)
 fused = ShardedSearcher(st, exchange=ex)
 for it in range(5):
     qi = torch.from_numpy(np.roll(q, it, axis=0).copy()).to(dev)
-    a_s, a_i, _ = s.search(qi, k, mode="f32")
-    b_s, b_i, _ = fused.search(qi, k, mode="f32")
+    a_s, a_i, a_f = s.search(qi, k, mode="f32")
+    b_s, b_i, b_f = fused.search(qi, k, mode="f32")
     torch.cuda.synchronize()
     assert torch.equal(a_i, b_i) and torch.equal(a_s, b_s), (rank, it)
+    assert int(b_f.sum()) == 0
 assert (b_i.cpu().numpy() == np.roll(ref_ids, 4, axis=0)).all()
+if world > 1:
+    # a peer that never shows up: the merge kernel's wait is bounded and reports CMW_FLAG_PEER_TIMEOUT
+    dist.barrier()
+    if rank == 0:
+        s64 = torch.zeros((4, 8), dtype=torch.float64, device=dev); ii = torch.zeros((4, 8), dtype=torch.int64, device=dev)
+        _, t_i, _, t_f = ex.exchange_merge(s64, ii, 8, flags=torch.zeros(4, dtype=torch.int32, device=dev), timeout_ms=100)
+        torch.cuda.synchronize()
+        assert (t_f.cpu().numpy() == N.FLAG_PEER_TIMEOUT).all() and (t_i.cpu().numpy() == -1).all()
+    dist.barrier()
 ex.close()
 dist.barrier(); dist.destroy_process_group()
 print("sharded ok", rank, world)
@@ -58,16 +91,16 @@ print("sharded ok", rank, world)
 
 
 def test_sharded_searcher_nccl(tmp_path):
+    """Every visible GPU is a rank (the driver's 8-GPU box runs this at world 8; a 1-GPU box at world 1)."""
     import torch
 
-    ngpu = torch.cuda.device_count()
-    world = 2 if ngpu >= 2 else 1
+    world = max(1, min(8, torch.cuda.device_count()))
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT))
     res = subprocess.run(
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
          "--master-addr", "127.0.0.1", "--master-port", "29547", str(script)],
-        capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+        capture_output=True, text=True, timeout=900, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert res.stdout.count("sharded ok") == world
 

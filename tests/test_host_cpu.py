@@ -355,6 +355,81 @@ def test_sharded_search_world_size_2_gloo(tmp_path):
     assert res.stdout.count("ok") == 2
 
 
+_GLOO_TWO_PHASE_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import synth
+from oracle import exact_topk, exact_scores, merge_topk
+from cmw_rag_b200.sharded import ShardedSearcher, shard_bounds
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n, d, k = 1501, 32, 12
+c = synth.make_corpus(n, d, seed=1)
+q, _ = synth.make_queries(c, 9, seed=2)
+lo, hi = shard_bounds(n, world)[rank]
+EPS = 1e-3
+
+class OracleBackend:
+    # the four device steps of the two-phase search, restated with the oracle (test stand-in for the kernels)
+    def __init__(self):
+        self.rescored = 0
+    def filter(self, qt, k, **kw):
+        self.s = exact_scores(c[lo:hi], qt.numpy())                       # [B, n_local] fp64
+        top = -np.sort(-self.s, axis=1)[:, :k]
+        return torch.from_numpy(top.astype(np.float32))
+    def kth(self, gathered, k):
+        g = gathered.numpy()                                               # [G, B, k]
+        assert g.shape == (world, q.shape[0], k)
+        flat = np.transpose(g, (1, 0, 2)).reshape(g.shape[1], -1)
+        return torch.from_numpy(-np.sort(-flat, axis=1)[:, k - 1].copy())
+    def finish(self, qt, k, kth, **kw):
+        b = qt.shape[0]
+        block = np.full((b, 2 * k + 1), -np.inf)
+        ids = np.full((b, k), -1, np.int64)
+        for i in range(b):
+            cut = float(kth[i]) - 2 * EPS if kth is not None else -np.inf
+            cand = np.flatnonzero(self.s[i] >= cut)
+            self.rescored += cand.size
+            order = cand[np.lexsort((cand, -self.s[i][cand]))][:k]
+            block[i, : order.size] = self.s[i][order]
+            ids[i, : order.size] = order + lo
+        block[:, k:2 * k] = ids.view(np.float64)
+        block[:, 2 * k] = 0.0
+        return torch.from_numpy(block.reshape(-1))
+    def merge(self, blocks, w, b, k):
+        g = blocks.numpy().reshape(w, b, 2 * k + 1)
+        mi, ms = merge_topk(np.ascontiguousarray(g[:, :, k:2 * k]).view(np.int64), np.ascontiguousarray(g[:, :, :k]), k)
+        return torch.from_numpy(ms), torch.from_numpy(mi), torch.zeros(b, dtype=torch.int32)
+
+be = OracleBackend()
+s = ShardedSearcher(backend=be)
+ms, mi, fl = s.search(torch.from_numpy(q), k)
+gi, gs, _ = exact_topk(c, q, k)
+assert (mi.numpy() == gi).all(), (rank, mi, gi)
+assert np.abs(ms.numpy() - gs).max() == 0.0
+# the point of the exchange: the shards together rescore little more than ONE shard's worth of candidates
+t = torch.tensor([be.rescored], dtype=torch.int64); dist.all_reduce(t)
+assert int(t) < 3 * k * q.shape[0], int(t)
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_sharded_two_phase_search_world_size_2_gloo(tmp_path):
+    """Host logic of the two-phase row-sharded search (filter | all-gather | global k-th | finish | all-gather |
+    merge) under gloo on CPU, the oracle standing in for the four device steps."""
+    script = tmp_path / "worker2.py"
+    script.write_text(_GLOO_TWO_PHASE_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    res = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", "29543", str(script)],
+        capture_output=True, text=True, timeout=300, env=env)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert res.stdout.count("ok") == 2
+
+
 def test_reference_arm_json_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on a tiny corpus: one JSON line with
     the contract's keys, rank 0 only."""
