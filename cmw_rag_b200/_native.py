@@ -24,6 +24,7 @@ SLABS_SAFE = 1 << 16
 KPRIME_MAX = 1 << 17
 STORE_F32 = 1
 STORE_BF16 = 2
+STORE_F16 = 4
 FLAG_UNCERTIFIED = 1
 FLAG_PEER_TIMEOUT = 2
 HOST_SLOTS = 4

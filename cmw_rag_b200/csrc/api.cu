@@ -77,12 +77,13 @@ static bool use_gemm(const Store* s, const Options& opt, int batch, int mode) {
 // K': candidates kept per query between slabs and handed to K3.  The certificate needs the K'-th best filter
 // score to lie more than eps below the k-th exact score, so K' follows the bound in use:
 //   fp32 scan filter (eps ~ 3.6e-6): k + 28;
-//   bf16 tensor-core filter, statistical bound (eps ~ 8.6e-4 at D = 1536): max(k + 64, 2k);
-//   bf16 tensor-core filter, rigorous bound (eps ~ 3.5e-3): max(k + 108, 3k + 20) -- at 1M iid rows the k-th and
-//   the K'-th score are then ~7.8e-3 apart for k = 100 (5 standard deviations of the order statistics over eps).
-// k above ~330 cannot be certified behind the bf16 filter (K' is capped at 1024): such queries are flagged and the
-// host API repairs them through the fp32 scan.
-static int pick_kprime(const Options& opt, int k, int mode, bool gemm) {
+//   fp16 tiles, rigorous bound (eps ~ 6.5e-4 at D = 1536), and either format with the statistical bound
+//   (eps ~ 8.6e-4 for bf16): max(k + 64, 2k);
+//   bf16 tiles, rigorous bound (eps ~ 3.5e-3): max(k + 108, 3k + 20) -- at 1M iid rows the k-th and the K'-th
+//   score are then ~7.8e-3 apart for k = 100 (5 standard deviations of the order statistics over eps).
+// k above ~330 (bf16 tiles) / ~500 (fp16) cannot be certified behind the tensor-core filter (K' is capped at
+// 1024): such queries are flagged and the host API repairs them through the fp32 scan.
+static int pick_kprime(const Options& opt, int k, int mode, bool gemm, bool half_tiles) {
     int kp;
     if (mode & CMW_KPRIME_MAX) {
         kp = kMaxKPrime;
@@ -90,7 +91,7 @@ static int pick_kprime(const Options& opt, int k, int mode, bool gemm) {
         kp = (int)opt.kprime;
     } else if ((mode & 0xff) == CMW_MODE_BF16) {
         kp = k;
-    } else if (gemm && opt.strict_certificate != 0 && opt.bf16_eps <= 0) {
+    } else if (gemm && opt.strict_certificate != 0 && opt.bf16_eps <= 0 && !half_tiles) {
         kp = (3 * k + 20 > k + 108) ? 3 * k + 20 : k + 108;
     } else if (gemm) {
         kp = (k + 64 > 2 * k) ? k + 64 : 2 * k;
@@ -373,7 +374,7 @@ static int make_plan(SearchPlan& pl, cmw_store* h, const float* queries_dev, int
     if (base_mode == CMW_MODE_F32_EXACT)
         CMW_REQUIRE(s->f32 != nullptr, "%s: CMW_MODE_F32_EXACT needs a CMW_STORE_F32 store", who);
     if (base_mode == CMW_MODE_BF16)
-        CMW_REQUIRE(s->bf16 != nullptr, "%s: CMW_MODE_BF16 needs a CMW_STORE_BF16 store", who);
+        CMW_REQUIRE(s->bf16 != nullptr, "%s: CMW_MODE_BF16 needs a store with 16-bit tiles (CMW_STORE_BF16 / _F16)", who);
     CMW_CUDA_OK(cudaSetDevice(s->device));
     pl.s = s;
     pl.opt = g_opt;
@@ -386,7 +387,7 @@ static int make_plan(SearchPlan& pl, cmw_store* h, const float* queries_dev, int
     if ((mode & 0xff00) == CMW_ALGO_GEMM)
         CMW_REQUIRE(pl.gemm, "%s: CMW_ALGO_GEMM requested but the tcgen05 path is unavailable "
                              "(store without bf16 tiles or TMA descriptor)", who);
-    pl.kprime = pick_kprime(pl.opt, k, mode, pl.gemm);
+    pl.kprime = pick_kprime(pl.opt, k, mode, pl.gemm, s->half_tiles);
     pl.w = ws_layout(s->dim, batch, pl.kprime);
     CMW_REQUIRE(ws_dev != nullptr && ws_bytes >= pl.w.total, "%s: workspace too small (%zu bytes given, %zu needed)",
                 who, ws_bytes, pl.w.total);
@@ -477,8 +478,8 @@ static int run_filter_half(const SearchPlan& pl, const float* queries_dev, cudaS
     {
         PhaseTimer t(3, stream);
         if ((rc = launch_prep_queries(queries_dev, batch, w.bpad, s->dim, metric, pl.qn64, pl.q4, pl.qres, pl.q_f32,
-                                      gemm ? pl.q_bf16 : nullptr, pool, wide ? 0 : (int)slab0, seg, (int)slab0,
-                                      stream)))
+                                      gemm ? pl.q_bf16 : nullptr, s->half_tiles ? 1 : 0, pool, wide ? 0 : (int)slab0,
+                                      seg, (int)slab0, stream)))
             return rc;
     }
 
@@ -512,6 +513,7 @@ static int run_filter_half(const SearchPlan& pl, const float* queries_dev, cudaS
             ScanArgs a;
             a.rows = tiles;
             a.elt_bytes = filter_bf16 ? 2 : 4;
+            a.half_tiles = s->half_tiles ? 1 : 0;
             a.dim = s->dim;
             a.row_mul = row_mul;
             a.row_begin = r0;
@@ -605,6 +607,7 @@ static CertParams make_cert(const SearchPlan& pl, const float* global_kth) {
     cert.eps_fixed = opt.f32_eps > 0 ? opt.f32_eps : (double)(pl.s->dim / 32 + 12) * 5.9604644775390625e-8;
     cert.sigmas = 0.0;
     cert.acc_slack = (double)pl.s->dim * 1.1920928955078125e-7 * 1.01;  // D * 2^-23
+    cert.tile_u = pl.s->half_tiles ? 1.0 / 2048.0 : 1.0 / 256.0;
     if (pl.gemm) {
         if (opt.bf16_eps > 0) {
             cert.eps_fixed = opt.bf16_eps;
@@ -634,8 +637,8 @@ static int run_finish_half(const SearchPlan& pl, const float* queries_dev, const
                                      out_scores_dev, out_ids_dev, out_scores64_dev, out_flags_dev, out_aux_dev,
                                      fin_stream);
     }
-    return launch_pool_emit(pl.s, pl.pool, pl.batch, pl.k, out_scores_dev, out_ids_dev, out_scores64_dev,
-                            out_flags_dev, out_aux_dev, fin_stream);
+    return launch_pool_emit(pl.s, pl.pool, pl.batch, pl.k, pl.qn64, pl.metric, out_scores_dev, out_ids_dev,
+                            out_scores64_dev, out_flags_dev, out_aux_dev, fin_stream);
 }
 
 // `fin_stream` == `stream`: everything in order on one stream (the public cmw_search).  Otherwise the finish

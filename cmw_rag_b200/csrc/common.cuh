@@ -6,6 +6,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -105,7 +106,12 @@ struct Store {
     int64_t id_offset = 0;
     size_t hbm_bytes = 0;
     float* f32 = nullptr;            // [capacity, dim] raw rows (CMW_STORE_F32)
-    __nv_bfloat16* bf16 = nullptr;   // [capacity, dim] L2-normalised rows (CMW_STORE_BF16)
+    // [capacity, dim] L2-normalised rows as 16-bit tiles: bf16 (CMW_STORE_BF16) or fp16 (CMW_STORE_F16, `half_tiles`).
+    // Same bytes and tensor-core rate; fp16 keeps 11 significand bits instead of 8, so the rounding residual the
+    // exactness certificate has to absorb is 8x smaller -- and unit vectors never leave fp16's range
+    // (results below its smallest normal, 2^-14, are flushed to zero at conversion and counted in the residual)
+    __nv_bfloat16* bf16 = nullptr;
+    bool half_tiles = false;
     float* inv_norm = nullptr;       // [cap4] 1/|c| (0 for a zero row, NaN when tombstoned)
     float* norm = nullptr;           // [cap4] |c|   (NaN when tombstoned)
     float* live = nullptr;           // [cap4] 1.0   (NaN when tombstoned)
@@ -189,6 +195,7 @@ extern Options g_opt;
 struct ScanArgs {
     const void* rows;      // base pointer of the store's tiles (fp32 or bf16)
     int elt_bytes;         // 4 or 2
+    int half_tiles;        // 2-byte elements: 1 = fp16, 0 = bf16
     int dim;
     const float* row_mul;  // per-row multiplier (indexed by LOCAL row)
     int64_t row_begin, row_end;
@@ -205,7 +212,7 @@ int launch_scan(const ScanArgs& a, cudaStream_t stream);
 
 struct GemmArgs {
     const Store* store;
-    const __nv_bfloat16* q_bf16;  // [bpad, dim]
+    const __nv_bfloat16* q_bf16;  // [bpad, dim] 16-bit query tile in the store's tile format
     int batch;                    // real queries
     int bpad;                     // padded to the N tile
     const float* row_mul;
@@ -222,8 +229,8 @@ bool gemm_supported(const Store* s);
 bool gemm_scan_permuted(const Store* s, const Options& o, int bpad);
 
 int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64, double* q4,
-                        double* qres, float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count, Pool seg,
-                        int wide_rows, cudaStream_t stream);
+                        double* qres, float* q_f32, __nv_bfloat16* q_bf16, int half_tiles, Pool pool,
+                        int dense_count, Pool seg, int wide_rows, cudaStream_t stream);
 
 // how the certificate / rescoring cut bound is obtained (see Options::bf16_eps)
 enum CertKind : int { CERT_FIXED = 0, CERT_STATISTICAL = 1, CERT_RIGOROUS = 2 };
@@ -232,6 +239,7 @@ struct CertParams {
     double eps_fixed;       // CERT_FIXED: the bound itself (cosine units)
     double sigmas;          // CERT_STATISTICAL: multiples of the sigma bound from q4 and the store's max row 4-norm
     double acc_slack;       // CERT_RIGOROUS / STATISTICAL: fp32 accumulation slack of the filter, D * 2^-23
+    double tile_u;          // unit round-off of the 16-bit tile format: 2^-8 (bf16) or 2^-11 (fp16)
     const double* q4;       // [B] |q/|q||_4
     const double* qres;     // [B] |q^ - bf16(q^)|_2 relative to |q^| (the query tile's rounding residual)
     const double* qn64;     // [B] |q|
@@ -251,7 +259,7 @@ int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprim
                           float* out_scores, int64_t* out_ids, double* out_scores64,
                           int32_t* out_flags, double* out_aux, cudaStream_t stream);
 // bf16 mode: emit the pool's best k as they are
-int launch_pool_emit(const Store* s, Pool pool, int batch, int k, float* out_scores,
+int launch_pool_emit(const Store* s, Pool pool, int batch, int k, const double* qn64, int metric, float* out_scores,
                      int64_t* out_ids, double* out_scores64, int32_t* out_flags, double* out_aux,
                      cudaStream_t stream);
 
@@ -323,7 +331,13 @@ __device__ __forceinline__ uint64_t f64_orderable(double d) {
 __device__ __forceinline__ double f64_from_orderable(uint64_t u) {
     return __longlong_as_double((long long)((u >> 63) ? (u & 0x7fffffffffffffffull) : ~u));
 }
-// bound on |filter score - exact score| for query b and ANY stored row (see Options::strict_certificate)
+// Pool scores are in FILTER UNITS: the score of the L2-normalised query -- the cosine, or for the inner product
+// |c| cos = (exact score) / |q|.  (Normalising the query for the filter in both metrics keeps the 16-bit tiles
+// inside fp16's range whatever the scale of the caller's vectors.)  qscale turns filter units into exact units.
+__device__ __forceinline__ double cert_qscale(const CertParams& c, int b) {
+    return c.metric == CMW_METRIC_IP ? c.qn64[b] : 1.0;
+}
+// bound, in filter units, on |filter score - exact score| for query b and ANY stored row (Options::strict_certificate)
 __device__ __forceinline__ double cert_eps(const CertParams& c, int b) {
     double e = c.eps_fixed;
     if (c.kind != CERT_FIXED) {
@@ -332,15 +346,31 @@ __device__ __forceinline__ double cert_eps(const CertParams& c, int b) {
         const double rigorous = rq + (1.0 + rq) * rc;  // Cauchy-Schwarz on the two rounding residuals
         e = rigorous;
         if (c.kind == CERT_STATISTICAL) {
-            // u = 2^-8 (bf16 keeps 8 significand bits), independent roundings
-            const double bound = c.sigmas * (1.0 / 256.0) * 0.816496580927726 * c.q4[b] *
+            // independent roundings of relative size <= u
+            const double bound = c.sigmas * c.tile_u * 0.816496580927726 * c.q4[b] *
                                  (double)__uint_as_float(c.norms[1]);
             if (bound < e) e = bound;
         }
         e += c.acc_slack * (1.0 + rq) * (1.0 + rc) + 4e-7;
     }
-    if (c.metric == CMW_METRIC_IP) e *= c.qn64[b] * (double)__uint_as_float(c.norms[0]);
+    if (c.metric == CMW_METRIC_IP) e *= (double)__uint_as_float(c.norms[0]);  // rows of norm up to max |c|
     return e;
+}
+// fp32 -> one 16-bit tile element; `stored` = the value the tile now holds (what the residuals are measured from)
+__device__ __forceinline__ uint16_t to_tile16(float x, int half_tiles, float& stored) {
+    if (half_tiles) {
+        __half h = __float2half_rn(x);
+        float v = __half2float(h);
+        if (fabsf(v) < 6.103515625e-05f) {  // below 2^-14: no subnormals in the tiles, whatever the MMA does with them
+            h = __ushort_as_half((unsigned short)0);
+            v = 0.f;
+        }
+        stored = v;
+        return __half_as_ushort(h);
+    }
+    const __nv_bfloat16 bv = __float2bfloat16_rn(x);
+    stored = __bfloat162float(bv);
+    return __bfloat16_as_ushort(bv);
 }
 // key whose ASCENDING order is (score descending, id ascending)
 __device__ __forceinline__ uint64_t desc_key(float score, uint32_t id) {

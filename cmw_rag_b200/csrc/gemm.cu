@@ -206,15 +206,16 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, dim] tensor, box = 64 elements (128 bytes) x box_rows, 128-byte swizzle
-int encode_2d(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows) {
+// 2-D 16-bit (bf16 or fp16) row-major [rows, dim] tensor, box = 64 elements (128 bytes) x box_rows, 128-byte swizzle
+int encode_2d(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows, bool half_tiles) {
     EncodeTiledFn fn = get_encode_fn();
     CMW_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
     cuuint32_t estride[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+    CUresult r = fn(out, half_tiles ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void*>(base), gdim, gstride, box,
                     estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CMW_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -223,7 +224,7 @@ int encode_2d(CUtensorMap* out, const void* base, int64_t rows, int dim, int box
 
 int encode_bf16_tmap(Store* s) {
     if (s->bf16 == nullptr) return -1;
-    return encode_2d(&s->tmap_bf16, s->bf16, s->capacity, s->dim, kTileM);
+    return encode_2d(&s->tmap_bf16, s->bf16, s->capacity, s->dim, kTileM, s->half_tiles);
 }
 
 bool gemm_supported(const Store* s) { return s->bf16 != nullptr && s->tmap_ok; }
@@ -299,15 +300,17 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.dense_ids = a.wide_scores ? a.wide_ids : a.pool.ids;
     p.dense_stride = a.wide_scores ? a.wide_stride : kPoolCap;
     p.dynamic = 0;
-    // instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    // instruction descriptor: D = f32 (bit 4), A / B format at bits 7 / 10 (0 = fp16, 1 = bf16), both K-major,
+    // N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t fmt = s->half_tiles ? 0u : 1u;
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     p.row_mul = a.row_mul;
     p.pool_scores = a.pool.scores;
     p.pool_ids = a.pool.ids;
     p.pool_cnt = a.pool.cnt;
     p.pool_thr = a.pool.thr;
     CUtensorMap tmap_b;
-    int rc = encode_2d(&tmap_b, a.q_bf16, a.bpad, s->dim, p.nt);
+    int rc = encode_2d(&tmap_b, a.q_bf16, a.bpad, s->dim, p.nt, s->half_tiles);
     if (rc) return rc;
     const size_t smem = (size_t)nst * p.stage_bytes + tail + 1024;  // + slack for 1024-byte alignment
     static SmemAttrCache smem_set;

@@ -330,7 +330,7 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
 }
 
-int encode_2d(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows);  // gemm.cu
+int encode_2d(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows, bool half_tiles);  // gemm.cu
 void set_scan_order(GemmParams& p, const GemmArgs& a, int tile_rows);                     // gemm.cu
 
 int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
@@ -356,15 +356,16 @@ int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
     p.dense_scores = a.wide_scores ? a.wide_scores : a.pool.scores;
     p.dense_ids = a.wide_scores ? a.wide_ids : a.pool.ids;
     p.dense_stride = a.wide_scores ? a.wide_stride : kPoolCap;
-    // instruction descriptor: D = f32, A = B = bf16, K-major, N >> 3 at bit 17, M = 256 >> 4 at bit 24
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    // instruction descriptor: D = f32, A / B format (0 = fp16, 1 = bf16), K-major, N >> 3 at bit 17, M = 256 >> 4 at bit 24
+    const uint32_t fmt = s->half_tiles ? 0u : 1u;
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
     p.row_mul = a.row_mul;
     p.pool_scores = a.pool.scores;
     p.pool_ids = a.pool.ids;
     p.pool_cnt = a.pool.cnt;
     p.pool_thr = a.pool.thr;
     CUtensorMap tmap_b;
-    int rc = encode_2d(&tmap_b, a.q_bf16, a.bpad, s->dim, p.nt / 2);
+    int rc = encode_2d(&tmap_b, a.q_bf16, a.bpad, s->dim, p.nt / 2, s->half_tiles);
     if (rc) return rc;
     const size_t smem = (size_t)nst * p.stage_bytes + tail + 1024;
     static SmemAttrCache smem_set;

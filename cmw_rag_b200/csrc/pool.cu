@@ -15,8 +15,8 @@ namespace cmw {
 __global__ void __launch_bounds__(256)
 prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, int metric,
                     double* __restrict__ qn64, double* __restrict__ q4, double* __restrict__ qres,
-                    float* __restrict__ q_f32, __nv_bfloat16* __restrict__ q_bf16, Pool pool, int dense_count,
-                    Pool seg, int wide_rows) {
+                    float* __restrict__ q_f32, __nv_bfloat16* __restrict__ q_bf16, int half_tiles, Pool pool,
+                    int dense_count, Pool seg, int wide_rows) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= bpad) return;
@@ -56,7 +56,9 @@ prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, i
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     const double nrm = sqrt(acc);
-    const double scale = (metric == CMW_METRIC_COSINE) ? (nrm > 0.0 ? 1.0 / nrm : 0.0) : 1.0;
+    // the filter always sees the L2-normalised query (pool scores in filter units, see cert_qscale)
+    (void)metric;
+    const double scale = nrm > 0.0 ? 1.0 / nrm : 0.0;
     if (lane == 0) qn64[b] = nrm;
     {
         // |q/|q||_4 for the certificate bound
@@ -80,31 +82,27 @@ prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, i
         float4 w = make_float4((float)ex, (float)ey, (float)ez, (float)ew);
         of[c] = w;
         if (q_bf16 != nullptr) {
-            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(q_bf16 + (size_t)b * dim);
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
-            ob[2 * c] = lo;
-            ob[2 * c + 1] = hi;
-            const double dx = ex - (double)__low2float(lo), dy = ey - (double)__high2float(lo);
-            const double dz = ez - (double)__low2float(hi), dw = ew - (double)__high2float(hi);
+            uint2* ob = reinterpret_cast<uint2*>(q_bf16 + (size_t)b * dim);
+            float sx, sy, sz, sw;
+            const uint32_t tx = to_tile16(w.x, half_tiles, sx), ty = to_tile16(w.y, half_tiles, sy);
+            const uint32_t tz = to_tile16(w.z, half_tiles, sz), tw = to_tile16(w.w, half_tiles, sw);
+            ob[c] = make_uint2(tx | (ty << 16), tz | (tw << 16));
+            const double dx = ex - (double)sx, dy = ey - (double)sy, dz = ez - (double)sz, dw = ew - (double)sw;
             res2 += dx * dx + dy * dy + dz * dz + dw * dw;
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) res2 += __shfl_xor_sync(0xffffffffu, res2, o);
-    if (lane == 0) {
-        // relative to the scaled query's norm (1 for cosine, |q| for inner product), rounded up a little
-        const double ref = (metric == CMW_METRIC_COSINE) ? 1.0 : nrm;
-        qres[b] = ref > 0.0 ? sqrt(res2) / ref * (1.0 + 1e-9) + 1e-12 : 0.0;
-    }
+    if (lane == 0) qres[b] = sqrt(res2) * (1.0 + 1e-9) + 1e-12;  // the normalised query has norm 1; rounded up a little
 }
 
 int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64, double* q4,
-                        double* qres, float* q_f32, __nv_bfloat16* q_bf16, Pool pool, int dense_count, Pool seg,
-                        int wide_rows, cudaStream_t stream) {
+                        double* qres, float* q_f32, __nv_bfloat16* q_bf16, int half_tiles, Pool pool,
+                        int dense_count, Pool seg, int wide_rows, cudaStream_t stream) {
     const int wpb = 8;
     prep_queries_kernel<<<(bpad + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, batch, bpad, dim, metric, qn64, q4, qres,
-                                                                        q_f32, q_bf16, pool, dense_count, seg,
-                                                                        wide_rows);
+                                                                        q_f32, q_bf16, half_tiles, pool,
+                                                                        dense_count, seg, wide_rows);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
@@ -462,8 +460,10 @@ select_kernel(Pool pool, int k, int kprime, const double* __restrict__ exact, co
     if (threadIdx.x == 0 && out_aux != nullptr) {
         // row shards: what the cross-shard certificate needs from this shard -- every row outside this pool has
         // filter score <= t (none, if the pool never filled), and eps with this shard's own residual bound
-        out_aux[2 * b] = (n >= kprime) ? (double)pool.thr[b] : -INFINITY;
-        out_aux[2 * b + 1] = cert_eps(cert, b);
+        // (both in exact-score units, so that shards may be compared)
+        const double qs = cert_qscale(cert, b);
+        out_aux[2 * b] = (n >= kprime) ? (double)pool.thr[b] * qs : -INFINITY;
+        out_aux[2 * b + 1] = cert_eps(cert, b) * qs;
     }
     if (threadIdx.x == 0 && out_flags != nullptr) {
         int flag = 0;
@@ -478,7 +478,7 @@ select_kernel(Pool pool, int k, int kprime, const double* __restrict__ exact, co
             if (kk >= 1 && hi[kk - 1] < neg_inf_key) {
                 kth = f64_from_orderable(~hi[kk - 1]);
             }
-            if (!(kth > t + e)) flag = CMW_FLAG_UNCERTIFIED;
+            if (!(kth > (t + e) * cert_qscale(cert, b))) flag = CMW_FLAG_UNCERTIFIED;  // t, e: filter units
         }
         out_flags[b] = flag;
     }
@@ -509,18 +509,20 @@ int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprim
 }
 
 // bf16 mode: the pool is already sorted by the last compaction; emit its best k.
-__global__ void pool_emit_kernel(Pool pool, int k, int64_t id_offset, float* __restrict__ out_scores,
-                                 int64_t* __restrict__ out_ids, double* __restrict__ out_scores64,
-                                 int32_t* __restrict__ out_flags, double* __restrict__ out_aux) {
+__global__ void pool_emit_kernel(Pool pool, int k, int64_t id_offset, const double* __restrict__ qn64, int metric,
+                                 float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                                 double* __restrict__ out_scores64, int32_t* __restrict__ out_flags,
+                                 double* __restrict__ out_aux) {
     const int b = blockIdx.x;
     const int n = pool.cnt[b];
+    const float qs = metric == CMW_METRIC_IP ? (float)qn64[b] : 1.0f;  // filter units -> inner product
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
         float s = -INFINITY;
         int64_t id = -1;
         if (j < n) {
             const float v = pool.scores[(size_t)b * kPoolCap + j];
             if (v > -INFINITY) {
-                s = v;
+                s = v * qs;
                 id = (int64_t)pool.ids[(size_t)b * kPoolCap + j] + id_offset;
             }
         }
@@ -535,10 +537,10 @@ __global__ void pool_emit_kernel(Pool pool, int k, int64_t id_offset, float* __r
     }
 }
 
-int launch_pool_emit(const Store* s, Pool pool, int batch, int k, float* out_scores,
+int launch_pool_emit(const Store* s, Pool pool, int batch, int k, const double* qn64, int metric, float* out_scores,
                      int64_t* out_ids, double* out_scores64, int32_t* out_flags, double* out_aux,
                      cudaStream_t stream) {
-    pool_emit_kernel<<<batch, 128, 0, stream>>>(pool, k, s->id_offset, out_scores, out_ids,
+    pool_emit_kernel<<<batch, 128, 0, stream>>>(pool, k, s->id_offset, qn64, metric, out_scores, out_ids,
                                                out_scores64, out_flags, out_aux);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());

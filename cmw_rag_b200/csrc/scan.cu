@@ -55,6 +55,10 @@ template <>
 struct EltTraits<__nv_bfloat16> {
     static constexpr int kPerVec = 8;
 };
+template <>
+struct EltTraits<__half> {
+    static constexpr int kPerVec = 8;
+};
 
 template <int NQ>
 __device__ __forceinline__ void fma_vec(const float4& v, const float4 (&qv)[NQ], float (&acc)[NQ]) {
@@ -67,6 +71,20 @@ __device__ __forceinline__ void fma_vec(const float4& v, const float4 (&qv)[NQ],
     }
 }
 
+// eight 16-bit tile elements -> two float4 (bf16: a shift; fp16: cvt)
+template <typename ELT>
+__device__ __forceinline__ void unpack_x8(const uint4& u, float4& a, float4& b);
+template <>
+__device__ __forceinline__ void unpack_x8<float>(const uint4&, float4&, float4&) {}
+template <>
+__device__ __forceinline__ void unpack_x8<__half>(const uint4& u, float4& a, float4& b) {
+    const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    const float2 p2 = __half22float2(*reinterpret_cast<const __half2*>(&u.z));
+    const float2 p3 = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+    a = make_float4(p0.x, p0.y, p1.x, p1.y);
+    b = make_float4(p2.x, p2.y, p3.x, p3.y);
+}
 __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float4& a, float4& b) {
     a.x = __uint_as_float(u.x << 16);
     a.y = __uint_as_float(u.x & 0xffff0000u);
@@ -76,6 +94,10 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float4& a, float4&
     b.y = __uint_as_float(u.z & 0xffff0000u);
     b.z = __uint_as_float(u.w << 16);
     b.w = __uint_as_float(u.w & 0xffff0000u);
+}
+template <>
+__device__ __forceinline__ void unpack_x8<__nv_bfloat16>(const uint4& u, float4& a, float4& b) {
+    unpack_bf16x8(u, a, b);
 }
 
 // CHUNKS > 0: dim == CHUNKS * 32 * kPerVec and the query lives in registers.
@@ -178,7 +200,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
                         fma_vec<NQ>(v, qv, acc);
                     } else {
                         float4 a, b;
-                        unpack_bf16x8(u, a, b);
+                        unpack_x8<ELT>(u, a, b);
                         float4 qa[NQ], qb[NQ];
 #pragma unroll
                         for (int i = 0; i < NQ; ++i) {
@@ -202,7 +224,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
                         fma_vec<NQ>(v, qv, acc);
                     } else {
                         float4 a, b;
-                        unpack_bf16x8(u, a, b);
+                        unpack_x8<ELT>(u, a, b);
                         float4 qa[NQ], qb[NQ];
 #pragma unroll
                         for (int i = 0; i < NQ; ++i) {
@@ -317,6 +339,14 @@ int launch_scan(const ScanArgs& a, cudaStream_t stream) {
             case 2: return dispatch_chunks<float, 2>(p, grid, smem, stream);
             case 3: return dispatch_chunks<float, 3>(p, grid, smem, stream);
             default: return dispatch_chunks<float, 4>(p, grid, smem, stream);
+        }
+    }
+    if (a.half_tiles) {
+        switch (a.nq) {
+            case 1: return dispatch_chunks<__half, 1>(p, grid, smem, stream);
+            case 2: return dispatch_chunks<__half, 2>(p, grid, smem, stream);
+            case 3: return dispatch_chunks<__half, 3>(p, grid, smem, stream);
+            default: return dispatch_chunks<__half, 4>(p, grid, smem, stream);
         }
     }
     switch (a.nq) {

@@ -39,7 +39,7 @@ void set_error(const char* fmt, ...) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ingest_kernel(const float* __restrict__ src, const int32_t* __restrict__ gid_src, int64_t n, int dim,
-              int64_t row0, float* __restrict__ f32, __nv_bfloat16* __restrict__ bf16,
+              int64_t row0, float* __restrict__ f32, __nv_bfloat16* __restrict__ bf16, int half_tiles,
               float* __restrict__ inv_norm, float* __restrict__ norm, float* __restrict__ live,
               double* __restrict__ norm64, int32_t* __restrict__ kb_gid,
               uint32_t* __restrict__ maxnorm_bits) {
@@ -68,17 +68,16 @@ ingest_kernel(const float* __restrict__ src, const int32_t* __restrict__ gid_src
         }
         double res2 = 0.0;  // |c/|c| - its bf16 tile|^2 from the values actually written (rigorous certificate)
         if (bf16 != nullptr) {
-            __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(bf16 + dst * dim);
+            uint2* out = reinterpret_cast<uint2*>(bf16 + dst * dim);
             for (int c = lane; c < nvec; c += 32) {
                 float4 v = __ldg(in + c);
                 const double ex = (double)v.x * inv, ey = (double)v.y * inv, ez = (double)v.z * inv,
                              ew = (double)v.w * inv;
-                const __nv_bfloat162 lo = __floats2bfloat162_rn((float)ex, (float)ey);
-                const __nv_bfloat162 hi = __floats2bfloat162_rn((float)ez, (float)ew);
-                out[2 * c] = lo;
-                out[2 * c + 1] = hi;
-                const double dx = ex - (double)__low2float(lo), dy = ey - (double)__high2float(lo);
-                const double dz = ez - (double)__low2float(hi), dw = ew - (double)__high2float(hi);
+                float sx, sy, sz, sw;
+                const uint32_t tx = to_tile16((float)ex, half_tiles, sx), ty = to_tile16((float)ey, half_tiles, sy);
+                const uint32_t tz = to_tile16((float)ez, half_tiles, sz), tw = to_tile16((float)ew, half_tiles, sw);
+                out[c] = make_uint2(tx | (ty << 16), tz | (tw << 16));
+                const double dx = ex - (double)sx, dy = ey - (double)sy, dz = ez - (double)sz, dw = ew - (double)sw;
                 res2 += dx * dx + dy * dy + dz * dz + dw * dw;
             }
 #pragma unroll
@@ -270,8 +269,10 @@ int cmw_store_create(int device, int dim, int64_t capacity_rows, uint32_t flags,
     CMW_REQUIRE(capacity_rows > 0 && capacity_rows < (1ll << 31),
                 "cmw_store_create: capacity_rows must be in (0, 2^31), got %lld",
                 (long long)capacity_rows);
-    CMW_REQUIRE((flags & (CMW_STORE_F32 | CMW_STORE_BF16)) != 0,
-                "cmw_store_create: flags must include CMW_STORE_F32 and/or CMW_STORE_BF16");
+    CMW_REQUIRE((flags & (CMW_STORE_F32 | CMW_STORE_BF16 | CMW_STORE_F16)) != 0,
+                "cmw_store_create: flags must include CMW_STORE_F32 and/or one of CMW_STORE_BF16 / CMW_STORE_F16");
+    CMW_REQUIRE((flags & (CMW_STORE_BF16 | CMW_STORE_F16)) != (CMW_STORE_BF16 | CMW_STORE_F16),
+                "cmw_store_create: CMW_STORE_BF16 and CMW_STORE_F16 are alternatives (one set of 16-bit tiles)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0) {
@@ -302,7 +303,8 @@ int cmw_store_create(int device, int dim, int64_t capacity_rows, uint32_t flags,
     int rc = 0;
     const size_t elems = (size_t)capacity_rows * (size_t)dim;
     if (!rc && (flags & CMW_STORE_F32)) rc = alloc((void**)&s->f32, elems * sizeof(float));
-    if (!rc && (flags & CMW_STORE_BF16)) rc = alloc((void**)&s->bf16, elems * sizeof(__nv_bfloat16));
+    s->half_tiles = (flags & CMW_STORE_F16) != 0;
+    if (!rc && (flags & (CMW_STORE_BF16 | CMW_STORE_F16))) rc = alloc((void**)&s->bf16, elems * sizeof(__nv_bfloat16));
     if (!rc) rc = alloc((void**)&s->inv_norm, cap4 * sizeof(float));
     if (!rc) rc = alloc((void**)&s->norm, cap4 * sizeof(float));
     if (!rc) rc = alloc((void**)&s->live, cap4 * sizeof(float));
@@ -405,7 +407,7 @@ int cmw_store_append_f32(cmw_store* h, const float* rows_dev, const int32_t* kb_
     const int64_t max_blocks = (int64_t)s->sm_count * 16;
     if (blocks > max_blocks) blocks = max_blocks;
     ingest_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(
-        rows_dev, kb_gid_dev, n, s->dim, s->rows, s->f32, s->bf16, s->inv_norm, s->norm, s->live,
+        rows_dev, kb_gid_dev, n, s->dim, s->rows, s->f32, s->bf16, s->half_tiles ? 1 : 0, s->inv_norm, s->norm, s->live,
         s->norm64, s->kb_gid, s->maxnorm_bits);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());

@@ -56,12 +56,19 @@ class DenseStore:
     ``dim``: embedding width (FRIDA: 1536 -- rag_engine/config/models.yaml:8-11 of the reference).
     ``capacity``: rows reserved in HBM up front (pointers never move, TMA descriptors stay valid).
     ``id_offset``: added to row numbers in results (row shards of a multi-GPU corpus).
+    ``bf16``: keep 16-bit tiles of the normalised rows (the tensor-core filter's operand); ``tiles16`` picks
+    their format -- ``"f16"`` (default: 8x smaller rounding residual, so the rigorous exactness certificate
+    costs nothing) or ``"bf16"`` (BASELINE.json's literal format).
     """
 
     def __init__(self, dim: int, capacity: int, device: int = 0, f32: bool = True, bf16: bool = True,
-                 id_offset: int = 0):
+                 id_offset: int = 0, tiles16: str = "f16"):
         lib = N.lib()
-        flags = (N.STORE_F32 if f32 else 0) | (N.STORE_BF16 if bf16 else 0)
+        if tiles16 not in ("f16", "bf16"):
+            raise ValueError(f"tiles16 must be 'f16' or 'bf16', got {tiles16!r}")
+        t16 = (N.STORE_F16 if tiles16 == "f16" else N.STORE_BF16) if bf16 else 0
+        flags = (N.STORE_F32 if f32 else 0) | t16
+        self.tiles16 = tiles16 if bf16 else None
         handle = ctypes.c_void_p()
         N.check(lib.cmw_store_create(int(device), int(dim), int(capacity), flags, int(id_offset),
                                      ctypes.byref(handle)), "cmw_store_create")

@@ -208,6 +208,43 @@ class ShardedSearcher:
         ev.record()
         self.timings.setdefault(name, []).append(ev)
 
+    _PHASES = (("filter", "start", "filter_done"), ("gather1", "filter_done", "gather1_done"),
+               ("kth", "gather1_done", "kth_done"), ("finish", "kth_done", "finish_done"),
+               ("gather2", "finish_done", "gather2_done"), ("merge", "gather2_done", "merge_done"))
+
+    def phase_ms(self) -> dict:
+        """Milliseconds per phase of the two-phase search, summed over the searches since ``timings = {}``
+        (synchronises).  filter = prep + filter slabs + compaction, finish = rescoring + selection."""
+        import torch
+
+        if not self.timings:
+            return {}
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self._PHASES:
+            ea, eb = self.timings.get(a, []), self.timings.get(b, [])
+            out[name] = float(sum(x.elapsed_time(y) for x, y in zip(ea, eb)))
+        return out
+
+    def search_host(self, queries_host, k: int, out=None, **kw):
+        """The host-buffer form (what a caller without device tensors uses, on every rank): H2D of the queries
+        (direct DMA when the array is page-locked), the sharded search, D2H of the merged result into ``out`` =
+        (scores f32[B,k], ids i64[B,k], flags i32[B]) numpy arrays (allocated when None); synchronises."""
+        import numpy as np
+        import torch
+
+        dev = torch.device(f"cuda:{self.store.device}")
+        q = torch.from_numpy(np.ascontiguousarray(queries_host, dtype=np.float32)).to(dev, non_blocking=True)
+        ms, mi, fl = self.search(q, k, **kw)
+        b = q.shape[0]
+        if out is None:
+            out = (np.empty((b, k), np.float32), np.empty((b, k), np.int64), np.zeros((b,), np.int32))
+        torch.from_numpy(out[0]).copy_(ms, non_blocking=True)
+        torch.from_numpy(out[1]).copy_(mi, non_blocking=True)
+        torch.from_numpy(out[2]).copy_(fl.to(torch.int32), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out
+
     def search(self, queries, k: int, **kw):
         """queries [B, dim] (replicated on every rank) -> (scores f32[B,k], ids i64[B,k], flags i32[B]),
         identical on every rank."""

@@ -88,8 +88,9 @@ class B200Store:
         metric: str = "cosine",  # vector_store.py:48-51 pins {"hnsw:space": "cosine"}
         mode: str = "f32",
         keep_f32: bool = True,
-        keep_bf16: bool = True,
+        keep_bf16: bool = True,  # keep the 16-bit tiles (tensor-core filter); their format is `tiles16`
         id_offset: int = 0,
+        tiles16: str = "f16",
     ):
         self.collection_name = collection_name
         self.host = host
@@ -100,6 +101,7 @@ class B200Store:
         self._capacity = int(capacity)
         self._device = int(device)
         self._keep = (keep_f32, keep_bf16)
+        self._tiles16 = tiles16
         self._id_offset = int(id_offset)
         self._dense: DenseStore | None = None
         self._lock = threading.RLock()
@@ -131,7 +133,7 @@ class B200Store:
             # (the reference's own store test uses 3-d vectors: tests/test_storage_vector_store.py:10-24)
             self._pdim = (self._dim + 7) // 8 * 8
             self._dense = DenseStore(self._pdim, self._capacity, device=self._device, f32=self._keep[0],
-                                     bf16=self._keep[1], id_offset=self._id_offset)
+                                     bf16=self._keep[1], id_offset=self._id_offset, tiles16=self._tiles16)
         elif dim != self._dim:
             raise ValueError(f"embedding dimension {dim} does not match the collection's {self._dim}")
         return self._dense
@@ -240,7 +242,7 @@ class B200Store:
         new_cap = max(needed, 2 * self._capacity)
         old = self._dense
         new = DenseStore(self._pdim, new_cap, device=self._device, f32=self._keep[0], bf16=self._keep[1],
-                         id_offset=self._id_offset)
+                         id_offset=self._id_offset, tiles16=self._tiles16)
         n = len(self._ids)
         for lo in range(0, n, chunk_rows):
             m = min(chunk_rows, n - lo)
@@ -279,7 +281,7 @@ class B200Store:
                 raise RuntimeError("compact() re-ingests from the fp32 tiles, which this collection does not keep")
             old = self._dense
             new = DenseStore(self._pdim, self._capacity, device=self._device, f32=self._keep[0], bf16=self._keep[1],
-                             id_offset=self._id_offset)
+                             id_offset=self._id_offset, tiles16=self._tiles16)
             alive = np.asarray(self._alive, bool)
             for lo in range(0, n, chunk_rows):
                 m = min(chunk_rows, n - lo)

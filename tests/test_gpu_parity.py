@@ -1027,7 +1027,8 @@ def _structured_case(d, m, n_decoys, seed):
 
 @pytest.mark.parametrize("d,m", [(1536, 1017), (1536, 254), (4096, 4068), (256, 254)])
 @pytest.mark.parametrize("metric", ["cosine", "ip"])
-def test_certificate_is_sound_on_adversarial_roundings(torch_cuda, d, m, metric):
+@pytest.mark.parametrize("tiles16", ["bf16", "f16"])
+def test_certificate_is_sound_on_adversarial_roundings(torch_cuda, d, m, metric, tiles16):
     """The guarantee of CMW_MODE_F32_EXACT: a query comes back with the oracle's ids OR flagged -- never a
     silent miss -- whatever the rounding structure of the vectors.  (Round 1's bound assumed u = 2^-9 and
     independent roundings; on these inputs the bf16 filter is off by up to 6.6e-3 and it certified wrong
@@ -1040,7 +1041,7 @@ def test_certificate_is_sound_on_adversarial_roundings(torch_cuda, d, m, metric)
     if metric == "ip":
         rows = rows * np.linspace(0.97, 1.03, rows.shape[0], dtype=np.float32)[:, None]
         q = q * np.float32(1.7)
-    st = DenseStore(d, rows.shape[0])
+    st = DenseStore(d, rows.shape[0], tiles16=tiles16)
     st.append(rows)
     qd = torch.from_numpy(q).cuda()
     silent, flagged = 0, 0
@@ -1072,11 +1073,20 @@ def test_certificate_is_sound_on_adversarial_roundings(torch_cuda, d, m, metric)
                                    for b in range(q.shape[0])))
     finally:
         N.set_option("strict_certificate", old)
-    print(f"adversarial d={d} m={m} {metric}: rigorous flagged {flagged}, statistical silent misses {stat_silent}")
+    print(f"adversarial {tiles16} d={d} m={m} {metric}: rigorous flagged {flagged}, "
+          f"statistical silent misses {stat_silent}")
     st.close()
 
 
-def test_filter_error_stays_inside_the_rigorous_bound(torch_cuda):
+def _f16_round(x32: np.ndarray) -> np.ndarray:
+    """fp32 -> fp16 (round to nearest even), results below the smallest normal flushed to zero -> fp32."""
+    h = np.ascontiguousarray(x32, dtype=np.float32).astype(np.float16).astype(np.float32)
+    h[np.abs(h) < 2.0 ** -14] = 0.0
+    return h
+
+
+@pytest.mark.parametrize("tiles16", ["bf16", "f16"])
+def test_filter_error_stays_inside_the_rigorous_bound(torch_cuda, tiles16):
     """What the certificate rests on, measured: bf16-mode scores (the tensor-core filter's own output) against
     (a) the fp64 dot product of the bf16-ROUNDED operands -- the fp32 accumulation error, bounded by D * 2^-23 --
     and (b) the exact cosine -- bounded by r_q + (1 + r_q) R_c + D * 2^-23 with the residuals recomputed here
@@ -1088,19 +1098,22 @@ def test_filter_error_stays_inside_the_rigorous_bound(torch_cuda):
     rows_a, q_a = _structured_case(d, 1017, n_decoys=1500, seed=9)
     c = np.concatenate([rows_a, synth.make_corpus(20000, d, seed=8, ties=False)])
     q = np.concatenate([q_a, synth.make_queries(c, 28, seed=9, tie_probe=False)[0]])
-    st = DenseStore(d, c.shape[0])
+    st = DenseStore(d, c.shape[0], tiles16=tiles16)
     st.append(c)
+    rnd = _bf16_round if tiles16 == "bf16" else _f16_round
+    u = 2.0 ** -8 if tiles16 == "bf16" else 2.0 ** -11
     sc, ids, _ = st.search(torch.from_numpy(q).cuda(), k, mode="bf16", algo="gemm")
     torch.cuda.synchronize()
     sc, ids = sc.cpu().numpy().astype(np.float64), ids.cpu().numpy()
     c64, q64 = c.astype(np.float64), q.astype(np.float64)
     c_hat = c64 / np.linalg.norm(c64, axis=1, keepdims=True)
     q_hat = q64 / np.linalg.norm(q64, axis=1, keepdims=True)
-    c_t = _bf16_round(c_hat.astype(np.float32)).astype(np.float64)
-    q_t = _bf16_round(q_hat.astype(np.float32)).astype(np.float64)
+    c_t = rnd(c_hat.astype(np.float32)).astype(np.float64)
+    q_t = rnd(q_hat.astype(np.float32)).astype(np.float64)
     r_c = np.linalg.norm(c_hat - c_t, axis=1)
     r_q = np.linalg.norm(q_hat - q_t, axis=1)
-    assert r_c.max() <= 2.0 ** -8 and r_q.max() <= 2.0 ** -8  # round to nearest, 8 significand bits
+    # round to nearest: relative error <= u per element (+ the flushed fp16 elements, each below 2^-14)
+    assert r_c.max() <= u + 2.0 ** -14 * np.sqrt(d) and r_q.max() <= u + 2.0 ** -14 * np.sqrt(d)
     slack = d * 2.0 ** -23
     worst_acc, worst_tot = 0.0, 0.0
     for b in range(q.shape[0]):
@@ -1111,8 +1124,9 @@ def test_filter_error_stays_inside_the_rigorous_bound(torch_cuda):
         assert np.abs(sc[b] - exact).max() <= bound, (b, np.abs(sc[b] - exact).max(), bound)
         worst_tot = max(worst_tot, float(np.abs(sc[b] - exact).max() / bound))
     assert worst_acc <= slack, (worst_acc, slack)
-    print(f"tensor-pipe accumulation error max {worst_acc:.3e} (slack {slack:.3e}); "
-          f"filter error / rigorous bound max {worst_tot:.3f}")
+    print(f"{tiles16}: tensor-pipe accumulation error max {worst_acc:.3e} (slack {slack:.3e}); "
+          f"filter error / rigorous bound max {worst_tot:.3f}; residuals r_c max {r_c.max():.3e} "
+          f"r_q max {r_q.max():.3e}")
     st.close()
 
 
@@ -1122,3 +1136,41 @@ def test_scan_kernel_four_queries_per_pass(cfg1, batch):
     sc, ids, fl = cfg1["store"].search_host(cfg1["q"][:batch], 20, mode="f32", algo="scan")
     _check_exact(ids, sc, cfg1["ref_ids"][:batch], cfg1["ref_sc"][:batch])
     assert (fl == 0).all()
+
+
+@pytest.mark.parametrize("metric", ["cosine", "ip"])
+def test_bf16_tiles_store(cfg1, torch_cuda, metric):
+    """BASELINE.json's literal tile format: a store whose 16-bit tiles are bf16 (the default is fp16).  Exact mode
+    through the tensor-core filter (batches on the 1-CTA and the CTA-pair kernel) and the 16-bit scan, device API:
+    the oracle's ids, nothing flagged; approximate mode within the north star's 2e-3.  Also a badly scaled query
+    (norm 1e-6 / 1e+6): the filter normalises the query in both metrics, so neither tile format cares."""
+    torch = torch_cuda
+    from cmw_rag_b200 import DenseStore
+
+    c, q = cfg1["c"], cfg1["q"].copy()
+    q[3] *= 1e-6
+    q[4] *= 1e6
+    st = DenseStore(1536, c.shape[0], tiles16="bf16")
+    st.append(c)
+    assert st.tiles16 == "bf16"
+    k = 20
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, k, metric=metric)
+    qd = torch.from_numpy(q).cuda()
+    scale = np.maximum(1.0, np.linalg.norm(q.astype(np.float64), axis=1))[:, None] if metric == "ip" else 1.0
+    for b in (1, 40, 64):
+        sc, ids, fl = st.search(qd[:b], k, metric=metric, mode="f32", algo="gemm")
+        torch.cuda.synchronize()
+        assert (ids.cpu().numpy() == ref_ids[:b]).all() and int(fl.sum()) == 0, b
+        err = np.abs(sc.cpu().numpy() - ref_sc[:b]) / (scale[:b] if metric == "ip" else 1.0)
+        assert err.max() <= F32_TOL
+    for store in (st, cfg1["store"]):  # bf16 tiles, fp16 tiles
+        for algo in ("scan", "gemm"):
+            sc, ids, _ = store.search_host(q, k, metric=metric, mode="bf16", algo=algo)
+            recall = np.mean([len(set(ids[b]) & set(ref_ids[b])) / k for b in range(q.shape[0])])
+            assert recall >= 0.97, (algo, recall)
+            ex = np.einsum("bkd,bd->bk", c[ids].astype(np.float64), q.astype(np.float64))
+            if metric == "cosine":
+                ex /= np.linalg.norm(q.astype(np.float64), axis=1)[:, None]
+                ex /= np.linalg.norm(c[ids].astype(np.float64), axis=2)
+            assert (np.abs(sc - ex) / scale).max() <= BF16_TOL, algo
+    st.close()

@@ -97,7 +97,7 @@ def test_where_filter():
 class FakeDense:
     """Stands in for DenseStore in host-logic tests: answers with the oracle."""
 
-    def __init__(self, dim, capacity, device=0, f32=True, bf16=True, id_offset=0):
+    def __init__(self, dim, capacity, device=0, f32=True, bf16=True, id_offset=0, tiles16="f16"):
         self.dim, self.id_offset = dim, id_offset
         self.rows_ = np.zeros((0, dim), np.float32)
         self.live = np.zeros((0,), bool)
