@@ -287,13 +287,14 @@ static int dispatch_chunks(const ScanParams& p, int grid, size_t smem, cudaStrea
     // 3-4 queries: NQ * D / 32 query floats per lane no longer fit the register file next to the row vectors
     // (ptxas spills from NQ = 3 at D = 1536), so the queries are read from shared memory: ~30 KB of LDS per
     // 6 KB row, still just inside the SM's shared-memory bandwidth at the HBM feed rate
-    if (NQ > 2) return launch_one<ELT, NQ, 0>(p, grid, smem, stream);
-    if (p.dim == 1536) {
-        return launch_one<ELT, NQ, 1536 / (32 * PV)>(p, grid, smem, stream);
+    if constexpr (NQ > 2) {
+        return launch_one<ELT, NQ, 0>(p, grid, smem, stream);
+    } else {
+        if (p.dim == 1536) return launch_one<ELT, NQ, 1536 / (32 * PV)>(p, grid, smem, stream);
+        if (p.dim == 1024) return launch_one<ELT, NQ, 1024 / (32 * PV)>(p, grid, smem, stream);
+        if (p.dim == 768 && PV == 4) return launch_one<ELT, NQ, 768 / 128>(p, grid, smem, stream);
+        return launch_one<ELT, NQ, 0>(p, grid, smem, stream);
     }
-    if (p.dim == 1024) return launch_one<ELT, NQ, 1024 / (32 * PV)>(p, grid, smem, stream);
-    if (p.dim == 768 && PV == 4) return launch_one<ELT, NQ, 768 / 128>(p, grid, smem, stream);
-    return launch_one<ELT, NQ, 0>(p, grid, smem, stream);
 }
 
 int launch_scan(const ScanArgs& a, cudaStream_t stream) {
