@@ -22,4 +22,12 @@ def __getattr__(name):  # lazy: engine/store import numpy-only modules but keep 
         from . import sharded
 
         return getattr(sharded, name)
+    if name in ("SearchBatcher",):
+        from . import batcher
+
+        return getattr(batcher, name)
+    if name in ("CollectionRegistry",):
+        from . import registry
+
+        return getattr(registry, name)
     raise AttributeError(name)

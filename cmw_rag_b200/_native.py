@@ -60,6 +60,7 @@ SIGNATURES = {
     "cmw_store_get_info": (c_int, [c_void_p, POINTER(StoreInfo)]),
     "cmw_store_append_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "cmw_store_append_host_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
+    "cmw_store_copy_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "cmw_store_tombstone": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "cmw_store_tombstone_host": (c_int, [c_void_p, c_void_p, c_int64]),
     "cmw_store_kb_gid_dev": (c_void_p, [c_void_p]),

@@ -38,8 +38,8 @@ void set_error(const char* fmt, ...) {
 // K0: ingest.  One warp per row: fp64 norm (fixed summation order), raw fp32 copy, normalised bf16.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-ingest_kernel(const float* __restrict__ src, const int32_t* __restrict__ gid_src, int64_t n, int dim,
-              int64_t row0, float* __restrict__ f32, __nv_bfloat16* __restrict__ bf16, int half_tiles,
+ingest_kernel(const float* __restrict__ src, const int32_t* __restrict__ gid_src,
+              const int64_t* __restrict__ src_index, int64_t n, int dim, int64_t row0, float* __restrict__ f32, __nv_bfloat16* __restrict__ bf16, int half_tiles,
               float* __restrict__ inv_norm, float* __restrict__ norm, float* __restrict__ live,
               double* __restrict__ norm64, int32_t* __restrict__ kb_gid,
               uint32_t* __restrict__ maxnorm_bits) {
@@ -48,7 +48,9 @@ ingest_kernel(const float* __restrict__ src, const int32_t* __restrict__ gid_src
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int nvec = dim >> 2;
     for (int64_t r = warp; r < n; r += nwarps) {
-        const float4* in = reinterpret_cast<const float4*>(src + r * dim);
+        // (device-to-device re-ingest gathers its source rows through an index; plain appends read row r)
+        const int64_t sr = src_index != nullptr ? src_index[r] : r;
+        const float4* in = reinterpret_cast<const float4*>(src + sr * dim);
         double acc = 0.0;
         for (int c = lane; c < nvec; c += 32) {
             float4 v = __ldg(in + c);
@@ -100,7 +102,7 @@ ingest_kernel(const float* __restrict__ src, const int32_t* __restrict__ gid_src
             norm[dst] = (float)nrm;
             live[dst] = 1.0f;
             norm64[dst] = nrm;
-            kb_gid[dst] = gid_src != nullptr ? gid_src[r] : -1;
+            kb_gid[dst] = gid_src != nullptr ? gid_src[sr] : -1;
             atomicMax(maxnorm_bits, __float_as_uint((float)nrm) + 1u);  // +1 ulp: upper bound
         }
     }
@@ -407,11 +409,43 @@ int cmw_store_append_f32(cmw_store* h, const float* rows_dev, const int32_t* kb_
     const int64_t max_blocks = (int64_t)s->sm_count * 16;
     if (blocks > max_blocks) blocks = max_blocks;
     ingest_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(
-        rows_dev, kb_gid_dev, n, s->dim, s->rows, s->f32, s->bf16, s->half_tiles ? 1 : 0, s->inv_norm, s->norm, s->live,
+        rows_dev, kb_gid_dev, nullptr, n, s->dim, s->rows, s->f32, s->bf16, s->half_tiles ? 1 : 0, s->inv_norm, s->norm, s->live,
         s->norm64, s->kb_gid, s->maxnorm_bits);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     s->rows += n;
+    return 0;
+}
+
+int cmw_store_copy_rows(cmw_store* dst_h, const cmw_store* src_h, const int64_t* src_rows_dev, int64_t src_row0,
+                        int64_t n, void* stream) {
+    CMW_REQUIRE(dst_h != nullptr && src_h != nullptr, "cmw_store_copy_rows: store is NULL");
+    Store* d = reinterpret_cast<Store*>(dst_h);
+    const Store* s = reinterpret_cast<const Store*>(src_h);
+    if (n == 0) return 0;
+    CMW_REQUIRE(n > 0, "cmw_store_copy_rows: bad row count");
+    CMW_REQUIRE(d != s, "cmw_store_copy_rows: source and destination are the same store");
+    CMW_REQUIRE(s->f32 != nullptr, "cmw_store_copy_rows: the source store keeps no fp32 tiles to re-ingest from");
+    CMW_REQUIRE(s->device == d->device && s->dim == d->dim,
+                "cmw_store_copy_rows: stores must live on the same device and have the same dim");
+    CMW_REQUIRE(d->rows + n <= d->capacity, "cmw_store_copy_rows: %lld rows + %lld exceed the capacity %lld",
+                (long long)d->rows, (long long)n, (long long)d->capacity);
+    if (src_rows_dev == nullptr)
+        CMW_REQUIRE(src_row0 >= 0 && src_row0 + n <= s->rows, "cmw_store_copy_rows: rows [%lld, %lld) out of range",
+                    (long long)src_row0, (long long)(src_row0 + n));
+    CMW_CUDA_OK(cudaSetDevice(d->device));
+    const int warps_per_block = 8;
+    int64_t blocks = (n + warps_per_block - 1) / warps_per_block;
+    const int64_t max_blocks = (int64_t)d->sm_count * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    const float* base = src_rows_dev ? s->f32 : s->f32 + (size_t)src_row0 * s->dim;
+    const int32_t* gid = src_rows_dev ? s->kb_gid : s->kb_gid + src_row0;
+    ingest_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(
+        base, gid, src_rows_dev, n, d->dim, d->rows, d->f32, d->bf16, d->half_tiles ? 1 : 0, d->inv_norm, d->norm,
+        d->live, d->norm64, d->kb_gid, d->maxnorm_bits);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    d->rows += n;
     return 0;
 }
 

@@ -138,6 +138,26 @@ class DenseStore:
         N.check(lib.cmw_store_append_host_f32(self._h, arr.ctypes.data, gid_ptr, arr.shape[0]),
                 "cmw_store_append_host_f32")
 
+    def copy_rows_from(self, src: "DenseStore", rows=None, row0: int = 0, n: int | None = None) -> None:
+        """Append rows of ``src`` (same GPU) to this store without leaving the device: ``rows`` = LOCAL row numbers
+        of ``src`` (array / tensor), or the contiguous range [row0, row0 + n).  K0 rebuilds tiles and norms."""
+        torch = _torch()
+        dev = torch.device(f"cuda:{self.device}")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if rows is not None:
+            idx = torch.as_tensor(np.asarray(rows, dtype=np.int64) if not isinstance(rows, torch.Tensor) else rows,
+                                  dtype=torch.int64, device=dev).contiguous()
+            if idx.numel():
+                N.check(N.lib().cmw_store_copy_rows(self._h, src._h, idx.data_ptr(), 0, idx.numel(), stream),
+                        "cmw_store_copy_rows")
+                torch.cuda.current_stream(dev).synchronize()  # the index tensor must outlive the kernel
+            return
+        n = src.rows - row0 if n is None else n
+        if n:
+            N.check(N.lib().cmw_store_copy_rows(self._h, src._h, None, int(row0), int(n), stream),
+                    "cmw_store_copy_rows")
+            torch.cuda.current_stream(dev).synchronize()  # the caller may close `src` right away
+
     def read_rows(self, row0: int, n: int, rows: bool = True):
         """Read LOCAL rows back: (f32 [n, dim] or None, kb_gid i32[n], live bool[n])."""
         out = np.empty((n, self.dim), np.float32) if rows else None

@@ -91,6 +91,10 @@ class B200Store:
         keep_bf16: bool = True,  # keep the 16-bit tiles (tensor-core filter); their format is `tiles16`
         id_offset: int = 0,
         tiles16: str = "f16",
+        batch_window_us: float = 250.0,  # bounded gather window of the micro-batching front-end (batcher.py)
+        max_batch: int = 64,
+        max_queue: int = 4096,
+        auto_compact: float | None = None,  # compact() by itself once this fraction of the rows is tombstoned
     ):
         self.collection_name = collection_name
         self.host = host
@@ -117,13 +121,15 @@ class B200Store:
         self._eq_index: dict[str, dict[Any, list[int]]] = {key: {} for key in self.INDEXED_KEYS}
         self._gid_of_key: dict[str, int] = {}
         self._key_of_gid: list[str] = []
-        # micro-batching of concurrent awaits
+        # micro-batching of concurrent callers: awaits of one event-loop tick are handed over as a group, and the
+        # batcher (its own dispatcher thread, bounded window / batch / queue, histograms) merges groups, ticks,
+        # threads and requests into launches
         self._pending: list[tuple[np.ndarray, int, asyncio.Future]] = []
-        import concurrent.futures
-
-        self._executor = concurrent.futures.ThreadPoolExecutor(max_workers=2, thread_name_prefix="b200store")
         self._flush_scheduled = False
-        self.stats = {"searches": 0, "launch_batches": 0, "max_batch": 0, "uncertified": 0}
+        self._batch_cfg = (int(max_batch), float(batch_window_us), int(max_queue))
+        self._batcher_obj = None
+        self._auto_compact = auto_compact
+        self._uncertified = 0
 
     # -- plumbing -----------------------------------------------------------------------------
     def _ensure(self, dim: int) -> DenseStore:
@@ -151,6 +157,42 @@ class B200Store:
 
     def count(self) -> int:
         return self._n_alive
+
+    @property
+    def batcher(self):
+        """The micro-batching front-end of this collection (created on first use)."""
+        if self._batcher_obj is None:
+            with self._lock:
+                if self._batcher_obj is None:
+                    from .batcher import SearchBatcher
+
+                    mb, win, mq = self._batch_cfg
+                    self._batcher_obj = SearchBatcher(lambda q, kmax: self.search(q, kmax), max_batch=mb,
+                                                      max_wait_us=win, max_queue=mq,
+                                                      name=f"b200store_{self.collection_name}")
+        return self._batcher_obj
+
+    @property
+    def stats(self) -> dict:
+        b = self._batcher_obj
+        c = b.counters if b is not None else {"requests": 0, "launches": 0}
+        return {"searches": c["requests"], "launch_batches": c["launches"],
+                "max_batch": int(b.h_batch.max) if b is not None else 0, "uncertified": self._uncertified}
+
+    def metrics(self) -> dict:
+        """Queue depth / batch size / latency histograms of the seam + collection gauges."""
+        m = self.batcher.metrics()
+        m["collection"] = {"name": self.collection_name, "rows": len(self._ids), "live_rows": self._n_alive,
+                           "uncertified_queries": self._uncertified}
+        return m
+
+    def close(self) -> None:
+        if self._batcher_obj is not None:
+            self._batcher_obj.close()
+            self._batcher_obj = None
+        if self._dense is not None:
+            self._dense.close()
+            self._dense = None
 
     def _index_row(self, row: int, meta: dict[str, Any] | None) -> None:
         if not meta:
@@ -233,10 +275,10 @@ class B200Store:
                 self._index_row(base + j, metadatas[i])
             self._n_alive += len(keep)
 
-    def _grow(self, needed: int, chunk_rows: int = 65536) -> DenseStore:
+    def _grow(self, needed: int) -> DenseStore:
         """A Chroma collection grows without bound; the HBM store is sized up front.  When an add would
-        overflow it, a store twice as large is created and the rows are copied over through the
-        read-back entry point (tombstones replayed).  Needs the fp32 tiles."""
+        overflow it, a store twice as large is created and the rows are re-ingested device to device
+        (cmw_store_copy_rows: no host round trip), tombstones replayed.  Needs the fp32 tiles."""
         if not self._keep[0]:
             raise RuntimeError(f"collection is full ({self._capacity} rows) and keeps no fp32 tiles to grow from")
         new_cap = max(needed, 2 * self._capacity)
@@ -244,10 +286,7 @@ class B200Store:
         new = DenseStore(self._pdim, new_cap, device=self._device, f32=self._keep[0], bf16=self._keep[1],
                          id_offset=self._id_offset, tiles16=self._tiles16)
         n = len(self._ids)
-        for lo in range(0, n, chunk_rows):
-            m = min(chunk_rows, n - lo)
-            rows, gid, _ = old.read_rows(lo, m)
-            new.append(rows, gid)
+        new.copy_rows_from(old, row0=0, n=n)
         dead = [r for r, alive in enumerate(self._alive) if not alive]
         if dead:
             new.tombstone(dead)
@@ -267,9 +306,10 @@ class B200Store:
                     break
         return out
 
-    def compact(self, chunk_rows: int = 65536) -> int:
-        """Drop tombstoned rows physically (they cost scan bandwidth until then): the live rows are copied,
-        in order, into a fresh HBM store through the read-back entry point and the sidecar is renumbered.
+    def compact(self) -> int:
+        """Drop tombstoned rows physically (they cost scan bandwidth until then): the live rows are re-ingested,
+        in order and device to device (cmw_store_copy_rows with a gather index), into a fresh HBM store and the
+        sidecar is renumbered.
         Row numbers returned by :meth:`search` change; string ids, documents and metadata do not.  Returns
         the number of rows reclaimed.  Needs the fp32 tiles."""
         with self._lock:
@@ -283,12 +323,7 @@ class B200Store:
             new = DenseStore(self._pdim, self._capacity, device=self._device, f32=self._keep[0], bf16=self._keep[1],
                              id_offset=self._id_offset, tiles16=self._tiles16)
             alive = np.asarray(self._alive, bool)
-            for lo in range(0, n, chunk_rows):
-                m = min(chunk_rows, n - lo)
-                keep = alive[lo:lo + m]
-                if keep.any():
-                    rows, gid, _ = old.read_rows(lo, m)
-                    new.append(np.ascontiguousarray(rows[keep]), gid[keep])
+            new.copy_rows_from(old, rows=np.flatnonzero(alive))
             old.close()
             self._dense = new
             live_rows = np.flatnonzero(alive).tolist()
@@ -320,6 +355,10 @@ class B200Store:
                 self._docs[r] = None
                 self._metas[r] = None  # its index entries stay behind and are skipped by the alive check
             self._n_alive -= len(rows)
+            n_all = len(self._ids)
+            if (self._auto_compact is not None and n_all >= 4096 and self._keep[0]
+                    and n_all - self._n_alive > self._auto_compact * n_all):
+                self.compact()  # tombstones cost scan bandwidth and thin out the first slabs: reclaim them
             return len(rows)
 
     def get(self, where=None, ids=None, include=("metadatas", "documents"), limit=None) -> dict:
@@ -376,7 +415,7 @@ class B200Store:
         PROVEN identical to the exact answer: count it and say so -- never pass it on silently."""
         bad = int(np.count_nonzero(flags))
         if bad:
-            self.stats["uncertified"] += bad
+            self._uncertified += bad
             log.warning("B200Store[%s]: %d of %d queries came back CMW_FLAG_UNCERTIFIED after the repair chain "
                         "(candidate pool overflow or unbreakable ties); results are the best rescored candidates",
                         self.collection_name, bad, len(flags))
@@ -415,18 +454,16 @@ class B200Store:
             res["distances"] = dists
         return res
 
-    def _search_docs(self, q: np.ndarray, kmax: int, ks: list[int]) -> list[list[RetrievedDoc]]:
-        _, ids, _ = self.search(q, kmax)
-        return [self._docs_for(ids[i, :k]) for i, k in enumerate(ks)]
-
     def similarity_search(self, query_embedding, k: int = 5) -> list[RetrievedDoc]:
-        _, ids, _ = self.search([query_embedding], k)
-        return self._docs_for(ids[0])
+        """Blocking form; concurrent callers (threads) share launches through the batcher."""
+        _, ids, _ = self.batcher.search_one(np.asarray(query_embedding, dtype=np.float32), int(k))
+        return self._docs_for(ids)
 
     async def similarity_search_async(self, query_embedding: list[float], k: int = 5) -> list[RetrievedDoc]:
-        """Same contract as ChromaStore.similarity_search_async (vector_store.py:54-66).  Awaits
-        issued in the same event-loop tick (asyncio.gather over segments, retriever.py:179-182)
-        share one batched kernel launch."""
+        """Same contract as ChromaStore.similarity_search_async (vector_store.py:54-66).  Awaits issued in the
+        same event-loop tick (asyncio.gather over segments, retriever.py:179-182) are handed to the batcher as one
+        group; the batcher merges groups from different ticks, threads and requests inside its bounded window.
+        The event loop is never blocked: the launch runs on the batcher's thread."""
         loop = asyncio.get_running_loop()
         fut: asyncio.Future = loop.create_future()
         self._pending.append((np.asarray(query_embedding, dtype=np.float32), int(k), fut))
@@ -436,25 +473,29 @@ class B200Store:
         return await fut
 
     async def _flush(self) -> None:
-        batch, self._pending = self._pending, []
+        from .batcher import QueueFull
+
+        group, self._pending = self._pending, []
         self._flush_scheduled = False
-        if not batch:
+        if not group:
             return
         try:
-            kmax = max(k for _, k, _ in batch)
-            q = np.stack([v for v, _, _ in batch])
-            self.stats["searches"] += len(batch)
-            self.stats["launch_batches"] += 1
-            self.stats["max_batch"] = max(self.stats["max_batch"], len(batch))
-            # the search runs on a worker thread of the store's own (the event loop is never blocked); the
-            # documents are materialised there too, the loop only hands them to the waiting futures
-            loop = asyncio.get_running_loop()
-            docs = await loop.run_in_executor(self._executor, self._search_docs, q, kmax, [k for _, k, _ in batch])
-            for (_, _, fut), d in zip(batch, docs):
-                if not fut.done():
-                    fut.set_result(d)
-        except Exception as exc:  # propagate like a chromadb error would (retrieve_context.py:435-449)
-            for _, _, fut in batch:
+            while True:
+                try:
+                    futs = self.batcher.submit_many([v for v, _, _ in group], [k for _, k, _ in group])
+                    break
+                except QueueFull:  # back-pressure without blocking the loop
+                    await asyncio.sleep(0.001)
+            results = await asyncio.gather(*[asyncio.wrap_future(f) for f in futs], return_exceptions=True)
+            for (_, _, fut), res in zip(group, results):
+                if fut.done():
+                    continue
+                if isinstance(res, BaseException):  # propagate like a chromadb error would (retrieve_context.py:435-449)
+                    fut.set_exception(res)
+                else:
+                    fut.set_result(self._docs_for(res[1]))
+        except Exception as exc:
+            for _, _, fut in group:
                 if not fut.done():
                     fut.set_exception(exc)
 

@@ -112,6 +112,12 @@ int cmw_store_append_f32(cmw_store* s, const float* rows_dev, const int32_t* kb_
                          void* stream);
 int cmw_store_append_host_f32(cmw_store* s, const float* rows_host, const int32_t* kb_gid_host,
                               int64_t n);
+/* Device-to-device re-ingest (store maintenance without a host round trip: growing a full collection, dropping
+ * tombstoned rows physically): appends n rows of `src` to `dst` -- the contiguous range [src_row0, src_row0 + n), or
+ * the LOCAL row numbers src_rows_dev i64[n] (valid rows of src; the caller picks the live ones) -- with their
+ * kb_gid; tiles and norms are rebuilt by K0 in dst's own formats.  Same device, same dim; src needs fp32 tiles. */
+int cmw_store_copy_rows(cmw_store* dst, const cmw_store* src, const int64_t* src_rows_dev, int64_t src_row0,
+                        int64_t n, void* stream);
 /* replaces collection.delete(where=...) of vector_store.py:102-105 once the host has resolved the
  * filter to row numbers (LOCAL rows, i.e. without id_offset).  Tombstoned rows are never returned. */
 int cmw_store_tombstone(cmw_store* s, const int64_t* rows_dev, int64_t n, void* stream);

@@ -118,7 +118,10 @@ def main():
         async def similarity_search_async(self, query_embedding, k=5):
             q = np.asarray(query_embedding, np.float32)[None, :]
             ids, sc, _ = exact_topk(corpus, q, k)
-            calls.append({"k": int(k), "ids": ids[0].tolist(), "scores": [float(x) for x in sc[0]]})
+            calls.append({"k": int(k), "ids": ids[0].tolist(), "scores": [float(x) for x in sc[0]],
+                          # the embedding the reference handed to the store: lets the GPU box replay the case
+                          # through the CUDA backend without importing the reference
+                          "query": [float(x) for x in q[0]]})
             return [
                 Doc(int(r), float(s), {"stable_id": f"{int(r):012d}", "kbId": kb[int(r)], "source_file": art_file}, f"chunk {r}")
                 for r, s in zip(ids[0], sc[0])

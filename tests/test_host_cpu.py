@@ -120,6 +120,14 @@ class FakeDense:
     def read_rows(self, row0, n, rows=True):
         return self.rows_[row0:row0 + n].copy(), self.gid[row0:row0 + n].copy(), self.live[row0:row0 + n].copy()
 
+    def copy_rows_from(self, src, rows=None, row0=0, n=None):
+        idx = np.asarray(rows, np.int64) if rows is not None else np.arange(row0, row0 + (len(src.rows_) - row0 if n is None else n))
+        self.append(src.rows_[idx], src.gid[idx])
+
+    @property
+    def rows(self):
+        return len(self.rows_)
+
     def search_host(self, q, k, metric="cosine", mode="f32", algo=None):
         self.calls.append(q.shape[0])
         ids, sc, _ = exact_topk(self.rows_, q, k, metric=metric, live=self.live, id_offset=self.id_offset)
