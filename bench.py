@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--tiles16", default="f16", choices=["f16", "bf16"],
                     help="format of the 16-bit tiles the tensor-core filter reads (same bytes, same tensor rate)")
+    ap.add_argument("--f16-bits", type=int, default=0, help="experiment: significand bits kept in fp16 tiles (8..11)")
     ap.add_argument("--shard", default="rows", choices=["rows", "queries"],
                     help="N > 1: row-sharded corpus + exchange + merge (default), or replicated corpus, sharded batch")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
@@ -534,6 +535,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     row_shard = args.shard == "rows" and world > 1
     k, B = args.k, args.batch
+    if args.f16_bits:
+        N.set_option("f16_bits", args.f16_bits)
 
     # ---- corpus -----------------------------------------------------------------------------
     if row_shard:
@@ -730,6 +733,10 @@ def run_ours(args):
                 "tiles16": args.tiles16, "qps": B * 1e3 / float(np.mean(lat)),
                 "recall_at_k": float(np.mean([len(np.intersect1d(ids_bh[i], ids0_h[i])) / k for i in range(B)])),
                 "max_abs_score_err_vs_exact": float((sc_b - sc0).abs().max().item()), "tolerance": 2e-3}
+        # a store WITHOUT 16-bit tiles (the north star's config 2 read literally: "1M x 1536 fp32 corpus"): the
+        # filter reads the fp32 rows through kind::tf32 MMAs -- one pass whatever the batch (K1: one per 4 queries)
+        if not args.no_f32:
+            extras["fp32_only_store"] = fp32_only_record(torch, N, args, device, q, ids0_h)
         if args.sustained_seconds > 0:
             time.sleep(args.leg_gap)
             extras["sustained"] = sustained_record(torch, N, st, q, k, args, device, dev_ms / args.steps, shard_rows,
@@ -914,7 +921,8 @@ def run_ours(args):
             "l2": "inputs larger than L2 (16-bit tiles >= 3 GB per pass vs 126 MB at N = 1; at N > 1 a shard's tiles "
                   "are re-read from HBM every step all the same: the per-step pools and candidates, 0.3 GB, evict them), "
                   "no flush",
-            "mode": args.mode, "algo": args.algo, "tiles16": args.tiles16, "uncertified_queries": uncertified,
+            "mode": args.mode, "algo": args.algo, "tiles16": args.tiles16, "f16_bits": int(N.get_option("f16_bits")),
+            "uncertified_queries": uncertified,
             "certificate": "rigorous" if N.get_option("strict_certificate") else "statistical",
         },
         "clocks": clocks,
@@ -952,6 +960,36 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def fp32_only_record(torch, N, args, device, q, ids_ref_h):
+    from cmw_rag_b200 import DenseStore
+
+    k = args.k
+    st3 = DenseStore(args.dim, args.rows, device=device.index, f32=True, bf16=False)
+    for g0, x in gen_rows(torch, device, args.dim, 0, args.rows):
+        st3.append(x)
+    peaks = measured_peaks()
+    floor_ms = args.rows * (args.dim * 4 + 4) / (peaks["hbm_gbs"] * 1e9) * 1e3
+    out = {"rows": args.rows, "filter": "kind::tf32 MMAs over the fp32 tiles (gemm_topk_kernel)",
+           "hbm_floor_ms_per_batch": floor_ms, "points": []}
+    for b in (1, 4, 16, 64):
+        qb = q[:b].contiguous()
+        for _ in range(5):
+            sc, ids, fl = st3.search(qb, k, mode="f32")
+        torch.cuda.synchronize(device)
+        assert (ids.cpu().numpy() == ids_ref_h[:b]).all() and int(fl.sum()) == 0, "tf32 filter: wrong or flagged"
+        lat = timed_search_loop(torch, lambda: st3.search(qb, k, mode="f32"), 50, device)
+        scan = None
+        if b <= 16:
+            for _ in range(3):
+                st3.search(qb, k, mode="f32", algo="scan")
+            scan = float(np.median(timed_search_loop(torch, lambda: st3.search(qb, k, mode="f32", algo="scan"), 20, device)))
+        out["points"].append({"batch": b, "p50_ms": float(np.median(lat)), "p99_ms": float(np.percentile(lat, 99)),
+                              "hbm_floor_frac": floor_ms / float(np.median(lat)), "k1_scan_p50_ms": scan})
+    out["batch16_over_batch1"] = out["points"][2]["p50_ms"] / out["points"][0]["p50_ms"]
+    st3.close()
+    return out
 
 
 def bf16_tiles_record(torch, N, args, device, q, ids_ref_h, sc_ref):

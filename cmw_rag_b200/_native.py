@@ -20,6 +20,7 @@ MODE_BF16 = 1
 ALGO_AUTO = 0 << 8
 ALGO_SCAN = 1 << 8
 ALGO_GEMM = 2 << 8
+ALGO_GEMM_TF32 = 3 << 8
 SLABS_SAFE = 1 << 16
 KPRIME_MAX = 1 << 17
 STORE_F32 = 1
@@ -34,7 +35,7 @@ METRICS = {"cosine": METRIC_COSINE, "ip": METRIC_IP, METRIC_COSINE: METRIC_COSIN
 MODES = {"f32": MODE_F32_EXACT, "exact": MODE_F32_EXACT, "bf16": MODE_BF16,
          MODE_F32_EXACT: MODE_F32_EXACT, MODE_BF16: MODE_BF16}
 ALGOS = {"auto": ALGO_AUTO, "scan": ALGO_SCAN, "gemm": ALGO_GEMM, None: ALGO_AUTO,
-         "scan_safe": ALGO_SCAN | SLABS_SAFE, "gemm_safe": ALGO_GEMM | SLABS_SAFE}
+         "gemm_tf32": ALGO_GEMM_TF32, "scan_safe": ALGO_SCAN | SLABS_SAFE, "gemm_safe": ALGO_GEMM | SLABS_SAFE}
 
 
 class StoreInfo(ctypes.Structure):

@@ -27,7 +27,7 @@ namespace cmw {
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-    size_t qn64, q4, qres, q_f32, q_bf16, pool_scores, pool_ids, pool_cnt, pool_thr, pool_ovf, exact, wide, total;
+    size_t qn64, q4, qres, q_f32, q_bf16, q_tf32, pool_scores, pool_ids, pool_cnt, pool_thr, pool_ovf, exact, wide, total;
     int bpad;
 };
 
@@ -37,7 +37,7 @@ static int pad_batch(int batch) {
     return (int)align_up((size_t)batch, 256);
 }
 
-static WsLayout ws_layout(int dim, int batch, int kprime) {
+static WsLayout ws_layout(int dim, int batch, int kprime, bool tf32 = true) {
     WsLayout w;
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -51,6 +51,7 @@ static WsLayout ws_layout(int dim, int batch, int kprime) {
     w.qres = take((size_t)batch * sizeof(double));
     w.q_f32 = take((size_t)batch * dim * sizeof(float));
     w.q_bf16 = take((size_t)w.bpad * dim * sizeof(__nv_bfloat16));
+    w.q_tf32 = take(tf32 ? (size_t)w.bpad * dim * sizeof(float) : 0);  // only stores that filter through tf32 MMAs
     w.pool_scores = take((size_t)batch * kPoolCap * sizeof(float));
     w.pool_ids = take((size_t)batch * kPoolCap * sizeof(int32_t));
     w.pool_cnt = take((size_t)w.bpad * sizeof(int32_t));
@@ -66,11 +67,19 @@ static WsLayout ws_layout(int dim, int batch, int kprime) {
     return w;
 }
 
+// does this search filter with fp32 rows through kind::tf32 MMAs?  Exact mode only (the tf32 filter has no
+// approximate-mode meaning), when asked for (CMW_ALGO_GEMM_TF32) or when the store keeps no 16-bit tiles
+static bool want_tf32(const Store* s, int mode) {
+    if ((mode & 0xff) != CMW_MODE_F32_EXACT || !gemm_tf32_supported(s)) return false;
+    const int algo = mode & 0xff00;
+    return algo == CMW_ALGO_GEMM_TF32 || (algo != CMW_ALGO_SCAN && !gemm_supported(s));
+}
+
 static bool use_gemm(const Store* s, const Options& opt, int batch, int mode) {
     const int algo = mode & 0xff00;
     if (algo == CMW_ALGO_SCAN) return false;
-    if (!gemm_supported(s)) return false;
-    if (algo == CMW_ALGO_GEMM) return true;
+    if (!gemm_supported(s) && !want_tf32(s, mode)) return false;
+    if (algo == CMW_ALGO_GEMM || algo == CMW_ALGO_GEMM_TF32) return true;
     return opt.gemm_enabled != 0 && batch > (int)opt.scan_max_batch;
 }
 
@@ -210,6 +219,7 @@ static int repair_flagged(cmw_store* h, Store* s, cudaStream_t stream, const Hos
     const int32_t* fl = reinterpret_cast<const int32_t*>(pin + io.q_bytes + io.sc_bytes + io.id_bytes);
     const bool exact = (mode & 0xff) == CMW_MODE_F32_EXACT;
     const bool first_was_gemm = use_gemm(s, g_opt, batch, mode);
+    if ((mode & 0xff00) == CMW_ALGO_GEMM_TF32) mode = (mode & ~0xff00) | CMW_ALGO_AUTO;  // repairs choose their own filter
     int stages[2];
     int nstage = 0;
     if (g_opt.repair >= 1 && !((mode & CMW_SLABS_SAFE) && (mode & CMW_KPRIME_MAX)))
@@ -335,7 +345,7 @@ size_t cmw_search_workspace_bytes(const cmw_store* h, int batch, int k, int mode
     (void)mode;
     (void)k;
     // sized for the largest K' so that option changes between the query and the call stay safe
-    return ws_layout(s->dim, batch, kMaxKPrime).total;
+    return ws_layout(s->dim, batch, kMaxKPrime, gemm_tf32_supported(s)).total;
 }
 
 }  // extern "C"
@@ -353,9 +363,11 @@ struct SearchPlan {
     Options opt;  // snapshot: cmw_set_option during a search must not change what its later slabs do
     int batch, k, metric, mode, base_mode, kprime;
     bool gemm;
+    bool tf32;  // the gemm filter reads the fp32 tiles through kind::tf32 MMAs
     WsLayout w;
     double *qn64, *q4, *qres, *exact;
     float* q_f32;
+    float* q_tf32;
     __nv_bfloat16* q_bf16;
     Pool pool;
     uint8_t* ws;
@@ -384,11 +396,13 @@ static int make_plan(SearchPlan& pl, cmw_store* h, const float* queries_dev, int
     pl.mode = mode;
     pl.base_mode = base_mode;
     pl.gemm = use_gemm(s, pl.opt, batch, mode);
-    if ((mode & 0xff00) == CMW_ALGO_GEMM)
-        CMW_REQUIRE(pl.gemm, "%s: CMW_ALGO_GEMM requested but the tcgen05 path is unavailable "
-                             "(store without bf16 tiles or TMA descriptor)", who);
-    pl.kprime = pick_kprime(pl.opt, k, mode, pl.gemm, s->half_tiles);
-    pl.w = ws_layout(s->dim, batch, pl.kprime);
+    pl.tf32 = pl.gemm && want_tf32(s, mode);
+    if ((mode & 0xff00) == CMW_ALGO_GEMM || (mode & 0xff00) == CMW_ALGO_GEMM_TF32)
+        CMW_REQUIRE(pl.gemm && (pl.tf32 || (mode & 0xff00) == CMW_ALGO_GEMM),
+                    "%s: a tcgen05 filter was requested but is unavailable (store without the tiles it reads, "
+                    "no TMA descriptor, or tf32 outside CMW_MODE_F32_EXACT)", who);
+    pl.kprime = pick_kprime(pl.opt, k, mode, pl.gemm, pl.tf32 || (s->half_tiles && s->half_bits >= 10));
+    pl.w = ws_layout(s->dim, batch, pl.kprime, gemm_tf32_supported(s));
     CMW_REQUIRE(ws_dev != nullptr && ws_bytes >= pl.w.total, "%s: workspace too small (%zu bytes given, %zu needed)",
                 who, ws_bytes, pl.w.total);
     CMW_REQUIRE((reinterpret_cast<uintptr_t>(ws_dev) & 255) == 0, "%s: workspace must be 256-byte aligned", who);
@@ -399,6 +413,7 @@ static int make_plan(SearchPlan& pl, cmw_store* h, const float* queries_dev, int
     pl.qres = reinterpret_cast<double*>(ws + pl.w.qres);
     pl.q_f32 = reinterpret_cast<float*>(ws + pl.w.q_f32);
     pl.q_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.w.q_bf16);
+    pl.q_tf32 = reinterpret_cast<float*>(ws + pl.w.q_tf32);
     pl.pool.scores = reinterpret_cast<float*>(ws + pl.w.pool_scores);
     pl.pool.ids = reinterpret_cast<int32_t*>(ws + pl.w.pool_ids);
     pl.pool.cnt = reinterpret_cast<int32_t*>(ws + pl.w.pool_cnt);
@@ -450,7 +465,7 @@ static int run_filter_half(const SearchPlan& pl, const float* queries_dev, cudaS
     // threshold is the kprime-th best of those.  K2 scans a stride permutation of the tiles, so its slabs see the
     // store-wide live fraction; K1 (and small stores) scan in storage order, where the tombstones may sit in one
     // block -- a re-indexed collection is exactly that -- and the per-block counts give the exact number.
-    const bool permuted = gemm && gemm_scan_permuted(s, opt, w.bpad);
+    const bool permuted = gemm && gemm_scan_permuted(s, opt, w.bpad, pl.tf32);
     const double live_frac = rows > 0 ? (double)(rows - s->dead) / (double)rows : 1.0;
     auto live_seen = [&](int64_t seen) -> double {
         if (s->dead == 0) return (double)seen;
@@ -478,13 +493,14 @@ static int run_filter_half(const SearchPlan& pl, const float* queries_dev, cudaS
     {
         PhaseTimer t(3, stream);
         if ((rc = launch_prep_queries(queries_dev, batch, w.bpad, s->dim, metric, pl.qn64, pl.q4, pl.qres, pl.q_f32,
-                                      gemm ? pl.q_bf16 : nullptr, s->half_tiles ? 1 : 0, pool, wide ? 0 : (int)slab0,
-                                      seg, (int)slab0, stream)))
+                                      (gemm && !pl.tf32) ? pl.q_bf16 : nullptr, s->half_tiles ? s->half_bits : 0,
+                                      pl.tf32 ? pl.q_tf32 : nullptr, pool, wide ? 0 : (int)slab0, seg, (int)slab0,
+                                      stream)))
             return rc;
     }
 
     // which tiles the filter reads, and the per-row multiplier that goes with them
-    const bool filter_bf16 = gemm || pl.base_mode == CMW_MODE_BF16;
+    const bool filter_bf16 = (gemm && !pl.tf32) || pl.base_mode == CMW_MODE_BF16;
     const void* tiles = filter_bf16 ? (const void*)s->bf16 : (const void*)s->f32;
     const float* row_mul;
     if (filter_bf16) row_mul = (metric == CMW_METRIC_COSINE) ? s->live : s->norm;  // rows pre-normalised
@@ -507,13 +523,15 @@ static int run_filter_half(const SearchPlan& pl, const float* queries_dev, cudaS
             g.wide_ids = wide_ids;
             g.wide_stride = kWideDenseRows;
             g.opt = &opt;
+            g.tf32 = pl.tf32 ? 1 : 0;
+            g.q_tf32 = pl.q_tf32;
             return launch_gemm(g, stream);
         }
         for (int b0 = 0; b0 < batch; b0 += kScanMaxQueries) {
             ScanArgs a;
             a.rows = tiles;
             a.elt_bytes = filter_bf16 ? 2 : 4;
-            a.half_tiles = s->half_tiles ? 1 : 0;
+            a.half_tiles = s->half_tiles ? s->half_bits : 0;
             a.dim = s->dim;
             a.row_mul = row_mul;
             a.row_begin = r0;
@@ -607,7 +625,8 @@ static CertParams make_cert(const SearchPlan& pl, const float* global_kth) {
     cert.eps_fixed = opt.f32_eps > 0 ? opt.f32_eps : (double)(pl.s->dim / 32 + 12) * 5.9604644775390625e-8;
     cert.sigmas = 0.0;
     cert.acc_slack = (double)pl.s->dim * 1.1920928955078125e-7 * 1.01;  // D * 2^-23
-    cert.tile_u = pl.s->half_tiles ? 1.0 / 2048.0 : 1.0 / 256.0;
+    cert.tile_u = pl.tf32 ? 1.0 / 1024.0 : (pl.s->half_tiles ? 1.0 / (double)(1 << pl.s->half_bits) : 1.0 / 256.0);
+    cert.res_slot = pl.tf32 ? 3 : 2;
     if (pl.gemm) {
         if (opt.bf16_eps > 0) {
             cert.eps_fixed = opt.bf16_eps;

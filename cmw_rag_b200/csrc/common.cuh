@@ -112,13 +112,15 @@ struct Store {
     // (results below its smallest normal, 2^-14, are flushed to zero at conversion and counted in the residual)
     __nv_bfloat16* bf16 = nullptr;
     bool half_tiles = false;
+    int half_bits = 11;  // significand bits kept in fp16 tiles (Options::f16_bits at create time)
     float* inv_norm = nullptr;       // [cap4] 1/|c| (0 for a zero row, NaN when tombstoned)
     float* norm = nullptr;           // [cap4] |c|   (NaN when tombstoned)
     float* live = nullptr;           // [cap4] 1.0   (NaN when tombstoned)
     double* norm64 = nullptr;        // [capacity] |c| in fp64
     int32_t* kb_gid = nullptr;       // [capacity]
-    // device scalars (float bits, rounded up): [0] max |c|, [1] max |c/|c||_4, [2] max |c/|c| - bf16(c/|c|)|_2
-    // (the rounding residual of the bf16 tiles: rigorous certificate); [16..17] tombstone counter
+    // device scalars (float bits, rounded up): [0] max |c|, [1] max |c/|c||_4, [2] max |c/|c| - tile16(c/|c|)|_2
+    // (the rounding residual of the 16-bit tiles: rigorous certificate), [3] max |c - tf32_trunc(c)|_2 / |c| (the
+    // same for fp32 rows read by tf32 MMAs); [16..17] tombstone counter
     uint32_t* maxnorm_bits = nullptr;
     // tombstones per block of 256 rows, as the device counted them (dead_blk) and as a host prefix sum
     // (dead_prefix[i] = dead rows among the first 256*i): the slab schedule needs the number of LIVE rows a
@@ -137,9 +139,12 @@ struct Store {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaStream_t tail = nullptr;  // finalisation of a ticket, next to the following ticket's filter
     HostSlot slots[kHostSlots];
-    // TMA descriptor of the bf16 tiles (K2), encoded at create time
+    // TMA descriptors of the 16-bit tiles and of the fp32 tiles (K2; the latter feeds kind::tf32 MMAs on stores
+    // that keep no 16-bit tiles), encoded at create time
     alignas(64) CUtensorMap tmap_bf16;
     bool tmap_ok = false;
+    alignas(64) CUtensorMap tmap_f32;
+    bool tmap_f32_ok = false;
     std::mutex host_mu;  // serialises the *_host entry points, which share the staging resources above
 };
 
@@ -186,6 +191,11 @@ struct Options {
     // K2 scans the row tiles in a stride permutation, so that every slab is a representative sample of the corpus
     double scan_permute = 1;
     double slab_growth = 0;   // 0 = automatic ((cap - K') / (3 K'), at most 8); else the fixed growth factor
+    // Significand bits kept in fp16 tiles (8..11, read when a store is created; its queries follow).  The step is
+    // power-capped and the multiplier array's power grows with the operand width, so fewer bits buy tensor-core
+    // clock at the price of a larger (measured, still rigorous) rounding residual: a tuning knob between bf16's
+    // 8 bits and fp16's 11.
+    double f16_bits = 11;
 };
 extern Options g_opt;
 
@@ -223,13 +233,16 @@ struct GemmArgs {
     int32_t* wide_ids;
     int wide_stride;
     const Options* opt;           // the options snapshot of this search (never g_opt: it may change mid-search)
+    int tf32;                     // 1 = operands are the fp32 tiles / q_tf32, kind::tf32 MMAs (1-CTA kernel)
+    const float* q_tf32;          // [bpad, dim] queries rounded to tf32
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 bool gemm_supported(const Store* s);
-bool gemm_scan_permuted(const Store* s, const Options& o, int bpad);
+bool gemm_tf32_supported(const Store* s);
+bool gemm_scan_permuted(const Store* s, const Options& o, int bpad, bool tf32);
 
 int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64, double* q4,
-                        double* qres, float* q_f32, __nv_bfloat16* q_bf16, int half_tiles, Pool pool,
+                        double* qres, float* q_f32, __nv_bfloat16* q_bf16, int half_tiles, float* q_tf32, Pool pool,
                         int dense_count, Pool seg, int wide_rows, cudaStream_t stream);
 
 // how the certificate / rescoring cut bound is obtained (see Options::bf16_eps)
@@ -243,7 +256,8 @@ struct CertParams {
     const double* q4;       // [B] |q/|q||_4
     const double* qres;     // [B] |q^ - bf16(q^)|_2 relative to |q^| (the query tile's rounding residual)
     const double* qn64;     // [B] |q|
-    const uint32_t* norms;  // store scalars: [0] max |c|, [1] max 4-norm, [2] max bf16 residual (float bits)
+    const uint32_t* norms;  // store scalars: [0] max |c|, [1] max 4-norm, [2] / [3] max row residual (float bits)
+    int res_slot;           // which residual applies: 2 = 16-bit tiles, 3 = fp32 rows read as tf32
     int metric;
     // row-sharded searches: per-query rescoring cut handed in from outside (the k-th best filter score over ALL
     // shards minus 2 eps); NULL = this store's own k-th filter score
@@ -342,7 +356,7 @@ __device__ __forceinline__ double cert_eps(const CertParams& c, int b) {
     double e = c.eps_fixed;
     if (c.kind != CERT_FIXED) {
         const double rq = c.qres[b];
-        const double rc = (double)__uint_as_float(c.norms[2]);
+        const double rc = (double)__uint_as_float(c.norms[c.res_slot]);
         const double rigorous = rq + (1.0 + rq) * rc;  // Cauchy-Schwarz on the two rounding residuals
         e = rigorous;
         if (c.kind == CERT_STATISTICAL) {
@@ -357,9 +371,16 @@ __device__ __forceinline__ double cert_eps(const CertParams& c, int b) {
     return e;
 }
 // fp32 -> one 16-bit tile element; `stored` = the value the tile now holds (what the residuals are measured from)
+// half_tiles: 0 = bf16, else fp16 keeping that many significand bits (11 = all)
 __device__ __forceinline__ uint16_t to_tile16(float x, int half_tiles, float& stored) {
     if (half_tiles) {
         __half h = __float2half_rn(x);
+        if (half_tiles < 11) {  // round the significand to fewer bits (carry into the exponent is what IEEE wants)
+            const unsigned drop = 11u - (unsigned)half_tiles;
+            unsigned short u = __half_as_ushort(h);
+            u = (unsigned short)((u + (1u << (drop - 1))) & ~((1u << drop) - 1u));
+            h = __ushort_as_half(u);
+        }
         float v = __half2float(h);
         if (fabsf(v) < 6.103515625e-05f) {  // below 2^-14: no subnormals in the tiles, whatever the MMA does with them
             h = __ushort_as_half((unsigned short)0);

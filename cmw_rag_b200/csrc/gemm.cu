@@ -97,8 +97,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     uint8_t* sa = stages + (size_t)stage * p.stage_bytes;
                     uint8_t* sb = sa + kABytes;
                     ptx::mbar_arrive_expect_tx(&full[stage], tx_bytes);
-                    ptx::tma_load_2d(sa, &tmap_a, kb * kBlockK, row0, &full[stage], pol_a);
-                    ptx::tma_load_2d(sb, &tmap_b, kb * kBlockK, q0, &full[stage], pol_b);
+                    ptx::tma_load_2d(sa, &tmap_a, kb * p.kb_elems, row0, &full[stage], pol_a);
+                    ptx::tma_load_2d(sb, &tmap_b, kb * p.kb_elems, q0, &full[stage], pol_b);
                     if (++stage == p.nstages) {
                         stage = 0;
                         phase ^= 1u;
@@ -130,9 +130,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (ptx::elect_one()) {
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        // 32 bytes of every operand row per instruction in either format: 16 x 16-bit or 8 x tf32
                         const uint64_t da = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + 2u * k);
                         const uint64_t db = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + 2u * k);
-                        ptx::umma_bf16(d_tmem, da, db, p.idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (p.tf32) ptx::umma_tf32(d_tmem, da, db, p.idesc, (kb | k) != 0 ? 1u : 0u);
+                        else ptx::umma_bf16(d_tmem, da, db, p.idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     ptx::umma_commit(&empty[stage]);  // frees the stage once these MMAs have read it
                     if (kb == p.num_kb - 1) ptx::umma_commit(&tmem_full[acc]);  // accumulator complete
@@ -206,15 +208,16 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D 16-bit (bf16 or fp16) row-major [rows, dim] tensor, box = 64 elements (128 bytes) x box_rows, 128-byte swizzle
-int encode_2d(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows, bool half_tiles) {
+// 2-D row-major [rows, dim] tensor of bf16 / fp16 / fp32 elements, box = 128 bytes x box_rows, 128-byte swizzle
+static int encode_2d_typed(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows,
+                           CUtensorMapDataType dtype, int elt_bytes) {
     EncodeTiledFn fn = get_encode_fn();
     CMW_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dim * (cuuint64_t)elt_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / elt_bytes), (cuuint32_t)box_rows};
     cuuint32_t estride[2] = {1, 1};
-    CUresult r = fn(out, half_tiles ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+    CUresult r = fn(out, dtype, 2,
                     const_cast<void*>(base), gdim, gstride, box,
                     estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -222,12 +225,23 @@ int encode_2d(CUtensorMap* out, const void* base, int64_t rows, int dim, int box
     return 0;
 }
 
+int encode_2d(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows, bool half_tiles) {
+    return encode_2d_typed(out, base, rows, dim, box_rows,
+                           half_tiles ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+}
+
 int encode_bf16_tmap(Store* s) {
     if (s->bf16 == nullptr) return -1;
     return encode_2d(&s->tmap_bf16, s->bf16, s->capacity, s->dim, kTileM, s->half_tiles);
 }
 
+int encode_f32_tmap(Store* s) {
+    if (s->f32 == nullptr) return -1;
+    return encode_2d_typed(&s->tmap_f32, s->f32, s->capacity, s->dim, kTileM, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
+}
+
 bool gemm_supported(const Store* s) { return s->bf16 != nullptr && s->tmap_ok; }
+bool gemm_tf32_supported(const Store* s) { return s->f32 != nullptr && s->tmap_f32_ok; }
 
 int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream);  // gemm2.cu
 
@@ -264,23 +278,26 @@ static bool use_cta_pairs(const Options& o, int bpad) {
 
 // true when the slabs of a multi-slab search scan the store's tiles in the stride permutation (set_scan_order),
 // i.e. every slab is a spread sample of the corpus; false = storage order
-bool gemm_scan_permuted(const Store* s, const Options& o, int bpad) {
-    const int tile_rows = use_cta_pairs(o, bpad) ? 2 * kTileM : kTileM;
+bool gemm_scan_permuted(const Store* s, const Options& o, int bpad, bool tf32) {
+    const int tile_rows = (!tf32 && use_cta_pairs(o, bpad)) ? 2 * kTileM : kTileM;
     return o.scan_permute != 0 && (s->rows + tile_rows - 1) / tile_rows >= 64;
 }
 
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     const Store* s = a.store;
-    CMW_REQUIRE(gemm_supported(s), "launch_gemm: store has no bf16 tiles / TMA descriptor");
+    CMW_REQUIRE(a.tf32 ? gemm_tf32_supported(s) : gemm_supported(s),
+                "launch_gemm: the store lacks the tiles / TMA descriptor this filter reads");
     if (a.row_end <= a.row_begin) return 0;
     if (a.dense)
         CMW_REQUIRE(a.row_end - a.row_begin <= (a.wide_scores ? a.wide_stride : kPoolCap),
                     "launch_gemm: dense slab larger than its destination");
     CMW_REQUIRE((a.row_begin % (2 * kTileM)) == 0, "launch_gemm: slab start must be a multiple of %d rows", 2 * kTileM);
-    if (use_cta_pairs(*a.opt, a.bpad)) return launch_gemm_2cta(a, stream);
+    if (!a.tf32 && use_cta_pairs(*a.opt, a.bpad)) return launch_gemm_2cta(a, stream);
     GemmParams p;
     p.dim = s->dim;
-    p.num_kb = (s->dim + kBlockK - 1) / kBlockK;
+    p.tf32 = a.tf32;
+    p.kb_elems = a.tf32 ? kBlockK / 2 : kBlockK;
+    p.num_kb = (s->dim + p.kb_elems - 1) / p.kb_elems;
     p.nt = a.bpad < kMaxNT ? a.bpad : kMaxNT;
     CMW_REQUIRE(p.nt % 16 == 0 && a.bpad % p.nt == 0, "launch_gemm: bad query padding %d", a.bpad);
     p.n_groups = a.bpad / p.nt;
@@ -302,7 +319,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.dynamic = 0;
     // instruction descriptor: D = f32 (bit 4), A / B format at bits 7 / 10 (0 = fp16, 1 = bf16), both K-major,
     // N >> 3 at bit 17, M >> 4 at bit 24
-    const uint32_t fmt = s->half_tiles ? 0u : 1u;
+    // (2 = tf32: the fp32 rows themselves, narrowed by the tensor core)
+    const uint32_t fmt = a.tf32 ? 2u : (s->half_tiles ? 0u : 1u);
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     p.row_mul = a.row_mul;
     p.pool_scores = a.pool.scores;
@@ -310,7 +328,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.pool_cnt = a.pool.cnt;
     p.pool_thr = a.pool.thr;
     CUtensorMap tmap_b;
-    int rc = encode_2d(&tmap_b, a.q_bf16, a.bpad, s->dim, p.nt, s->half_tiles);
+    int rc = a.tf32 ? encode_2d_typed(&tmap_b, a.q_tf32, a.bpad, s->dim, p.nt, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4)
+                    : encode_2d(&tmap_b, a.q_bf16, a.bpad, s->dim, p.nt, s->half_tiles);
     if (rc) return rc;
     const size_t smem = (size_t)nst * p.stage_bytes + tail + 1024;  // + slack for 1024-byte alignment
     static SmemAttrCache smem_set;
@@ -323,7 +342,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     const int grid = n_items < s->sm_count ? n_items : s->sm_count;
     // 8 epilogue warps for the widest query groups (192 or 256 columns): there the 4-warp epilogue of a tile takes as long as streaming its rows from HBM; narrower groups measured no gain
     const int threads = (p.nt >= 192 && p.nt % 64 == 0) ? kGemmThreadsWide : kGemmThreads;
-    gemm_topk_kernel<<<grid, threads, smem, stream>>>(s->tmap_bf16, tmap_b, p);
+    gemm_topk_kernel<<<grid, threads, smem, stream>>>(a.tf32 ? s->tmap_f32 : s->tmap_bf16, tmap_b, p);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;

@@ -337,6 +337,8 @@ int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
     const Store* s = a.store;
     GemmParams p;
     p.dim = s->dim;
+    p.tf32 = 0;
+    p.kb_elems = kBlockK;
     p.num_kb = (s->dim + kBlockK - 1) / kBlockK;
     p.nt = a.bpad < kMaxNT ? a.bpad : kMaxNT;
     CMW_REQUIRE(p.nt % 64 == 0 && a.bpad % p.nt == 0, "launch_gemm_2cta: bad query padding %d", a.bpad);

@@ -7,7 +7,7 @@
 namespace cmw {
 
 constexpr int kTileM = 128;          // corpus rows per CTA per item (= TMEM lanes)
-constexpr int kBlockK = 64;          // bf16 elements per k-block = one 128-byte swizzle atom
+constexpr int kBlockK = 64;          // 16-bit elements per k-block = one 128-byte swizzle atom (fp32: 32, GemmParams::kb_elems)
 constexpr int kUmmaK = 16;
 constexpr int kMaxNT = 256;
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KB
@@ -40,6 +40,8 @@ struct GemmParams {
     int64_t perm_mul;
     int64_t perm_tiles;
     int dynamic;          // CTA-pair kernel: 1 = work items handed out by cluster launch control
+    int tf32;             // 1-CTA kernel: operands are fp32 rows read by kind::tf32 MMAs (K = 8 per instruction)
+    int kb_elems;         // elements per 128-byte k-block: 64 (16-bit tiles) or 32 (fp32)
     uint32_t idesc;
     const float* row_mul;
     float* pool_scores;

@@ -15,8 +15,8 @@ namespace cmw {
 __global__ void __launch_bounds__(256)
 prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, int metric,
                     double* __restrict__ qn64, double* __restrict__ q4, double* __restrict__ qres,
-                    float* __restrict__ q_f32, __nv_bfloat16* __restrict__ q_bf16, int half_tiles, Pool pool,
-                    int dense_count, Pool seg, int wide_rows) {
+                    float* __restrict__ q_f32, __nv_bfloat16* __restrict__ q_bf16, int half_tiles,
+                    float* __restrict__ q_tf32, Pool pool, int dense_count, Pool seg, int wide_rows) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= bpad) return;
@@ -41,6 +41,10 @@ prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, i
         if (q_bf16 != nullptr) {
             uint2* out = reinterpret_cast<uint2*>(q_bf16 + (size_t)b * dim);
             for (int c = lane; c < nvec; c += 32) out[c] = make_uint2(0u, 0u);
+        }
+        if (q_tf32 != nullptr) {
+            float4* out = reinterpret_cast<float4*>(q_tf32 + (size_t)b * dim);
+            for (int c = lane; c < nvec; c += 32) out[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         return;
     }
@@ -90,6 +94,18 @@ prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, i
             const double dx = ex - (double)sx, dy = ey - (double)sy, dz = ez - (double)sz, dw = ew - (double)sw;
             res2 += dx * dx + dy * dy + dz * dz + dw * dw;
         }
+        if (q_tf32 != nullptr) {
+            // round to nearest even at 10 mantissa bits: exactly representable, so the MMA narrows nothing further
+            auto rn = [](float x) {
+                uint32_t u = __float_as_uint(x);
+                u += 0xfffu + ((u >> 13) & 1u);
+                return __uint_as_float(u & 0xffffe000u);
+            };
+            const float4 t = make_float4(rn(w.x), rn(w.y), rn(w.z), rn(w.w));
+            reinterpret_cast<float4*>(q_tf32 + (size_t)b * dim)[c] = t;
+            const double dx = ex - (double)t.x, dy = ey - (double)t.y, dz = ez - (double)t.z, dw = ew - (double)t.w;
+            res2 += dx * dx + dy * dy + dz * dz + dw * dw;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) res2 += __shfl_xor_sync(0xffffffffu, res2, o);
@@ -97,11 +113,11 @@ prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, i
 }
 
 int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric, double* qn64, double* q4,
-                        double* qres, float* q_f32, __nv_bfloat16* q_bf16, int half_tiles, Pool pool,
+                        double* qres, float* q_f32, __nv_bfloat16* q_bf16, int half_tiles, float* q_tf32, Pool pool,
                         int dense_count, Pool seg, int wide_rows, cudaStream_t stream) {
     const int wpb = 8;
     prep_queries_kernel<<<(bpad + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, batch, bpad, dim, metric, qn64, q4, qres,
-                                                                        q_f32, q_bf16, half_tiles, pool,
+                                                                        q_f32, q_bf16, half_tiles, q_tf32, pool,
                                                                         dense_count, seg, wide_rows);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());

@@ -51,16 +51,24 @@ ingest_kernel(const float* __restrict__ src, const int32_t* __restrict__ gid_src
         // (device-to-device re-ingest gathers its source rows through an index; plain appends read row r)
         const int64_t sr = src_index != nullptr ? src_index[r] : r;
         const float4* in = reinterpret_cast<const float4*>(src + sr * dim);
-        double acc = 0.0;
+        double acc = 0.0, t32 = 0.0;  // t32: |c - c with its low 13 mantissa bits cleared|^2 (what a tf32 MMA drops)
         for (int c = lane; c < nvec; c += 32) {
             float4 v = __ldg(in + c);
             acc += (double)v.x * (double)v.x;
             acc += (double)v.y * (double)v.y;
             acc += (double)v.z * (double)v.z;
             acc += (double)v.w * (double)v.w;
+            const double dx = (double)v.x - (double)__uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+            const double dy = (double)v.y - (double)__uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+            const double dz = (double)v.z - (double)__uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+            const double dw = (double)v.w - (double)__uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            t32 += dx * dx + dy * dy + dz * dz + dw * dw;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            t32 += __shfl_xor_sync(0xffffffffu, t32, o);
+        }
         const double nrm = sqrt(acc);
         const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
         const int64_t dst = row0 + r;
@@ -98,6 +106,9 @@ ingest_kernel(const float* __restrict__ src, const int32_t* __restrict__ gid_src
             atomicMax(maxnorm_bits + 1, __float_as_uint((float)sqrt(sqrt(s4))) + 1u);
             // rounded up, and a hair more for the fp64 arithmetic above (positive floats order like their bits)
             atomicMax(maxnorm_bits + 2, __float_as_uint(__double2float_ru(sqrt(res2) * (1.0 + 1e-9) + 1e-12)));
+            // truncation bounds every round-to-nearest variant element by element, so this holds whichever way
+            // the tensor core narrows fp32 to tf32
+            atomicMax(maxnorm_bits + 3, __float_as_uint(__double2float_ru(sqrt(t32) * inv * (1.0 + 1e-9) + 1e-12)));
             inv_norm[dst] = (float)inv;
             norm[dst] = (float)nrm;
             live[dst] = 1.0f;
@@ -169,6 +180,7 @@ int get_stream(Store* s, cudaStream_t* out) {
 }
 
 int encode_bf16_tmap(Store* s);  // gemm.cu
+int encode_f32_tmap(Store* s);   // gemm.cu
 
 // ---------------------------------------------------------------------------------------------
 // host staging for the *_host entry points
@@ -234,6 +246,7 @@ int cmw_set_option(const char* name, double value) {
     else if (!strcmp(name, "gemm_2cta")) g_opt.gemm_2cta = value;
     else if (!strcmp(name, "gemm_clc")) g_opt.gemm_clc = value;
     else if (!strcmp(name, "gemm_2cta_min_batch")) g_opt.gemm_2cta_min_batch = value;
+    else if (!strcmp(name, "f16_bits")) g_opt.f16_bits = value;
     else {
         set_error("unknown option '%s'", name);
         return -1;
@@ -258,6 +271,7 @@ double cmw_get_option(const char* name) {
     if (!strcmp(name, "gemm_2cta")) return g_opt.gemm_2cta;
     if (!strcmp(name, "gemm_clc")) return g_opt.gemm_clc;
     if (!strcmp(name, "gemm_2cta_min_batch")) return g_opt.gemm_2cta_min_batch;
+    if (!strcmp(name, "f16_bits")) return g_opt.f16_bits;
     if (!strcmp(name, "pool_cap")) return (double)kPoolCap;
     return 0.0;
 }
@@ -306,6 +320,7 @@ int cmw_store_create(int device, int dim, int64_t capacity_rows, uint32_t flags,
     const size_t elems = (size_t)capacity_rows * (size_t)dim;
     if (!rc && (flags & CMW_STORE_F32)) rc = alloc((void**)&s->f32, elems * sizeof(float));
     s->half_tiles = (flags & CMW_STORE_F16) != 0;
+    s->half_bits = (int)g_opt.f16_bits < 8 ? 8 : ((int)g_opt.f16_bits > 11 ? 11 : (int)g_opt.f16_bits);
     if (!rc && (flags & (CMW_STORE_BF16 | CMW_STORE_F16))) rc = alloc((void**)&s->bf16, elems * sizeof(__nv_bfloat16));
     if (!rc) rc = alloc((void**)&s->inv_norm, cap4 * sizeof(float));
     if (!rc) rc = alloc((void**)&s->norm, cap4 * sizeof(float));
@@ -332,6 +347,7 @@ int cmw_store_create(int device, int dim, int64_t capacity_rows, uint32_t flags,
         // a failed encode only disables K2 (the store stays usable through K1); reported by info
         s->tmap_ok = (encode_bf16_tmap(s) == 0);
     }
+    if (!rc && s->f32 != nullptr) s->tmap_f32_ok = (encode_f32_tmap(s) == 0);
     if (rc) {
         cmw_store_destroy(reinterpret_cast<cmw_store*>(s));
         return rc;
@@ -382,7 +398,7 @@ int cmw_store_get_info(const cmw_store* h, cmw_store_info* out) {
     const Store* s = reinterpret_cast<const Store*>(h);
     out->device = s->device;
     out->dim = s->dim;
-    out->flags = s->flags | (s->tmap_ok ? 0x100u : 0u);
+    out->flags = s->flags | ((s->tmap_ok || s->tmap_f32_ok) ? 0x100u : 0u) | (s->tmap_f32_ok ? 0x200u : 0u);
     out->sm_count = s->sm_count;
     out->capacity_rows = s->capacity;
     out->rows = s->rows;
@@ -409,7 +425,7 @@ int cmw_store_append_f32(cmw_store* h, const float* rows_dev, const int32_t* kb_
     const int64_t max_blocks = (int64_t)s->sm_count * 16;
     if (blocks > max_blocks) blocks = max_blocks;
     ingest_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(
-        rows_dev, kb_gid_dev, nullptr, n, s->dim, s->rows, s->f32, s->bf16, s->half_tiles ? 1 : 0, s->inv_norm, s->norm, s->live,
+        rows_dev, kb_gid_dev, nullptr, n, s->dim, s->rows, s->f32, s->bf16, s->half_tiles ? s->half_bits : 0, s->inv_norm, s->norm, s->live,
         s->norm64, s->kb_gid, s->maxnorm_bits);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
@@ -441,7 +457,7 @@ int cmw_store_copy_rows(cmw_store* dst_h, const cmw_store* src_h, const int64_t*
     const float* base = src_rows_dev ? s->f32 : s->f32 + (size_t)src_row0 * s->dim;
     const int32_t* gid = src_rows_dev ? s->kb_gid : s->kb_gid + src_row0;
     ingest_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(
-        base, gid, src_rows_dev, n, d->dim, d->rows, d->f32, d->bf16, d->half_tiles ? 1 : 0, d->inv_norm, d->norm,
+        base, gid, src_rows_dev, n, d->dim, d->rows, d->f32, d->bf16, d->half_tiles ? d->half_bits : 0, d->inv_norm, d->norm,
         d->live, d->norm64, d->kb_gid, d->maxnorm_bits);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());

@@ -53,6 +53,9 @@ extern "C" {
 #define CMW_ALGO_SCAN (1 << 8) /* K1: TMA-staged streaming dot product, 1-4 queries per pass (HBM-bound);
                                   F32_EXACT scans the fp32 tiles, BF16 the bf16 tiles */
 #define CMW_ALGO_GEMM (2 << 8) /* K2: tcgen05/TMEM GEMM with fused top-k epilogue */
+#define CMW_ALGO_GEMM_TF32 (3 << 8) /* K2 over the fp32 tiles themselves, read by kind::tf32 MMAs (exact mode only):
+                                  what a store WITHOUT 16-bit tiles runs by default -- one pass over the fp32 rows for
+                                  any batch size, where K1 needs one pass per 4 queries */
 /* slab schedule override, OR-ed into `mode`: fixed slabs small enough that the candidate pool can
  * never overflow, whatever the row order (slower; cmw_search_host falls back to it by itself) */
 #define CMW_SLABS_SAFE (1 << 16)
@@ -258,6 +261,8 @@ int cmw_profile_read(double* ms, int64_t* counts, int n);
  *                             of the corpus, the admission thresholds hold whatever order the corpus is stored in
  *   "host_overlap" (0)        pipelined host API: 1 = a ticket's finalisation runs next to the following ticket's filter (measured: no gain)
  *   "slab_growth" (0 = automatic)   cap on the geometric growth of the slabs
+ *   "f16_bits" (11)           significand bits kept in fp16 tiles, 8..11, read when a store is created (fewer bits:
+ *                             less multiplier power under the power cap, larger -- measured -- rounding residual)
  *   "pool_cap" (read-only)    candidate-pool slots per query */
 int cmw_set_option(const char* name, double value);
 double cmw_get_option(const char* name);

@@ -1027,7 +1027,7 @@ def _structured_case(d, m, n_decoys, seed):
 
 @pytest.mark.parametrize("d,m", [(1536, 1017), (1536, 254), (4096, 4068), (256, 254)])
 @pytest.mark.parametrize("metric", ["cosine", "ip"])
-@pytest.mark.parametrize("tiles16", ["bf16", "f16"])
+@pytest.mark.parametrize("tiles16", ["bf16", "f16", "tf32"])
 def test_certificate_is_sound_on_adversarial_roundings(torch_cuda, d, m, metric, tiles16):
     """The guarantee of CMW_MODE_F32_EXACT: a query comes back with the oracle's ids OR flagged -- never a
     silent miss -- whatever the rounding structure of the vectors.  (Round 1's bound assumed u = 2^-9 and
@@ -1041,7 +1041,9 @@ def test_certificate_is_sound_on_adversarial_roundings(torch_cuda, d, m, metric,
     if metric == "ip":
         rows = rows * np.linspace(0.97, 1.03, rows.shape[0], dtype=np.float32)[:, None]
         q = q * np.float32(1.7)
-    st = DenseStore(d, rows.shape[0], tiles16=tiles16)
+    # "tf32": no 16-bit tiles at all -- the filter reads the fp32 rows through kind::tf32 MMAs, which drop 13
+    # mantissa bits of every element the same way (truncation): the same kind of systematic error
+    st = DenseStore(d, rows.shape[0], tiles16=tiles16) if tiles16 != "tf32" else DenseStore(d, rows.shape[0], bf16=False)
     st.append(rows)
     qd = torch.from_numpy(q).cuda()
     silent, flagged = 0, 0
@@ -1174,3 +1176,225 @@ def test_bf16_tiles_store(cfg1, torch_cuda, metric):
                 ex /= np.linalg.norm(c[ids].astype(np.float64), axis=2)
             assert (np.abs(sc - ex) / scale).max() <= BF16_TOL, algo
     st.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: rerank-side plumbing, golden replay through the CUDA backend, batching front-end on the GPU
+# ------------------------------------------------------------------------------------------------
+def test_tool_result_merge_matches_reference_golden(golden_dir, torch_cuda):
+    """accumulate_articles_from_tool_results (rag_engine/tools/utils.py:70-152) -- dedup by kb_id keeping the best
+    score, sort best first -- through K4, against lists the reference's own function produced."""
+    from cmw_rag_b200.articles import merge_tool_results
+
+    with open(os.path.join(golden_dir, "f3_golden.json")) as f:
+        g = json.load(f)
+    assert len(g["tool_merge"]) >= 20
+    for case in g["tool_merge"]:
+        lists = []
+        for raw in case["tool_results"]:
+            arts = json.loads(raw)["articles"]
+            lists.append([(a["kb_id"], a["metadata"].get("rerank_score"), a["content"]) for a in arts])
+        got = merge_tool_results(lists)
+        assert [[kb, content, score] for kb, score, content in got] == case["expected"]
+    assert merge_tool_results([]) == [] and merge_tool_results([[], []]) == []
+
+
+def _golden_store(golden, torch):
+    from cmw_rag_b200.store import B200Store
+
+    n, d = golden["n"], 48
+    corpus = synth.make_corpus(n, d, seed=99)
+    kb = golden["kb"]
+    store = B200Store(collection_name="golden", capacity=n)
+    store.add(texts=[f"chunk {r}" for r in range(n)],
+              metadatas=[{"stable_id": f"{r:012d}", "kbId": kb[r]} for r in range(n)],
+              ids=[f"{r:012d}" for r in range(n)], embeddings=corpus)
+    return store
+
+
+def test_golden_replay_through_the_cuda_backend(golden_dir, torch_cuda):
+    """The drop-in check that needs no reference checkout: the embeddings the reference's unmodified RAGRetriever
+    handed to its store and the Article lists it returned were recorded by tests/golden/make_golden.py; here the
+    same embeddings go through B200Store on the GPU (batched search, K4 union / cap, the reference's rerank stand-in
+    or its no-rerank truncation, K4 grouping, inclusive threshold, ranks) and must reproduce those lists."""
+    torch = torch_cuda
+    from cmw_rag_b200.articles import boost_and_order, group_scored_chunks
+
+    with open(os.path.join(golden_dir, "multivector_golden.json")) as f:
+        golden = json.load(f)
+    store = _golden_store(golden, torch)
+    assert len(golden["cases"]) == 7
+    for case in golden["cases"]:
+        p = case["params"]
+        segs = case["segments"]
+        assert all("query" in s for s in segs), "golden fixture predates the recorded embeddings"
+        qv = np.asarray([s["query"] for s in segs], np.float32)[None, :, :]  # [1, S, d]
+        k = p["top_k_retrieve"]
+        res, ids, scores = store.search_multivector(qv, k, prl=p["prl"])
+        # (1) per-segment lists = what the reference's store returned
+        for si, s_ in enumerate(segs):
+            assert ids[0, si].tolist() == s_["ids"], (case["name"], si)
+            assert np.abs(scores[0, si] - np.asarray(s_["scores"], np.float32)).max() <= F32_TOL
+        cn = int(res.cand_n[0])
+        cand = res.cand_ids[0, :cn].numpy()
+        cand_sc = res.cand_scores[0, :cn].numpy()
+        if p["rerank"]:
+            # (2) the union handed to the reranker, in the reference's first-seen order
+            assert [f"{int(r):012d}" for r in cand] == case["rerank_input_stable_ids"], case["name"]
+            # the fixture's stand-in reranker: score = the candidate's own (first-seen) score, best top_k, stable
+            order, final = boost_and_order(cand_sc.tolist(), [None] * cn, None, top_k=p["top_k_rerank"])
+            rows, sc = cand[order], np.asarray(final, np.float32)
+            threshold = p["threshold"]
+        else:
+            # rerank off: every score 0.0, list cut to top_k_rerank (retriever.py:229-231), no threshold
+            rows, sc = cand[: p["top_k_rerank"]], np.zeros(min(cn, p["top_k_rerank"]), np.float32)
+            threshold = None
+        arts = group_scored_chunks(store, rows[None, :], sc[None, :], threshold=threshold)[0] if len(rows) else []
+        got = [{"kb_id": a.kb_id, "rerank_score": a.score, "normalized_rank": a.normalized_rank,
+                "article_rank": a.article_rank, "matched": [f"{r:012d}" for r in a.rows]} for a in arts]
+        want = case["articles"]
+        assert len(got) == len(want), case["name"]
+        for g_, w_ in zip(got, want):
+            assert (g_["kb_id"], g_["article_rank"], g_["matched"]) == (w_["kb_id"], w_["article_rank"], w_["matched"])
+            assert g_["normalized_rank"] == pytest.approx(w_["normalized_rank"], abs=1e-12)
+            assert g_["rerank_score"] == pytest.approx(w_["rerank_score"], abs=1e-6)
+    store.close()
+
+
+def test_threshold_cases_mirror_reference_tests(torch_cuda):
+    """rag_engine/tests/test_retriever.py:333-462: articles below the threshold are filtered, all filtered -> empty
+    list, a score exactly at the threshold is INCLUDED (`>=`)."""
+    from cmw_rag_b200.articles import group_scored_chunks, retrieval_confidence
+    from cmw_rag_b200.store import B200Store
+
+    store = B200Store(collection_name="thr", capacity=16)
+    kb = ["high_score", "low_score", "medium_score", "123", "exact_threshold", "above_threshold"]
+    rng = np.random.default_rng(0)
+    store.add([f"chunk{i}" for i in range(6)], [{"kbId": kb[i]} for i in range(6)], ids=[f"c{i}" for i in range(6)],
+              embeddings=rng.standard_normal((6, 8)).astype(np.float32))
+    rows = np.array([[0, 1, 2], [3, -1, -1], [4, 5, -1]], np.int64)
+    sc = np.array([[0.9, 0.1, 0.5], [0.1, -np.inf, -np.inf], [0.5, 0.51, -np.inf]], np.float32)
+    arts = group_scored_chunks(store, rows, sc, threshold=0.5)
+    assert {a.kb_id for a in arts[0]} == {"high_score", "medium_score"} and len(arts[0]) == 2
+    assert arts[1] == []
+    assert [a.kb_id for a in arts[2]] == ["above_threshold", "exact_threshold"]
+    assert [a.article_rank for a in arts[2]] == [0, 1] and [a.normalized_rank for a in arts[2]] == [0.0, 1.0]
+    conf = retrieval_confidence(sc[0])
+    assert conf["top_score"] == pytest.approx(0.9) and conf["n_above_threshold"] == 2 and conf["likely_relevant"]
+    store.close()
+
+
+def test_concurrent_callers_through_the_seam_on_the_gpu(cfg1):
+    """48 threads and 32 asyncio tasks hit one B200Store at once: every caller gets the oracle's answer for ITS
+    query, the launches are shared (batch sizes > 1 in the histogram), and the seam latency stays bounded by a
+    few launches -- not by one launch per caller."""
+    import asyncio
+    import threading
+    import time
+
+    from cmw_rag_b200.store import B200Store
+
+    c, q = cfg1["c"], cfg1["q"]
+    store = B200Store(collection_name="conc", capacity=c.shape[0], batch_window_us=300, max_batch=32)
+    store.add([f"t{i}" for i in range(c.shape[0])], [{"kbId": str(i // 8), "stable_id": f"{i:06d}"} for i in range(c.shape[0])],
+              ids=[f"{i:06d}" for i in range(c.shape[0])], embeddings=c)
+    store.similarity_search(q[0], k=5)  # warm-up (first launch allocates workspaces)
+    ref = cfg1["ref_ids"]
+    out, lat = {}, {}
+
+    def worker(i):
+        t0 = time.perf_counter()
+        out[i] = [d_.metadata["stable_id"] for d_ in store.similarity_search(q[i % 64], k=20)]
+        lat[i] = time.perf_counter() - t0
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(48)]
+    t_all = time.perf_counter()
+    for t in threads:
+        t.start()
+
+    async def main():
+        return await asyncio.gather(*[store.similarity_search_async(q[i].tolist(), k=20) for i in range(32)])
+
+    res = asyncio.run(main())
+    for t in threads:
+        t.join()
+    wall = time.perf_counter() - t_all
+    for i in range(48):
+        assert out[i] == [f"{r:06d}" for r in ref[i % 64]], i
+    for i, r in enumerate(res):
+        assert [d_.metadata["stable_id"] for d_ in r] == [f"{x:06d}" for x in ref[i]]
+    m = store.metrics()
+    assert m["counters"]["requests"] == 81 and m["counters"]["launches"] <= 20, m["counters"]
+    assert m["batch_size"]["max"] >= 8 and m["counters"]["flagged"] == 0
+    # 80 callers in a handful of launches: far below 80 sequential single-query searches
+    single = m["launch_ms"]["mean"]
+    print(f"80 concurrent callers: {m['counters']['launches'] - 1} launches, wall {wall * 1e3:.1f} ms, seam latency p50 "
+          f"{m['seam_latency_ms']['p50']} ms p99 {m['seam_latency_ms']['p99']} ms, launch mean {single:.3f} ms")
+    assert max(lat.values()) < 0.5
+    store.close()
+
+
+def test_auto_compaction_and_device_side_growth(torch_cuda):
+    """Store maintenance without a host round trip (cmw_store_copy_rows): a collection that outgrows its HBM
+    reservation is re-ingested device to device, and auto_compact reclaims tombstones once they dominate."""
+    from cmw_rag_b200.store import B200Store
+
+    n, d = 9000, 64
+    c = synth.make_corpus(n, d, seed=21, ties=False)
+    store = B200Store(collection_name="maint", capacity=4096, auto_compact=0.5)
+    for lo in range(0, n, 3000):  # 4096 -> 8192 -> 16384 rows reserved: two device-side growths
+        store.add([f"t{i}" for i in range(lo, lo + 3000)], [{"kbId": str(i // 4), "doc_stable_id": f"d{i // 100}"} for i in range(lo, lo + 3000)],
+                  ids=[f"{i:05d}" for i in range(lo, lo + 3000)], embeddings=c[lo:lo + 3000])
+    assert store.dense.capacity >= n and store.dense.rows == n
+    q, _ = synth.make_queries(c, 8, seed=3, tie_probe=False)
+    ref, _, _ = exact_topk_c(c, q, 5)
+    _, ids, fl = store.search(q, 5)
+    assert (ids == ref).all() and (fl == 0).all()
+    # delete 56 % of the documents: crosses auto_compact = 0.5 -> physical compaction, rows renumbered
+    for doc in range(0, 50):
+        store.delete(where={"doc_stable_id": f"d{doc}"})
+    assert store.count() == n - 5000 and store.dense.rows == n - 5000, (store.count(), store.dense.rows)
+    live = np.zeros(n, np.uint8)
+    live[5000:] = 1
+    ref2, _, _ = exact_topk_c(c, q, 5, live=live)
+    got = [[d_.metadata["doc_stable_id"] for d_ in store.similarity_search(q[b], k=5)] for b in range(8)]
+    assert got == [[f"d{r // 100}" for r in ref2[b]] for b in range(8)]
+    store.close()
+
+
+def test_tf32_filter_over_fp32_tiles(cfg1, torch_cuda):
+    """A store WITHOUT 16-bit tiles filters through kind::tf32 MMAs over the fp32 rows: one pass for any batch size
+    (K1 needs one pass per 4 queries).  Device API: the oracle's ids, nothing flagged; also selectable on a store
+    that has 16-bit tiles (algo="gemm_tf32"); and the D = 200 / 768 dims exercise the partial last k-block."""
+    torch = torch_cuda
+    from cmw_rag_b200 import DenseStore
+
+    c, q = cfg1["c"], cfg1["q"]
+    st = DenseStore(1536, c.shape[0], bf16=False)
+    st.append(c)
+    assert st.info()["gemm_ready"]
+    qd = torch.from_numpy(q).cuda()
+    for b in (1, 16, 40, 64):
+        sc, ids, fl = st.search(qd[:b], 20, mode="f32")  # auto -> tf32 filter
+        torch.cuda.synchronize()
+        _check_exact(ids.cpu().numpy(), sc.cpu().numpy(), cfg1["ref_ids"][:b], cfg1["ref_sc"][:b])
+        assert int(fl.sum()) == 0, b
+    sc, ids, fl = cfg1["store"].search(qd, 20, mode="f32", algo="gemm_tf32")
+    torch.cuda.synchronize()
+    _check_exact(ids.cpu().numpy(), sc.cpu().numpy(), cfg1["ref_ids"], cfg1["ref_sc"])
+    assert int(fl.sum()) == 0
+    sc, ids, fl = st.search_host(q[:9], 20, metric="ip", mode="f32")
+    ref_ids, ref_sc, _ = exact_topk_c(c, q[:9], 20, metric="ip")
+    _check_exact(ids, sc, ref_ids, ref_sc)
+    st.close()
+    for n, d in ((30000, 200), (20011, 768)):
+        c2 = synth.make_corpus(n, d, seed=n, ties=False)
+        q2, _ = synth.make_queries(c2, 33, seed=2, tie_probe=False)
+        s2 = DenseStore(d, n, bf16=False)
+        s2.append(c2)
+        ref_ids, ref_sc, _ = exact_topk_c(c2, q2, 10)
+        sc, ids, fl = s2.search(torch.from_numpy(q2).cuda(), 10, mode="f32")
+        torch.cuda.synchronize()
+        _check_exact(ids.cpu().numpy(), sc.cpu().numpy(), ref_ids, ref_sc)
+        assert int(fl.sum()) == 0, (n, d)
+        s2.close()

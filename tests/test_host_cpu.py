@@ -502,3 +502,147 @@ def test_scan_order_permutation_is_a_bijection_and_spreads_evenly():
             tiles = np.sort(perm[start:start + n])
             gaps = np.diff(np.concatenate([tiles, [tiles[0] + T]]))
             assert gaps.max() <= 8 * (T / n) + 2, (T, start, int(gaps.max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: rerank-side statistics, batching front-end, versioned collections
+# ------------------------------------------------------------------------------------------------
+def test_confidence_statistics_match_reference_golden(golden_dir):
+    """retrieval/confidence.py:13-117 of the reference, through golden vectors its own functions produced
+    (tests/golden/make_golden_f3.py)."""
+    import json
+
+    from cmw_rag_b200.articles import (normalized_confidence_from_traces, retrieval_confidence,
+                                       retrieval_confidence_batch)
+
+    with open(os.path.join(golden_dir, "f3_golden.json")) as f:
+        g = json.load(f)
+    assert len(g["confidence"]) >= 50
+    for case in g["confidence"]:
+        got = retrieval_confidence(case["scores"], case["threshold"], case["mean_top_k"])
+        want = case["expected"]
+        assert got["n_above_threshold"] == want["n_above_threshold"] and got["likely_relevant"] == want["likely_relevant"]
+        for key in ("top_score", "mean_top_k", "score_gap"):
+            assert got[key] == pytest.approx(want[key], abs=1e-12), (key, case)
+    for case in g["normalized"]:
+        got = normalized_confidence_from_traces(case["traces"])
+        assert (got is None) == (case["expected"] is None)
+        if got is not None:
+            assert got == pytest.approx(case["expected"], abs=1e-12)
+    rows = np.array([[0.9, 0.2, 0.6, 0.0], [0.1, 0.1, 0.0, 0.0]])
+    out = retrieval_confidence_batch(rows, counts=[3, 2])
+    assert out[0] == retrieval_confidence([0.9, 0.2, 0.6]) and out[1] == retrieval_confidence([0.1, 0.1])
+
+
+def test_batcher_window_batchsize_backpressure_and_metrics():
+    import threading
+    import time
+
+    from cmw_rag_b200.batcher import QueueFull, SearchBatcher
+
+    calls = []
+    gate = threading.Event()
+
+    def search(q, kmax):
+        calls.append(q.shape[0])
+        gate.wait(5)  # the "GPU" is busy until the test says so
+        ids = np.tile(np.arange(kmax), (q.shape[0], 1)) + q[:, :1].astype(np.int64) * 1000
+        return np.zeros((q.shape[0], kmax), np.float32), ids, np.zeros(q.shape[0], np.int32)
+
+    b = SearchBatcher(search, max_batch=8, max_wait_us=20_000, max_queue=12, name="t")
+    try:
+        first = b.submit(np.full(4, 1.0), 3)
+        time.sleep(0.08)  # the window (20 ms) expires: a batch of one is dispatched and blocks on the gate
+        assert calls == [1]
+        # while that launch runs, requests pile up: 12 fit, the 13th is refused without blocking
+        futs = [b.submit(np.full(4, float(i + 2)), 2 + i % 3) for i in range(12)]
+        with pytest.raises(QueueFull):
+            b.submit(np.zeros(4), 1, block=False)
+        gate.set()
+        sc, ids, flag = first.result(5)
+        assert ids.tolist() == [1000, 1001, 1002] and flag == 0
+        for i, f in enumerate(futs):
+            sc, ids, flag = f.result(5)
+            assert ids.shape == (2 + i % 3,) and ids[0] == (i + 2) * 1000  # every caller gets ITS row, cut to ITS k
+        assert calls[1] == 8 and sum(calls) == 13  # max_batch caps a launch; nothing is lost
+        m = b.metrics()
+        assert m["counters"]["requests"] == 13 and m["counters"]["rejected"] == 1
+        assert m["batch_size"]["max"] == 8 and m["queue_depth_at_dispatch"]["max"] == 12
+        assert m["seam_latency_ms"]["count"] == 13 and m["queue_wait_ms"]["p99"] > 0
+        text = b.prometheus()
+        assert "cmw_t_batch_size_bucket" in text and "cmw_t_requests_total 13" in text
+        # an exception in the launch reaches every waiter of that batch
+        b._search = lambda q, k: (_ for _ in ()).throw(RuntimeError("boom"))
+        f = b.submit(np.zeros(4), 1)
+        with pytest.raises(RuntimeError, match="boom"):
+            f.result(5)
+    finally:
+        gate.set()
+        b.close()
+
+
+def test_concurrent_callers_share_launches_through_the_store(fake_store):
+    """Threads calling similarity_search and asyncio tasks awaiting similarity_search_async at the same time end up
+    in shared launches (the reference issues one HTTP query per call: retriever.py:179-182,
+    retrieve_context.py:397-409), each getting its own answer."""
+    import asyncio
+    import threading
+
+    store = fake_store
+    rng = np.random.default_rng(5)
+    n, d = 300, 8
+    emb = rng.standard_normal((n, d)).astype(np.float32)
+    store.add([f"t{i}" for i in range(n)], [{"kbId": str(i // 3), "stable_id": f"s{i}"} for i in range(n)],
+              ids=[f"s{i}" for i in range(n)], embeddings=emb)
+    out = {}
+
+    def worker(i):
+        out[i] = [d_.metadata["stable_id"] for d_ in store.similarity_search(emb[i] * 1.5, k=1)]
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(24)]
+    for t in threads:
+        t.start()
+
+    async def main():
+        return await asyncio.gather(*[store.similarity_search_async(emb[100 + i].tolist(), k=2) for i in range(12)])
+
+    res = asyncio.run(main())
+    for t in threads:
+        t.join()
+    assert all(out[i] == [f"s{i}"] for i in range(24))
+    assert all(r[0].metadata["stable_id"] == f"s{100 + i}" and len(r) == 2 for i, r in enumerate(res))
+    st = store.stats
+    assert st["searches"] == 36 and st["launch_batches"] < 36 and st["max_batch"] >= 12
+    m = store.metrics()
+    assert m["collection"]["live_rows"] == n and m["batch_size"]["count"] == st["launch_batches"]
+    store.close()
+
+
+def test_collection_registry_names_cache_and_persistence(monkeypatch, tmp_path):
+    """config/settings.py:261-273 (collection name per product version) and the per-version store cache of
+    tools/retrieve_context.py:101-131."""
+    import cmw_rag_b200.store as store_mod
+    from cmw_rag_b200.registry import CollectionRegistry
+
+    monkeypatch.setattr(store_mod, "DenseStore", FakeDense)
+    reg = CollectionRegistry("kb", overrides={"v5": "legacy_five", "v6": ""}, root=str(tmp_path), capacity=64)
+    # the reference's three rules: override if non-empty, else {base}_{version}, unknown version -> base
+    assert reg.collection_name("v5") == "legacy_five"
+    assert reg.collection_name("v6") == "kb_v6"
+    assert reg.collection_name("v7") == "kb" and reg.collection_name(None) == "kb"
+    s5, s6 = reg.get_store("v5"), reg.get_store("v6")
+    assert s5 is reg.get_store("v5") and s5 is not s6 and s5.collection_name == "legacy_five"
+    rng = np.random.default_rng(1)
+    e5 = rng.standard_normal((10, 8)).astype(np.float32)
+    s5.add([f"five{i}" for i in range(10)], [{"kbId": str(i)} for i in range(10)], ids=[f"a{i}" for i in range(10)],
+           embeddings=e5)
+    s6.add(["six"], [{"kbId": "600"}], ids=["b0"], embeddings=rng.standard_normal((1, 8)).astype(np.float32))
+    assert s5.count() == 10 and s6.count() == 1  # one store per product version
+    path = reg.save("v5")
+    assert path.endswith("legacy_five") and os.path.exists(os.path.join(path, "meta.json"))
+    reg.close()
+    reg2 = CollectionRegistry("kb", overrides={"v5": "legacy_five"}, root=str(tmp_path), capacity=64)
+    again = reg2.get_store("v5")  # found on disk, like a Chroma collection in the server's --path directory
+    assert again.count() == 10 and again.similarity_search(e5[3], k=1)[0].page_content == "five3"
+    assert reg2.get_store("v6").count() == 0  # never saved: starts empty
+    reg2.close()
