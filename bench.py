@@ -370,6 +370,13 @@ def make_queries(torch, dist, first, lo, batch, dim, device, seed, rank, world):
     return q.contiguous(), needle
 
 
+def simple_setup(torch, rows, dim, device, batch, seed=7, f32=True, tiles16="f16"):
+    """One-GPU helper for the scripts under benchmarks/: (store, queries [batch, dim], needle ids)."""
+    st, first = build_store(torch, dim, device, 0, rows, f32=f32, tiles16=tiles16)
+    q, needle = make_queries(torch, None, first, 0, batch, dim, device, seed, 0, 1)
+    return st, first, q, needle
+
+
 def host_corpus_from_blocks(torch, device, dim, rows) -> np.ndarray:
     out = np.empty((rows, dim), np.float32)
     for g0, x in gen_rows(torch, device, dim, 0, rows):

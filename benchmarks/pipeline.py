@@ -35,8 +35,7 @@ def main():
 
     device = torch.device("cuda:0")
     torch.cuda.set_device(device)
-    st, first = bench.build_store(torch, args_ns(args), device, 0, 1)
-    q, _ = bench.make_queries(torch, first, args.batch, args.dim, device, 7)
+    st, first, q, _ = bench.simple_setup(torch, args.rows, args.dim, device, args.batch)
     B, k = args.batch, args.k
     q_host = pinned_empty((B, args.dim), np.float32)
     q_host[:] = q.cpu().numpy()

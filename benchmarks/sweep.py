@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--algos", default="auto")
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--no-f32", action="store_true")
+    ap.add_argument("--tiles16", default="f16", choices=["f16", "bf16"])
     ap.add_argument("--multivector", action="store_true")
     ap.add_argument("--out", default="")
     ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE",
@@ -52,12 +53,7 @@ def main():
         N.set_option(name, float(value))
         options[name] = float(value)
 
-    class A:
-        pass
-
-    a = A()
-    a.rows, a.dim, a.shard, a.no_f32 = args.rows, args.dim, "queries", args.no_f32
-    st, first = bench.build_store(torch, a, device, 0, 1)
+    st, first = bench.build_store(torch, args.dim, device, 0, args.rows, f32=not args.no_f32, tiles16=args.tiles16)
     peaks = bench.measured_peaks()
     out_f = open(args.out, "a") if args.out else None
 
@@ -76,7 +72,7 @@ def main():
         qn, s, k = 512, 8, 50
         _, art = synth.make_kbids(args.rows)
         st2_gid = torch.from_numpy(art.astype(np.int32)).to(device)
-        q, _ = bench.make_queries(torch, first, qn * s, args.dim, device, 11)
+        q, _ = bench.make_queries(torch, None, first, 0, qn * s, args.dim, device, 11, 0, 1)
         seg = q.view(qn, s, args.dim)
         for prl in (60, 0):
             for mode in args.modes.split(","):
@@ -121,7 +117,7 @@ def main():
             continue
         for algo in args.algos.split(","):
             for b in [int(x) for x in args.batches.split(",")]:
-                q, needle = bench.make_queries(torch, first, b, args.dim, device, 100 + b)
+                q, needle = bench.make_queries(torch, None, first, 0, b, args.dim, device, 100 + b, 0, 1)
                 for _ in range(3):
                     sc, ids, fl = st.search(q, args.k, mode=mode, algo=algo)
                 torch.cuda.synchronize()

@@ -20,10 +20,8 @@ def main():
     from cmw_rag_b200 import _native as N
     dev = torch.device("cuda:0")
 
-    class A: pass
-    a = A(); a.rows, a.dim, a.shard, a.no_f32 = args.rows, 1536, "queries", False
-    st, first = bench.build_store(torch, a, dev, 0, 1)
-    q, needle = bench.make_queries(torch, first, args.batch, 1536, dev, 7)
+    ap_tiles = os.environ.get("CMW_TILES16", "f16")
+    st, first, q, needle = bench.simple_setup(torch, args.rows, 1536, dev, args.batch, tiles16=ap_tiles)
     for v in [float(x) for x in args.values.split(",")]:
         N.set_option(args.option, v)
         for _ in range(3):
