@@ -198,10 +198,45 @@ __device__ __forceinline__ void select_and_compact(uint32_t (&key)[kCompactPer],
     uint32_t T = 0xffffffffu;  // keep everything that is present
     const bool select = valid > kprime;
     if (select) {
-        uint32_t prefix = 0, mask = 0;
+        // The keys of one pool are scores from a narrow range: their leading bits (sign, exponent, often a few
+        // mantissa bits) are all the same.  Find that common prefix first (block-wide AND / OR) and run the radix
+        // passes only over the bits below it: usually 3 passes of 8 bits instead of 4, and no pass in which all
+        // 4096 shared-memory atomics land on one or two bins.
+        uint32_t k_and = 0xffffffffu, k_or = 0u;
+#pragma unroll
+        for (int j = 0; j < kCompactPer; ++j) {
+            if (rid[j] >= 0) {
+                k_and &= key[j];
+                k_or |= key[j];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            k_and &= __shfl_xor_sync(0xffffffffu, k_and, o);
+            k_or |= __shfl_xor_sync(0xffffffffu, k_or, o);
+        }
+        __syncthreads();  // hist is free (nothing has used it yet in this call; a previous pass may have)
+        if ((t & 31) == 0) {
+            sm.hist[t >> 5] = (int)k_and;
+            sm.hist[32 + (t >> 5)] = (int)k_or;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kCompactThreads / 32; ++w) {
+            k_and &= (uint32_t)sm.hist[w];
+            k_or |= (uint32_t)sm.hist[32 + w];
+        }
+        __syncthreads();
+        const uint32_t diff = k_and ^ k_or;
+        const int common = diff ? __clz(diff) : 32;  // leading bits shared by every present key
+        uint32_t mask = common ? ~(0xffffffffu >> common) : 0u;
+        if (common == 32) mask = 0xffffffffu;
+        uint32_t prefix = k_and & mask;
         int remaining = kprime;
-        for (int pass = 0; pass < 4; ++pass) {
-            const int shift = 24 - 8 * pass;
+        for (int top = 32 - common; top > 0; top -= 8) {
+            // digit = bits [shift, shift + 8); the last digit may overlap bits that are already decided, which
+            // are equal for every key still in play
+            const int shift = top >= 8 ? top - 8 : 0;
             sm.hist[t] = 0;
             __syncthreads();
 #pragma unroll
@@ -218,7 +253,7 @@ __device__ __forceinline__ void select_and_compact(uint32_t (&key)[kCompactPer],
                 sm.sel_below = cum - h;
             }
             __syncthreads();
-            prefix |= (uint32_t)sm.sel_digit << shift;
+            prefix = (prefix & ~(0xffu << shift)) | ((uint32_t)sm.sel_digit << shift);
             mask |= 0xffu << shift;
             remaining -= sm.sel_below;
         }
@@ -624,25 +659,43 @@ int launch_pool_topk_scores(Pool pool, int batch, int k, float* out, cudaStream_
     return 0;
 }
 
-// after all-gather 1: the k-th best filter score over all shards, per query (-inf when fewer than k exist)
+// after all-gather 1: the k-th best filter score over all shards, per query (-inf when fewer than k exist).
+// One WARP per query: MSB-first bitwise selection on the order-preserving keys -- 32 rounds of "how many keys have
+// this prefix and a 1 in the next bit" over the G*k gathered scores (3 KB per query, L1-resident after the first
+// round) -- instead of sorting them: at G = 8, k = 100 a sort of 1024 keys per query cost more than the exchange.
 __global__ void __launch_bounds__(256)
 shard_kth_kernel(const float* __restrict__ gathered, int G, int B, int k, float* __restrict__ out_kth) {
-    extern __shared__ __align__(16) uint8_t kth_smem[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(kth_smem);
-    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
     const int n = G * k;
-    const int m = next_pow2(n < 2 ? 2 : n);
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
-        uint64_t key = ~0ull;
-        if (i < n) {
-            const int g = i / k, j = i - g * k;
-            const float v = gathered[((size_t)g * B + b) * k + j];
-            if (v > -INFINITY) key = desc_key(v, 0u);
-        }
-        keys[i] = key;
+    // ascending orderable key = ascending score; absent entries (-inf) and NaN never count
+    auto key_of = [&](int i) -> uint32_t {
+        const int g = i / k, j = i - g * k;
+        const float v = gathered[((size_t)g * B + b) * k + j];
+        return (v > -INFINITY) ? f32_orderable(v) : 0u;  // 0 is below every real score's key
+    };
+    int valid = 0;
+    for (int i = lane; i < n; i += 32) valid += key_of(i) != 0u ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    if (valid < k) {
+        if (lane == 0) out_kth[b] = -INFINITY;
+        return;
     }
-    bitonic_sort_u64(keys, m);
-    if (threadIdx.x == 0) out_kth[b] = (keys[k - 1] != ~0ull) ? desc_key_score(keys[k - 1]) : -INFINITY;
+    uint32_t prefix = 0u;
+    int want = k;  // the want-th LARGEST key among those matching the prefix so far
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t probe = prefix | (1u << bit);
+        const uint32_t mask = ~((1u << bit) - 1u);
+        int ones = 0;
+        for (int i = lane; i < n; i += 32) ones += ((key_of(i) & mask) == probe) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ones += __shfl_xor_sync(0xffffffffu, ones, o);
+        if (ones >= want) prefix = probe;  // the answer has this bit set
+        else want -= ones;                 // it lies among the keys with a 0 here
+    }
+    if (lane == 0) out_kth[b] = f32_from_orderable(prefix);
 }
 
 // after all-gather 2: G blocks -> the global top k_out by (exact score desc, id asc) and the cross-shard
@@ -654,26 +707,53 @@ shard_merge_kernel(const uint8_t* __restrict__ blocks, int G, int B, int k, int 
                    float* __restrict__ out_scores, int64_t* __restrict__ out_ids, double* __restrict__ out_scores64,
                    int32_t* __restrict__ out_flags) {
     extern __shared__ __align__(16) uint8_t sm_smem[];
+    __shared__ int warp_tot[8];
     const int b = blockIdx.x;
-    const int n = G * k;
-    const int m = next_pow2(n < 2 ? 2 : n);
+    const int n_all = G * k;
+    const int m_all = next_pow2(n_all < 2 ? 2 : n_all);
     uint64_t* hi = reinterpret_cast<uint64_t*>(sm_smem);
-    uint64_t* lo = hi + m;
+    uint64_t* lo = hi + m_all;
     const ShardBlock lay = shard_block(B, k);
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    // With the global rescoring cut most of a shard's k slots are empty (only the candidates that can still reach
+    // the global top-k were rescored): pack the valid ones first and sort next_pow2(valid) keys, not G*k.
+    int base = 0;
+    for (int i0 = 0; i0 < n_all; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
         uint64_t h = ~0ull, l = ~0ull;
-        if (i < n) {
+        bool ok = false;
+        if (i < n_all) {
             const int g = i / k, j = i - g * k;
             const uint8_t* blk = blocks + (size_t)g * lay.total;
             const int64_t id = reinterpret_cast<const int64_t*>(blk + lay.ids)[(size_t)b * k + j];
             const double s = reinterpret_cast<const double*>(blk + lay.scores)[(size_t)b * k + j];
-            if (id >= 0 && s == s) {
+            if (id >= 0 && s == s && s > -INFINITY) {
                 h = ~f64_orderable(s);
                 l = (uint64_t)id;
+                ok = true;
             }
         }
-        hi[i] = h;
-        lo[i] = l;
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) warp_tot[w] = __popc(bal);
+        __syncthreads();
+        int before = 0, round_total = 0;
+        for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) {
+            if (ww < w) before += warp_tot[ww];
+            round_total += warp_tot[ww];
+        }
+        if (ok) {
+            const int pos = base + before + __popc(bal & ((1u << lane) - 1u));
+            hi[pos] = h;
+            lo[pos] = l;
+        }
+        base += round_total;
+        __syncthreads();
+    }
+    const int n = base;  // valid candidates
+    const int m = next_pow2(n < 2 ? 2 : n);
+    for (int i = n + threadIdx.x; i < m; i += blockDim.x) {
+        hi[i] = ~0ull;
+        lo[i] = ~0ull;
     }
     bitonic_sort_u128(hi, lo, m);
     for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
@@ -697,9 +777,8 @@ shard_merge_kernel(const uint8_t* __restrict__ blocks, int G, int B, int k, int 
             if (aux[0] > -INFINITY && aux[0] + aux[1] > bar) bar = aux[0] + aux[1];
         }
         if (bar > -INFINITY) {
-            const int kk = k_out <= n ? k_out : n;
-            double kth = -INFINITY;
-            if (!(hi[kk - 1] == ~0ull && lo[kk - 1] == ~0ull)) kth = f64_from_orderable(~hi[kk - 1]);
+            // (a pool that filled holds at least K' >= k rows of which the k best were rescored: n >= k_out)
+            const double kth = (n >= k_out) ? f64_from_orderable(~hi[k_out - 1]) : -INFINITY;
             if (!(kth > bar)) flag |= CMW_FLAG_UNCERTIFIED;
         }
         out_flags[b] = flag;
@@ -736,14 +815,8 @@ namespace cmw {
 
 int launch_shard_kth(const float* gathered, int G, int B, int k, float* out_kth, cudaStream_t stream) {
     const int n = G * k;
-    CMW_REQUIRE(n <= 16384, "cmw_shard_kth: G*k = %d exceeds 16384", n);
-    const size_t smem = (size_t)next_pow2_host(n < 2 ? 2 : n) * 8;
-    static SmemAttrCache smem_set;
-    if (smem > 48 * 1024 && smem_set.needs(smem)) {
-        CMW_CUDA_OK(cudaFuncSetAttribute(shard_kth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set.done(smem);
-    }
-    shard_kth_kernel<<<B, 256, smem, stream>>>(gathered, G, B, k, out_kth);
+    CMW_REQUIRE(n <= 65536, "cmw_shard_kth: G*k = %d exceeds 65536", n);
+    shard_kth_kernel<<<(B + 7) / 8, 256, 0, stream>>>(gathered, G, B, k, out_kth);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
