@@ -480,12 +480,16 @@ class B200Store:
         if not group:
             return
         try:
-            while True:
-                try:
-                    futs = self.batcher.submit_many([v for v, _, _ in group], [k for _, k, _ in group])
-                    break
-                except QueueFull:  # back-pressure without blocking the loop
-                    await asyncio.sleep(0.001)
+            futs = []
+            step = max(1, self.batcher.max_queue // 2)  # a tick's group larger than the queue goes in pieces
+            for lo in range(0, len(group), step):
+                part = group[lo:lo + step]
+                while True:
+                    try:
+                        futs += self.batcher.submit_many([v for v, _, _ in part], [k for _, k, _ in part])
+                        break
+                    except QueueFull:  # back-pressure without blocking the loop
+                        await asyncio.sleep(0.001)
             results = await asyncio.gather(*[asyncio.wrap_future(f) for f in futs], return_exceptions=True)
             for (_, _, fut), res in zip(group, results):
                 if fut.done():
