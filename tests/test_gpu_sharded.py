@@ -135,3 +135,32 @@ def test_two_devices_in_one_process():
             assert (ids2.cpu().numpy() == ref[:3]).all()
     for st in stores:
         st.close()
+
+
+def test_shard_kth_matches_a_sort():
+    """cmw_shard_kth (the kernel between the two exchanges of the row-sharded search): the k-th best of the G*k
+    gathered filter scores per query, against torch's sort -- through all three kernel variants (keys in 8 / 32
+    registers per lane, memory-resident), with absent (-inf) entries, duplicates, negative scores, queries with
+    fewer than k real entries (-> -inf), and keys that agree on most of their bits."""
+    import torch
+
+    from cmw_rag_b200.engine import shard_kth
+
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for G, B, k in ((2, 37, 100), (8, 513, 100), (3, 5, 7), (1, 9, 20), (8, 64, 128), (16, 33, 100), (8, 16, 1024)):
+        x = torch.randn((G, B, k), generator=gen, device="cuda") * 0.05
+        x[:, 1] = 0.25 + x[:, 1] * 1e-4            # nearly equal keys: long common prefix
+        x[:, 2] = torch.round(x[:, 2] * 200) / 200  # many exact duplicates
+        if B > 4:
+            x[:, 3] = float("-inf")                 # nothing at all -> -inf
+            x[1:, 4] = float("-inf")                # one shard's worth only
+            x[0, 4, k // 2:] = float("-inf")        # ... and not even k of those -> -inf
+        drop = torch.rand((G, B, k), generator=gen, device="cuda") < 0.2
+        drop[:, :3] = False
+        x = torch.where(drop, torch.full_like(x, float("-inf")), x)
+        x = torch.sort(x, dim=2, descending=True).values.contiguous()  # shards send their scores best first
+        got = shard_kth(x, k)
+        flat = x.permute(1, 0, 2).reshape(B, G * k)
+        want = torch.sort(flat, dim=1, descending=True).values[:, k - 1]
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), (G, B, k, (got != want).nonzero()[:5])

@@ -66,6 +66,39 @@ def test_numpy_and_c_oracles_agree_config1():
         assert order.tolist() == i1[b].tolist()
 
 
+def test_topk_oracle_agrees_with_independent_libraries():
+    """chromadb / hnswlib (where the reference's arithmetic for this path lives: requirements.txt `chromadb==1.3.0`)
+    cannot be installed offline, so the top-k oracle is pinned a second way: against two independent third-party
+    implementations of the same definition -- scikit-learn's brute-force NearestNeighbors in the `cosine` metric
+    (distance = 1 - cos, the very quantity hnswlib's `cosine` space and Chroma's `distances` report:
+    rag_engine/storage/vector_store.py:48-51) and scipy's cdist.  Un-normalised rows, so cosine != inner product."""
+    from scipy.spatial.distance import cdist
+    from sklearn.neighbors import NearestNeighbors
+
+    rng = np.random.default_rng(5)
+    for n, d, b, k in ((3000, 1536, 24, 100), (777, 96, 16, 20), (50, 8, 5, 50)):
+        c = (rng.standard_normal((n, d)) * rng.uniform(0.2, 3.0, size=(n, 1))).astype(np.float32)
+        q = (rng.standard_normal((b, d)) * rng.uniform(0.5, 2.0, size=(b, 1))).astype(np.float32)
+        ids, sc, sc64 = exact_topk(c, q, k)
+        ids_c, sc_c, _ = exact_topk_c(c, q, k)
+        nn = NearestNeighbors(n_neighbors=k, algorithm="brute", metric="cosine").fit(c.astype(np.float64))
+        dist, nbr = nn.kneighbors(q.astype(np.float64))
+        full = 1.0 - cdist(q.astype(np.float64), c.astype(np.float64), metric="cosine")
+        for i in range(b):
+            # the three agree on the SET and the ORDER wherever neighbouring scores differ by more than fp64 noise
+            gaps = np.abs(np.diff(np.sort(full[i])[::-1][: k + 1]))
+            assert gaps.min() > 1e-12, "seeded case has a near-tie; pick another seed"
+            assert ids[i].tolist() == nbr[i].tolist() == ids_c[i].tolist()
+            assert np.argsort(-full[i], kind="stable")[:k].tolist() == ids[i].tolist()
+        assert np.abs((1.0 - dist) - sc64).max() < 1e-12
+        assert np.abs(np.take_along_axis(full, ids, axis=1) - sc64).max() < 1e-12
+        # inner product: against numpy's own fp64 matmul
+        ids_ip, _, sc_ip = exact_topk(c, q, k, metric="ip")
+        ipm = q.astype(np.float64) @ c.astype(np.float64).T
+        assert (np.argsort(-ipm, axis=1, kind="stable")[:, :k] == ids_ip).all()
+        assert np.abs(np.take_along_axis(ipm, ids_ip, axis=1) - sc_ip).max() < 1e-9
+
+
 def test_topk_edge_cases():
     rng = np.random.default_rng(0)
     c = rng.standard_normal((37, 16)).astype(np.float32)
