@@ -189,6 +189,8 @@ class ShardedSearcher:
         self._merge = merge
         self._exchange = exchange
         self.timings = None  # set to {} to collect CUDA-event pairs per phase (bench.py)
+        self._copy_streams = None
+        self._qbufs: dict = {}
 
     # -- helpers ------------------------------------------------------------------------------------
     def _all_gather(self, t):
@@ -230,20 +232,57 @@ class ShardedSearcher:
         """The host-buffer form (what a caller without device tensors uses, on every rank): H2D of the queries
         (direct DMA when the array is page-locked), the sharded search, D2H of the merged result into ``out`` =
         (scores f32[B,k], ids i64[B,k], flags i32[B]) numpy arrays (allocated when None); synchronises."""
+        return self.search_host_wait(self.search_host_submit(queries_host, k, out=out, **kw))
+
+    def search_host_submit(self, queries_host, k: int, out=None, **kw):
+        """Pipelined host-buffer form, the row-sharded twin of cmw_search_host_submit: the queries go up on a copy
+        stream, the search (with both exchanges) runs on the caller's current stream behind that copy, the merged
+        result comes down on a second copy stream; returns a ticket for ``search_host_wait``.  With two or more
+        tickets outstanding the copies of one batch hide under the kernels of its neighbours.  Every rank must
+        submit the same batches in the same order (the exchanges are collectives)."""
         import numpy as np
         import torch
 
         dev = torch.device(f"cuda:{self.store.device}")
-        q = torch.from_numpy(np.ascontiguousarray(queries_host, dtype=np.float32)).to(dev, non_blocking=True)
-        ms, mi, fl = self.search(q, k, **kw)
-        b = q.shape[0]
+        if self._copy_streams is None:
+            self._copy_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        up, down = self._copy_streams
+        main = torch.cuda.current_stream(dev)
+        src = torch.from_numpy(np.ascontiguousarray(queries_host, dtype=np.float32))
+        b = src.shape[0]
         if out is None:
             out = (np.empty((b, k), np.float32), np.empty((b, k), np.int64), np.zeros((b,), np.int32))
-        torch.from_numpy(out[0]).copy_(ms, non_blocking=True)
-        torch.from_numpy(out[1]).copy_(mi, non_blocking=True)
-        torch.from_numpy(out[2]).copy_(fl.to(torch.int32), non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        return out
+        # query buffers are the searcher's own and go round (an allocation in flight -- cudaMalloc behind the
+        # caching allocator -- stalls the host for tens of milliseconds while the GPU is busy)
+        free = self._qbufs.setdefault(tuple(src.shape), [])
+        q = free.pop() if free else torch.empty(src.shape, dtype=torch.float32, device=dev)
+        with torch.cuda.stream(up):
+            q.copy_(src, non_blocking=True)
+            e_in = torch.cuda.Event()
+            e_in.record(up)
+        main.wait_event(e_in)
+        ms, mi, fl = self.search(q, k, **kw)
+        fl = fl.to(torch.int32)
+        e_done = torch.cuda.Event()
+        e_done.record(main)
+        with torch.cuda.stream(down):
+            down.wait_event(e_done)
+            torch.from_numpy(out[0]).copy_(ms, non_blocking=True)
+            torch.from_numpy(out[1]).copy_(mi, non_blocking=True)
+            torch.from_numpy(out[2]).copy_(fl, non_blocking=True)
+            e_out = torch.cuda.Event()
+            e_out.record(down)
+        # the ticket keeps every device tensor alive until the wait: nothing allocated on one stream is handed
+        # back to the caching allocator while another stream may still be reading it
+        return {"event": e_out, "out": out, "keep": (src, ms, mi, fl), "q": q}
+
+    def search_host_wait(self, ticket):
+        ticket["event"].synchronize()
+        ticket["keep"] = None
+        q = ticket.pop("q", None)
+        if q is not None:
+            self._qbufs.setdefault(tuple(q.shape), []).append(q)
+        return ticket["out"]
 
     def search(self, queries, k: int, **kw):
         """queries [B, dim] (replicated on every rank) -> (scores f32[B,k], ids i64[B,k], flags i32[B]),

@@ -57,6 +57,14 @@ for mode in ("f32", "bf16"):
         rec = np.mean([len(set(mi[b].tolist()) & set(ref_ids[b])) / k for b in range(37)])
         assert rec >= 0.95, rec
         assert torch.equal(mi, oi)
+# the host-buffer forms: blocking, and pipelined with three batches outstanding (different batches: a ticket must
+# come back with ITS answer)
+h = s.search_host(q, k)
+assert (h[1] == ref_ids).all() and np.abs(h[0] - ref_sc).max() <= 1e-5 and (h[2] == 0).all(), rank
+tickets = [s.search_host_submit(np.roll(q, it, axis=0).copy(), k) for it in range(3)]
+for it, t in enumerate(tickets):
+    o = s.search_host_wait(t)
+    assert (o[1] == np.roll(ref_ids, it, axis=0)).all() and (o[2] == 0).all(), (rank, it)
 # a failed certificate on ONE shard must flag the merged answer on EVERY rank (and never pass silently)
 old = N.get_option("bf16_eps")
 N.set_option("bf16_eps", 0.5)
