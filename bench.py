@@ -1162,7 +1162,45 @@ def config4_record(torch, dist, N, args, device, rank, world):
     if ph is not None:
         rec["shard_phases_ms_per_step"] = {n: v / steps for n, v in ph.items()}
     st4.close()
+    if world > 1:
+        # STRONG scaling where the corpus is large enough for it to mean something (SURVEY 8e recommends a corpus
+        # that fits one GPU): the very 25M-row corpus of the N = 1 weak record (same seeded blocks), row-sharded
+        # over the N GPUs, batch 1024.  Its one-GPU time is `config4_weak.ms_per_step` of the N = 1 line.
+        del st4, s4
+        slo, shi = shard_bounds_local(rows, world, rank)
+        st5, first5 = build_store(torch, args.dim, device, slo, shi, f32=False, tiles16="bf16")
+        q5, needle5 = make_queries(torch, dist, first5, slo, B, args.dim, device, 13, rank, world)
+        s5 = ShardedSearcher(st5)
+        for _ in range(3):
+            out5 = s5.search(q5, k, mode="bf16")
+        torch.cuda.synchronize(device)
+        nd5 = needle5.cpu().numpy()
+        ok5 = bool((out5[1].cpu().numpy()[nd5 >= 0, 0] == nd5[nd5 >= 0]).all())
+        assert ok5, "config 4 (strong): planted needles are not top-1"
+        steps5 = 10
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps5):
+            s5.search(q5, k, mode="bf16")
+        e1.record()
+        torch.cuda.synchronize(device)
+        t5 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        ms5 = float(t5[0]) / steps5
+        rec["strong"] = {"total_rows": rows, "rows_per_gpu": shi - slo, "batch": B, "k": k, "ms_per_step": ms5,
+                         "qps": B * 1e3 / ms5, "needles_top1_in_every_shard": ok5,
+                         "one_gpu_baseline": "config4_weak.ms_per_step of the N = 1 line (the same 25M-row corpus on "
+                                             "one GPU)",
+                         "scaling": "strong: total rows fixed; speed-up = ms_per_step(N = 1 weak record) / ms_per_step"}
+        st5.close()
     return rec
+
+
+def shard_bounds_local(rows, world, rank):
+    from cmw_rag_b200.sharded import shard_bounds
+
+    return shard_bounds(rows, world)[rank]
 
 
 def main():

@@ -5,6 +5,7 @@
     python benchmarks/profile_cases.py b1        # 12 batch-1 searches (K2 NT=16, wide first slab)
     python benchmarks/profile_cases.py tf32      # 12 batch-16 searches on a store WITHOUT 16-bit tiles (tf32 filter)
     python benchmarks/profile_cases.py scan      # 12 batch-1 searches through K1 (fp32 scan)
+    python benchmarks/profile_cases.py mid 256   # 6 searches of a crossover batch (here 256)
 """
 import os
 import sys
@@ -31,9 +32,9 @@ if case == "tf32":
     for _ in range(12):
         st.search(q, 100)
 else:
-    batch = 4096 if case == "step" else 1
+    batch = 4096 if case == "step" else (int(sys.argv[2]) if case == "mid" else 1)
     st, first, q, _ = bench.simple_setup(torch, 1_000_000, 1536, dev, batch)
-    for _ in range(6 if case == "step" else 12):
+    for _ in range(6 if case in ("step", "mid") else 12):
         st.search(q, 100, algo="scan" if case == "scan" else "auto")
 torch.cuda.synchronize()
 print("done", case)
