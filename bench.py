@@ -679,7 +679,8 @@ def run_ours(args):
         e2e_ms = (time.perf_counter() - t0) * 1e3
         for o in outs[: min(depth, args.steps)]:
             assert (o[1] == ids0_h).all(), "host-buffer path and device path disagree"
-        e2e_api = "ShardedSearcher.search_host_submit/_wait on every rank (pinned host buffers)"
+        e2e_api = ("ShardedSearcher.search_host_submit/_wait on every rank (pinned host buffers; each rank uploads "
+                   "its 1/N of the batch, NVLink all-gather; every rank downloads the merged result)")
         # one blocking call after the other, for the per-call latency
         barrier()
         t0 = time.perf_counter()
@@ -1006,7 +1007,9 @@ def run_ours(args):
             "certificate": "rigorous" if N.get_option("strict_certificate") else "statistical",
         },
         "clocks": clocks,
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * args.dim * 4 * (world if row_shard else 1),
+        # row shards: rank g uploads rows [g B/N, (g+1) B/N) of the batch over its own PCIe link and an NVLink
+        # all-gather completes it on every GPU (each query crosses PCIe once); every rank reads the whole result back
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * args.dim * 4,
                 "d2h_bytes_per_step": (B * k * 12 + B * 4) * (world if row_shard else 1),
                 "ms_per_step": e2e_ms / args.steps, "in_flight": depth, "api": e2e_api,
                 "blocking": ({"value": units / (e2e_serial_ms * 1e-3), "unit": UNIT,

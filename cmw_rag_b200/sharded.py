@@ -190,6 +190,7 @@ class ShardedSearcher:
         self._exchange = exchange
         self.timings = None  # set to {} to collect CUDA-event pairs per phase (bench.py)
         self._copy_streams = None
+        self._upload_group = None
         self._qbufs: dict = {}
 
     # -- helpers ------------------------------------------------------------------------------------
@@ -234,12 +235,17 @@ class ShardedSearcher:
         (scores f32[B,k], ids i64[B,k], flags i32[B]) numpy arrays (allocated when None); synchronises."""
         return self.search_host_wait(self.search_host_submit(queries_host, k, out=out, **kw))
 
-    def search_host_submit(self, queries_host, k: int, out=None, **kw):
+    def search_host_submit(self, queries_host, k: int, out=None, upload: str = "sliced", **kw):
         """Pipelined host-buffer form, the row-sharded twin of cmw_search_host_submit: the queries go up on a copy
         stream, the search (with both exchanges) runs on the caller's current stream behind that copy, the merged
         result comes down on a second copy stream; returns a ticket for ``search_host_wait``.  With two or more
         tickets outstanding the copies of one batch hide under the kernels of its neighbours.  Every rank must
-        submit the same batches in the same order (the exchanges are collectives)."""
+        submit the same batches in the same order (the exchanges are collectives).
+
+        ``upload="sliced"`` (default, world > 1): ``queries_host`` holds the same batch on every rank; rank g
+        copies only rows ``[g B/G, (g+1) B/G)`` over ITS PCIe link and an all-gather over NVLink completes the batch
+        on every GPU -- each query crosses PCIe once (B D 4 bytes per step in total), instead of G ranks pulling
+        G copies of the batch out of the same host memory.  ``upload="full"``: every rank copies the whole batch."""
         import numpy as np
         import torch
 
@@ -249,17 +255,32 @@ class ShardedSearcher:
         up, down = self._copy_streams
         main = torch.cuda.current_stream(dev)
         src = torch.from_numpy(np.ascontiguousarray(queries_host, dtype=np.float32))
-        b = src.shape[0]
+        b, dim = src.shape
         if out is None:
             out = (np.empty((b, k), np.float32), np.empty((b, k), np.int64), np.zeros((b,), np.int32))
+        sliced = upload == "sliced" and self.world > 1 and b >= self.world
+        per = (b + self.world - 1) // self.world if sliced else b
+        rows_buf = per * self.world if sliced else b
         # query buffers are the searcher's own and go round (an allocation in flight -- cudaMalloc behind the
         # caching allocator -- stalls the host for tens of milliseconds while the GPU is busy)
-        free = self._qbufs.setdefault(tuple(src.shape), [])
-        q = free.pop() if free else torch.empty(src.shape, dtype=torch.float32, device=dev)
+        free = self._qbufs.setdefault((rows_buf, dim), [])
+        qbuf = free.pop() if free else torch.zeros((rows_buf, dim), dtype=torch.float32, device=dev)
         with torch.cuda.stream(up):
-            q.copy_(src, non_blocking=True)
+            if sliced:
+                if self._upload_group is None:  # its own communicator: independent of the search's exchanges
+                    self._upload_group = self.dist.new_group(backend="nccl") if self.group is None else self.group
+                lo = min(b, self.rank * per)
+                hi = min(b, lo + per)
+                mine = qbuf[self.rank * per:(self.rank + 1) * per]
+                if hi > lo:
+                    mine[: hi - lo].copy_(src[lo:hi], non_blocking=True)
+                # in place: rank g's slice already sits at its position of the gathered batch
+                self.dist.all_gather_into_tensor(qbuf.view(-1), mine.reshape(-1), group=self._upload_group)
+            else:
+                qbuf.copy_(src, non_blocking=True)
             e_in = torch.cuda.Event()
             e_in.record(up)
+        q = qbuf[:b]
         main.wait_event(e_in)
         ms, mi, fl = self.search(q, k, **kw)
         fl = fl.to(torch.int32)
@@ -274,7 +295,8 @@ class ShardedSearcher:
             e_out.record(down)
         # the ticket keeps every device tensor alive until the wait: nothing allocated on one stream is handed
         # back to the caching allocator while another stream may still be reading it
-        return {"event": e_out, "out": out, "keep": (src, ms, mi, fl), "q": q}
+        return {"event": e_out, "out": out, "keep": (src, ms, mi, fl), "q": qbuf,
+                "h2d_bytes": (min(b, self.rank * per + per) - min(b, self.rank * per) if sliced else b) * dim * 4}
 
     def search_host_wait(self, ticket):
         ticket["event"].synchronize()
