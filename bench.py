@@ -59,9 +59,11 @@ def parse_args():
     ap.add_argument("--f16-bits", type=int, default=0, help="experiment: significand bits kept in fp16 tiles (8..11)")
     ap.add_argument("--shard", default="rows", choices=["rows", "queries"],
                     help="N > 1: row-sharded corpus + exchange + merge (default), or replicated corpus, sharded batch")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
-                    help="--shard rows: two-phase search over NCCL all-gathers, or one-phase with the fused NVLink "
-                         "peer-memory exchange")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "gather", "nccl", "peer"],
+                    help="--shard rows: the two exchanges of the two-phase search over NVLink peer memory "
+                         "(cmw_peer_gather: `gather`; `auto` = that when every rank can map its peers' buffers, else "
+                         "NCCL), over NCCL all-gathers (`nccl`), or the one-phase search with the fused peer-memory "
+                         "exchange + merge (`peer`)")
     ap.add_argument("--no-f32", action="store_true", help="16-bit tiles only")
     ap.add_argument("--cpu-queries", type=int, default=16, help="queries of the exact fp64 brute-force CPU sample")
     ap.add_argument("--parity-queries", type=int, default=0,
@@ -542,7 +544,7 @@ def run_ours(args):
 
     from cmw_rag_b200 import _native as N
     from cmw_rag_b200.engine import pinned_empty
-    from cmw_rag_b200.sharded import PeerExchange, ShardedSearcher, shard_bounds
+    from cmw_rag_b200.sharded import PeerExchange, PeerGather, ShardedSearcher, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -574,10 +576,27 @@ def run_ours(args):
 
     searcher = None
     peer_ex = None
+    peer_gather = None
+    exchange_used = args.exchange
     if row_shard:
         if args.exchange == "peer":
             peer_ex = PeerExchange(device=local_rank, max_batch=B, max_k=k)
-        searcher = ShardedSearcher(st, exchange=peer_ex)
+        elif args.exchange in ("auto", "gather"):
+            # one decision for all ranks: the peer path needs every rank to have mapped every peer's buffer
+            ok = 1
+            try:
+                peer_gather = PeerGather(device=local_rank, max_batch=max(B, 1024), max_k=k)
+            except Exception as exc:  # noqa: BLE001
+                if args.exchange == "gather":
+                    raise
+                print(f"bench.py: rank {rank}: peer-memory exchange unavailable ({exc!r})", file=sys.stderr)
+                ok = 0
+            t_ok = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            if int(t_ok.item()) == 0:
+                peer_gather = None
+            exchange_used = "gather" if peer_gather is not None else "nccl"
+        searcher = ShardedSearcher(st, exchange=peer_ex, gather=peer_gather)
 
     def step_device():
         if searcher is None:
@@ -811,13 +830,13 @@ def run_ours(args):
             config4 = {"skipped": f"needs {need_b >> 30} GiB of HBM per GPU, {free_b >> 30} GiB free on rank {rank}"}
         elif world == 1:
             try:
-                config4 = config4_record(torch, dist, N, args, device, rank, world)
+                config4 = config4_record(torch, dist, N, args, device, rank, world, peer_gather)
             except Exception as exc:  # noqa: BLE001 -- an extra record must not cost the headline line
                 print(f"bench.py: config4_weak failed: {exc!r}", file=sys.stderr)
                 config4 = {"error": repr(exc)}
                 N.profile_enable(False)
         else:
-            config4 = config4_record(torch, dist, N, args, device, rank, world)
+            config4 = config4_record(torch, dist, N, args, device, rank, world, peer_gather)
     if world > 1:
         dist.barrier()
 
@@ -981,9 +1000,12 @@ def run_ours(args):
     if row_shard:
         par = (f"corpus row-sharded over {world} GPUs ({shard_rows} rows each), same {B} queries on every rank; " +
                ("one-phase search + fused NVLink peer-store exchange + merge kernels (no collective)"
-                if args.exchange == "peer" else
-                "two-phase search: filter | NCCL all-gather of the k-th filter scores | rescoring shared between the "
-                "shards | NCCL all-gather of the packed candidate blocks | merge kernel + cross-shard certificate"))
+                if exchange_used == "peer" else
+                "two-phase search: filter | exchange of the k-th filter scores | rescoring shared between the shards | "
+                "exchange of the packed candidate blocks | merge kernel + cross-shard certificate; exchanges = " +
+                ("peer stores over NVLink into every rank's gather buffer + epoch flags, read in place "
+                 "(cmw_peer_gather; no NCCL on the data path)" if exchange_used == "gather" else
+                 "NCCL all-gathers")))
     elif world > 1:
         par = f"corpus replicated, query batch sharded over {world} GPUs (no collective)"
     else:
@@ -1002,6 +1024,7 @@ def run_ours(args):
             "l2": "inputs larger than L2 (16-bit tiles >= 3 GB per pass vs 126 MB at N = 1; at N > 1 a shard's tiles "
                   "are re-read from HBM every step all the same: the per-step pools and candidates, 0.3 GB, evict them), "
                   "no flush",
+            "exchange": exchange_used if row_shard else None,
             "mode": args.mode, "algo": args.algo, "tiles16": args.tiles16, "f16_bits": int(N.get_option("f16_bits")),
             "uncertified_queries": uncertified,
             "certificate": "rigorous" if N.get_option("strict_certificate") else "statistical",
@@ -1107,7 +1130,7 @@ def bf16_tiles_record(torch, N, args, device, q, ids_ref_h, sc_ref):
     return out
 
 
-def config4_record(torch, dist, N, args, device, rank, world):
+def config4_record(torch, dist, N, args, device, rank, world, gather=None):
     """BASELINE.json config 4 as weak scaling (200M x 1536 bf16 = 614 GB fits 8 GPUs, not 1 or 2):
     `--config4-rows` bf16 rows PER GPU, batch 1024, top-100, approximate mode (no fp32 tiles at this size), the
     exchange + merge in the timed region.  The driver's N = 1 run of this record is the one-shard baseline."""
@@ -1120,7 +1143,7 @@ def config4_record(torch, dist, N, args, device, rank, world):
     torch.cuda.synchronize(device)
     build_s = time.perf_counter() - t0
     q4, needle = make_queries(torch, dist, first, lo, B, args.dim, device, 11, rank, world)
-    s4 = ShardedSearcher(st4) if world > 1 else None
+    s4 = ShardedSearcher(st4, gather=gather) if world > 1 else None
 
     def step():
         if s4 is None:
@@ -1173,7 +1196,7 @@ def config4_record(torch, dist, N, args, device, rank, world):
         slo, shi = shard_bounds_local(rows, world, rank)
         st5, first5 = build_store(torch, args.dim, device, slo, shi, f32=False, tiles16="bf16")
         q5, needle5 = make_queries(torch, dist, first5, slo, B, args.dim, device, 13, rank, world)
-        s5 = ShardedSearcher(st5)
+        s5 = ShardedSearcher(st5, gather=gather)
         for _ in range(3):
             out5 = s5.search(q5, k, mode="bf16")
         torch.cuda.synchronize(device)

@@ -96,6 +96,11 @@ SIGNATURES = {
                                   c_size_t, c_void_p]),
     "cmw_shard_merge": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
+    "cmw_shard_merge_ex": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
+    "cmw_peer_gather_bytes": (c_size_t, [c_int, c_size_t]),
+    "cmw_peer_gather": (c_int, [POINTER(c_void_p), c_int, c_int, c_size_t, c_void_p, c_size_t, c_uint32, c_int,
+                                c_void_p, POINTER(c_void_p), c_void_p]),
     "cmw_kernel_launches": (c_int64, []),
     "cmw_profile_enable": (c_int, [c_int]),
     "cmw_profile_read": (c_int, [POINTER(c_double), POINTER(c_int64), c_int]),

@@ -740,12 +740,19 @@ int cmw_shard_kth(const float* filter_topk_gathered_dev, int G, int B, int k, fl
 
 int cmw_shard_merge(const void* blocks_dev, int G, int B, int k, int k_out, float* out_scores_dev,
                     int64_t* out_ids_dev, double* out_scores64_dev, int32_t* out_flags_dev, void* stream) {
+    return cmw_shard_merge_ex(blocks_dev, G, B, k, k_out, out_scores_dev, out_ids_dev, out_scores64_dev, out_flags_dev,
+                              nullptr, stream);
+}
+
+int cmw_shard_merge_ex(const void* blocks_dev, int G, int B, int k, int k_out, float* out_scores_dev,
+                       int64_t* out_ids_dev, double* out_scores64_dev, int32_t* out_flags_dev,
+                       const int32_t* peer_status_dev, void* stream) {
     CMW_REQUIRE(blocks_dev && out_scores_dev && out_ids_dev, "cmw_shard_merge: NULL argument");
     CMW_REQUIRE(G >= 1 && B >= 0 && k >= 1 && k_out >= 1, "cmw_shard_merge: bad sizes");
     if (B == 0) return 0;
     PhaseTimer t(5, (cudaStream_t)stream);
     return launch_shard_merge(blocks_dev, G, B, k, k_out, out_scores_dev, out_ids_dev, out_scores64_dev,
-                              out_flags_dev, (cudaStream_t)stream);
+                              out_flags_dev, peer_status_dev, (cudaStream_t)stream);
 }
 
 int cmw_search_host(cmw_store* h, const float* queries_host, int batch, int k, int metric, int mode,

@@ -296,7 +296,7 @@ __host__ __device__ inline ShardBlock shard_block(int B, int k) {
 int launch_pool_topk_scores(Pool pool, int batch, int k, float* out, cudaStream_t stream);
 int launch_shard_kth(const float* gathered, int G, int B, int k, float* out_kth, cudaStream_t stream);
 int launch_shard_merge(const void* blocks, int G, int B, int k, int k_out, float* out_scores, int64_t* out_ids,
-                       double* out_scores64, int32_t* out_flags, cudaStream_t stream);
+                       double* out_scores64, int32_t* out_flags, const int32_t* peer_status, cudaStream_t stream);
 
 // host-API resources (store.cu)
 int ensure_pinned(Store* s, size_t bytes);

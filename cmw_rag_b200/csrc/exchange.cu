@@ -26,6 +26,7 @@ namespace cmw {
 
 constexpr int kXMaxRanks = 64;
 constexpr size_t kXHeaderBytes = 2048;
+static inline size_t x_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct XPeers {
     uint8_t* buf[kXMaxRanks];
@@ -46,6 +47,46 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     return t;
 }
 
+// publish (end of a send kernel, all threads): every block fences its peer stores system-wide; the last one to
+// finish writes the shape word and then raises this rank's epoch flag on every peer
+__device__ __forceinline__ void x_publish(const XPeers& peers, int G, int rank, int parity, uint32_t epoch,
+                                          uint32_t shape) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t* done = x_done(peers.buf[rank], parity);
+        const uint32_t prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) {
+            *done = 0;  // ready for the next use of this parity
+            __threadfence_system();
+            for (int g = 0; g < G; ++g) *(volatile uint32_t*)(x_shape(peers.buf[g], parity) + rank) = shape;
+            __threadfence_system();
+            for (int g = 0; g < G; ++g) {
+                volatile uint32_t* f = x_flags(peers.buf[g], parity) + rank;
+                *f = epoch;
+            }
+            __threadfence_system();
+        }
+    }
+}
+
+// bounded wait (threads 0 .. G-1 of a block; the others pass through) until source rank threadIdx.x has published
+// `epoch` with the expected shape word.  Returns false for a thread whose rank timed out or is out of step.
+__device__ __forceinline__ bool x_wait(uint8_t* self, int G, int parity, uint32_t epoch, uint32_t shape,
+                                       uint64_t timeout_ns) {
+    if ((int)threadIdx.x >= G) return true;
+    volatile uint32_t* f = x_flags(self, parity) + threadIdx.x;
+    const uint64_t t0 = global_timer_ns();
+    unsigned ns = 32;
+    while (*f != epoch) {
+        if (global_timer_ns() - t0 > timeout_ns) return false;
+        __nanosleep(ns);
+        if (ns < 2048) ns <<= 1;
+    }
+    __threadfence_system();
+    return *(volatile uint32_t*)(x_shape(self, parity) + threadIdx.x) == shape;
+}
+
 __global__ void __launch_bounds__(256)
 exchange_send_kernel(XPeers peers, int G, int rank, int B, int k, size_t slot_elems, size_t parity_bytes, int parity,
                      uint32_t epoch, const double* __restrict__ scores, const int64_t* __restrict__ ids,
@@ -63,25 +104,7 @@ exchange_send_kernel(XPeers peers, int G, int rank, int B, int k, size_t slot_el
             if (i < (size_t)B) df[i] = flags != nullptr ? flags[i] : 0;
         }
     }
-    // publish: every block fences its peer stores system-wide; the last one to finish raises the flags
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t* done = x_done(peers.buf[rank], parity);
-        const uint32_t prev = atomicAdd(done, 1u);
-        if (prev == gridDim.x - 1) {
-            *done = 0;  // ready for the next use of this parity
-            __threadfence_system();
-            const uint32_t shape = ((uint32_t)B << 12) | (uint32_t)k;
-            for (int g = 0; g < G; ++g) *(volatile uint32_t*)(x_shape(peers.buf[g], parity) + rank) = shape;
-            __threadfence_system();
-            for (int g = 0; g < G; ++g) {
-                volatile uint32_t* f = x_flags(peers.buf[g], parity) + rank;
-                *f = epoch;
-            }
-            __threadfence_system();
-        }
-    }
+    x_publish(peers, G, rank, parity, epoch, ((uint32_t)B << 12) | (uint32_t)k);
 }
 
 __global__ void __launch_bounds__(256)
@@ -94,26 +117,8 @@ exchange_merge_kernel(uint8_t* self, int G, int B, int k, int k_out, size_t slot
     if (threadIdx.x == 0) bad = 0;
     __syncthreads();
     // wait -- for a bounded time -- until every source rank has published this epoch
-    if (threadIdx.x < G) {
-        volatile uint32_t* f = x_flags(self, parity) + threadIdx.x;
-        const uint64_t t0 = global_timer_ns();
-        unsigned ns = 32;
-        bool ok = true;
-        while (*f != epoch) {
-            if (global_timer_ns() - t0 > timeout_ns) {
-                ok = false;
-                break;
-            }
-            __nanosleep(ns);
-            if (ns < 2048) ns <<= 1;
-        }
-        if (ok) {
-            __threadfence_system();
-            const uint32_t shape = *(volatile uint32_t*)(x_shape(self, parity) + threadIdx.x);
-            ok = shape == (((uint32_t)B << 12) | (uint32_t)k);  // every rank must exchange the same (B, k)
-        }
-        if (!ok) atomicExch(&bad, 1);
-    }
+    // every rank must exchange the same (B, k)
+    if (!x_wait(self, G, parity, epoch, ((uint32_t)B << 12) | (uint32_t)k, timeout_ns)) atomicExch(&bad, 1);
     __syncthreads();
     __threadfence_system();
     const int b = blockIdx.x;
@@ -171,6 +176,46 @@ exchange_merge_kernel(uint8_t* self, int G, int B, int k, int k_out, size_t slot
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Generic peer all-gather: the two exchanges of the TWO-PHASE row-sharded search (sharded.py) over NVLink peer
+// memory instead of NCCL.  Same buffer header and epoch-parity protocol as above.  A parity region holds G slots
+// of `nbytes`, rank-major and contiguous -- exactly what an all-gather into one tensor leaves -- so the consumers
+// (shard_kth_kernel, shard_merge_kernel) read the gathered data IN PLACE in this rank's peer buffer.  The send
+// kernel stores this rank's slot into every peer's region and publishes; the wait kernel (one block) holds the
+// stream until every rank's slot of this epoch has landed, for a bounded time: a dead or out-of-step peer sets
+// CMW_FLAG_PEER_TIMEOUT in `status` (sticky; cmw_shard_merge_ex then flags every query) instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+peer_gather_send_kernel(XPeers peers, int G, int rank, size_t nbytes, size_t region_bytes, int parity, uint32_t epoch,
+                        const uint8_t* __restrict__ src) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t off = kXHeaderBytes + (size_t)parity * region_bytes + (size_t)rank * nbytes;
+    if ((nbytes & 15) == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        const size_t n = nbytes >> 4;
+        for (size_t i = first; i < n; i += stride) {
+            const uint4 v = __ldg(s4 + i);
+            for (int g = 0; g < G; ++g) reinterpret_cast<uint4*>(peers.buf[g] + off)[i] = v;
+        }
+    } else {
+        const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src);
+        const size_t n = nbytes >> 2;
+        for (size_t i = first; i < n; i += stride) {
+            const uint32_t v = __ldg(s1 + i);
+            for (int g = 0; g < G; ++g) reinterpret_cast<uint32_t*>(peers.buf[g] + off)[i] = v;
+        }
+    }
+    x_publish(peers, G, rank, parity, epoch, (uint32_t)(nbytes >> 2));
+}
+
+__global__ void __launch_bounds__(64)
+peer_gather_wait_kernel(uint8_t* self, int G, int parity, uint32_t epoch, uint32_t shape, uint64_t timeout_ns,
+                        int32_t* __restrict__ status) {
+    if (!x_wait(self, G, parity, epoch, shape, timeout_ns)) atomicOr(status, CMW_FLAG_PEER_TIMEOUT);
+    __threadfence_system();
+}
+
 }  // namespace cmw
 
 using namespace cmw;
@@ -220,6 +265,45 @@ int cmw_peer_close(void* dev_ptr) {
 
 int cmw_peer_free(void* dev_ptr) {
     if (dev_ptr) CMW_CUDA_OK(cudaFree(dev_ptr));
+    return 0;
+}
+
+size_t cmw_peer_gather_bytes(int G, size_t max_bytes_per_rank) {
+    if (G < 1 || G > kXMaxRanks || max_bytes_per_rank < 4) return 0;
+    return kXHeaderBytes + 2 * (size_t)G * x_align_up(max_bytes_per_rank, 256);
+}
+
+int cmw_peer_gather(void* const* peer_bufs_host, int G, int rank, size_t max_bytes_per_rank, const void* src_dev,
+                    size_t nbytes, uint32_t epoch, int timeout_ms, int32_t* status_dev, void** gathered_dev_out,
+                    void* stream_v) {
+    CMW_REQUIRE(peer_bufs_host && src_dev && status_dev && gathered_dev_out, "cmw_peer_gather: NULL argument");
+    CMW_REQUIRE(G >= 1 && G <= kXMaxRanks && rank >= 0 && rank < G, "cmw_peer_gather: bad rank/world");
+    CMW_REQUIRE(nbytes >= 4 && (nbytes & 3) == 0 && nbytes <= max_bytes_per_rank && (nbytes >> 2) < 0xffffffffull,
+                "cmw_peer_gather: nbytes = %zu must be a multiple of 4 and at most %zu", nbytes, max_bytes_per_rank);
+    CMW_REQUIRE((reinterpret_cast<uintptr_t>(src_dev) & 15) == 0, "cmw_peer_gather: src_dev must be 16-byte aligned");
+    CMW_REQUIRE(epoch != 0, "cmw_peer_gather: epoch must be non-zero");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    XPeers peers;
+    for (int g = 0; g < G; ++g) {
+        CMW_REQUIRE(peer_bufs_host[g] != nullptr, "cmw_peer_gather: peer buffer %d is NULL", g);
+        peers.buf[g] = reinterpret_cast<uint8_t*>(peer_bufs_host[g]);
+    }
+    const size_t region_bytes = (size_t)G * x_align_up(max_bytes_per_rank, 256);
+    const int parity = (int)(epoch & 1u);
+    const uint64_t timeout_ns = (uint64_t)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
+    const size_t vecs = (nbytes & 15) == 0 ? nbytes >> 4 : nbytes >> 2;
+    int blocks = (int)((vecs + 255) / 256);
+    if (blocks > 296) blocks = 296;
+    if (blocks < 1) blocks = 1;
+    peer_gather_send_kernel<<<blocks, 256, 0, stream>>>(peers, G, rank, nbytes, region_bytes, parity, epoch,
+                                                        reinterpret_cast<const uint8_t*>(src_dev));
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    peer_gather_wait_kernel<<<1, 64, 0, stream>>>(peers.buf[rank], G, parity, epoch, (uint32_t)(nbytes >> 2),
+                                                  timeout_ns, status_dev);
+    CMW_LAUNCHED();
+    CMW_CUDA_OK(cudaGetLastError());
+    *gathered_dev_out = peers.buf[rank] + kXHeaderBytes + (size_t)parity * region_bytes;
     return 0;
 }
 

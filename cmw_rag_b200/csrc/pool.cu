@@ -764,10 +764,20 @@ shard_kth_reg_kernel(const float* __restrict__ gathered, int G, int B, int k, fl
 __global__ void __launch_bounds__(256)
 shard_merge_kernel(const uint8_t* __restrict__ blocks, int G, int B, int k, int k_out,
                    float* __restrict__ out_scores, int64_t* __restrict__ out_ids, double* __restrict__ out_scores64,
-                   int32_t* __restrict__ out_flags) {
+                   int32_t* __restrict__ out_flags, const int32_t* __restrict__ peer_status) {
     extern __shared__ __align__(16) uint8_t sm_smem[];
     __shared__ int warp_tot[8];
     const int b = blockIdx.x;
+    if (peer_status != nullptr && *peer_status != 0) {
+        // an exchange over peer memory did not complete (cmw_peer_gather): nothing below can be trusted
+        for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
+            out_scores[(size_t)b * k_out + j] = -INFINITY;
+            out_ids[(size_t)b * k_out + j] = -1;
+            if (out_scores64 != nullptr) out_scores64[(size_t)b * k_out + j] = -INFINITY;
+        }
+        if (threadIdx.x == 0 && out_flags != nullptr) out_flags[b] = *peer_status;
+        return;
+    }
     const int n_all = G * k;
     const int m_all = next_pow2(n_all < 2 ? 2 : n_all);
     uint64_t* hi = reinterpret_cast<uint64_t*>(sm_smem);
@@ -884,7 +894,7 @@ int launch_shard_kth(const float* gathered, int G, int B, int k, float* out_kth,
 }
 
 int launch_shard_merge(const void* blocks, int G, int B, int k, int k_out, float* out_scores, int64_t* out_ids,
-                       double* out_scores64, int32_t* out_flags, cudaStream_t stream) {
+                       double* out_scores64, int32_t* out_flags, const int32_t* peer_status, cudaStream_t stream) {
     const int n = G * k;
     CMW_REQUIRE(n <= 8192, "cmw_shard_merge: G*k = %d exceeds 8192", n);
     const size_t smem = (size_t)next_pow2_host(n < 2 ? 2 : n) * 16;
@@ -894,7 +904,7 @@ int launch_shard_merge(const void* blocks, int G, int B, int k, int k_out, float
         smem_set.done(smem);
     }
     shard_merge_kernel<<<B, 256, smem, stream>>>(reinterpret_cast<const uint8_t*>(blocks), G, B, k, k_out, out_scores,
-                                                out_ids, out_scores64, out_flags);
+                                                out_ids, out_scores64, out_flags, peer_status);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;

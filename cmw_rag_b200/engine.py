@@ -406,16 +406,32 @@ def merge_topk(scores64, ids, k_out: int):
     return out_s, out_i, out_s64
 
 
-def shard_kth(filter_topk_gathered, k: int):
-    """f32[G,B,k] gathered per-shard filter scores -> f32[B]: the k-th best over all shards."""
+class DevicePtr:
+    """A raw device pointer to `nbytes` of gathered data that lives outside torch (in a peer buffer of
+    libcmwdense.so: PeerGather); `status` = the exchange's i32[1] status tensor."""
+
+    __slots__ = ("ptr", "nbytes", "device", "status")
+
+    def __init__(self, ptr: int, nbytes: int, device, status=None):
+        self.ptr, self.nbytes, self.device, self.status = int(ptr), int(nbytes), device, status
+
+
+def shard_kth(filter_topk_gathered, k: int, world: int | None = None, batch: int | None = None):
+    """f32[G,B,k] gathered per-shard filter scores (a tensor, or a DevicePtr with `world` and `batch`) -> f32[B]:
+    the k-th best over all shards."""
     torch = _torch()
-    t = filter_topk_gathered.contiguous()
-    g, b, kk = t.shape
-    assert kk == k and t.dtype == torch.float32 and t.is_cuda
-    out = torch.empty((b,), dtype=torch.float32, device=t.device)
+    if isinstance(filter_topk_gathered, DevicePtr):
+        g, b, dev, ptr = int(world), int(batch), filter_topk_gathered.device, filter_topk_gathered.ptr
+        assert filter_topk_gathered.nbytes >= g * b * k * 4
+    else:
+        t = filter_topk_gathered.contiguous()
+        g, b, kk = t.shape
+        assert kk == k and t.dtype == torch.float32 and t.is_cuda
+        dev, ptr = t.device, t.data_ptr()
+    out = torch.empty((b,), dtype=torch.float32, device=dev)
     if b:
-        N.check(N.lib().cmw_shard_kth(t.data_ptr(), g, b, k, out.data_ptr(),
-                                      torch.cuda.current_stream(t.device).cuda_stream), "cmw_shard_kth")
+        N.check(N.lib().cmw_shard_kth(ptr, g, b, k, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                "cmw_shard_kth")
     return out
 
 
@@ -423,14 +439,19 @@ def shard_merge(blocks, world: int, batch: int, k: int, k_out: int | None = None
     """uint8[G * block_bytes] gathered shard blocks -> (scores f32[B,k_out], ids i64, scores64 f64, flags i32)."""
     torch = _torch()
     k_out = k if k_out is None else k_out
-    dev = blocks.device
+    status = None
+    if isinstance(blocks, DevicePtr):
+        dev, ptr, have, status = blocks.device, blocks.ptr, blocks.nbytes, blocks.status
+    else:
+        dev, ptr, have = blocks.device, blocks.data_ptr(), blocks.numel()
     out_s = torch.empty((batch, k_out), dtype=torch.float32, device=dev)
     out_i = torch.empty((batch, k_out), dtype=torch.int64, device=dev)
     out_s64 = torch.empty((batch, k_out), dtype=torch.float64, device=dev)
     flags = torch.zeros((batch,), dtype=torch.int32, device=dev)
     if batch:
-        assert blocks.numel() >= world * int(N.lib().cmw_shard_block_bytes(batch, k))
-        N.check(N.lib().cmw_shard_merge(blocks.data_ptr(), world, batch, k, k_out, out_s.data_ptr(), out_i.data_ptr(),
-                                        out_s64.data_ptr(), flags.data_ptr(),
-                                        torch.cuda.current_stream(dev).cuda_stream), "cmw_shard_merge")
+        assert have >= world * int(N.lib().cmw_shard_block_bytes(batch, k))
+        N.check(N.lib().cmw_shard_merge_ex(ptr, world, batch, k, k_out, out_s.data_ptr(), out_i.data_ptr(),
+                                           out_s64.data_ptr(), flags.data_ptr(),
+                                           status.data_ptr() if status is not None else None,
+                                           torch.cuda.current_stream(dev).cuda_stream), "cmw_shard_merge")
     return out_s, out_i, out_s64, flags

@@ -124,6 +124,91 @@ class PeerExchange:
         self._own, self._opened = None, []
 
 
+class PeerGather:
+    """The two exchanges of the two-phase row-sharded search over NVLink peer memory instead of NCCL
+    (cmw_peer_gather, exchange.cu): a send kernel stores this rank's slot into every rank's peer buffer and raises
+    an epoch flag, a one-block kernel holds the stream -- for a bounded time -- until all slots have landed, and the
+    consumers (cmw_shard_kth, cmw_shard_merge) read the gathered data in place.  No collective call, no NCCL kernel
+    on the data path; a dead or out-of-step peer yields FLAG_PEER_TIMEOUT on every query instead of a hung GPU
+    (the status is sticky: rebuild the exchange).  Sized for ``max_bytes`` per rank =
+    ``cmw_shard_block_bytes(max_batch, max_k)``."""
+
+    def __init__(self, group=None, device: int = 0, max_batch: int = 4096, max_k: int = 128, timeout_ms: int = 0):
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _native as N
+
+        self._N = N
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = int(device)
+        self.timeout_ms = int(timeout_ms)
+        lib = N.lib()
+        self.max_bytes = int(lib.cmw_shard_block_bytes(int(max_batch), int(max_k)))
+        nbytes = int(lib.cmw_peer_gather_bytes(self.world, self.max_bytes))
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        N.check(lib.cmw_peer_alloc(self.device, nbytes, ctypes.byref(own), handle), "cmw_peer_alloc")
+        handles: list = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self._own = own
+        self._opened = []
+        ptrs = []
+        for g in range(self.world):
+            if g == self.rank:
+                ptrs.append(own.value)
+                continue
+            p = ctypes.c_void_p()
+            N.check(lib.cmw_peer_open(self.device, ctypes.create_string_buffer(handles[g], 64), ctypes.byref(p)),
+                    "cmw_peer_open")
+            self._opened.append(p)
+            ptrs.append(p.value)
+        self._ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=f"cuda:{self.device}")
+        self.epoch = 0
+        dist.barrier(group=group)
+
+    def gather(self, t):
+        """t: a contiguous CUDA tensor (the same number of bytes on every rank) -> DevicePtr of the world * nbytes
+        gathered bytes, rank-major, valid until the call after next."""
+        import ctypes
+
+        import torch
+
+        from .engine import DevicePtr
+
+        t = t.contiguous()
+        nbytes = t.numel() * t.element_size()
+        if nbytes > self.max_bytes:
+            raise ValueError(f"exchange sized for {self.max_bytes} bytes per rank, got {nbytes}")
+        self.epoch += 1
+        out = ctypes.c_void_p()
+        self._N.check(
+            self._N.lib().cmw_peer_gather(self._ptrs, self.world, self.rank, self.max_bytes, t.data_ptr(), nbytes,
+                                          (self.epoch & 0xffffffff) or 2, self.timeout_ms, self.status.data_ptr(),
+                                          ctypes.byref(out), torch.cuda.current_stream(t.device).cuda_stream),
+            "cmw_peer_gather")
+        return DevicePtr(out.value, self.world * nbytes, t.device, self.status)
+
+    def close(self):
+        import torch
+        import torch.distributed as dist
+
+        if self._own is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # nobody may still be writing into a buffer that is about to go
+        lib = self._N.lib()
+        for p in self._opened:
+            lib.cmw_peer_close(p)
+        lib.cmw_peer_free(self._own)
+        self._own, self._opened = None, []
+
+
 class CudaShardBackend:
     """The four device steps of the two-phase row-sharded search, as implemented by libcmwdense.so for one
     ``DenseStore`` shard.  (A stand-in with the same four methods is what the gloo CPU tests inject.)"""
@@ -134,10 +219,10 @@ class CudaShardBackend:
     def filter(self, q, k, **kw):
         return self.store.search_filter(q, k, **kw)
 
-    def kth(self, gathered, k):
+    def kth(self, gathered, k, world=None, batch=None):
         from .engine import shard_kth
 
-        return shard_kth(gathered, k)
+        return shard_kth(gathered, k, world=world, batch=batch)
 
     def finish(self, q, k, kth, **kw):
         return self.store.search_finish(q, k, global_kth=kth, **kw)
@@ -163,7 +248,8 @@ class ShardedSearcher:
     every rank, one packed exchange, merge."""
 
     def __init__(self, store=None, group=None, local_search: Callable | None = None,
-                 merge: Callable | None = None, exchange: PeerExchange | None = None, backend=None):
+                 merge: Callable | None = None, exchange: PeerExchange | None = None, backend=None,
+                 gather: PeerGather | None = None):
         import torch.distributed as dist
 
         self.dist = dist
@@ -188,6 +274,7 @@ class ShardedSearcher:
         self._local_search = local_search
         self._merge = merge
         self._exchange = exchange
+        self._gather = gather  # two-phase search: both exchanges over NVLink peer memory instead of NCCL
         self.timings = None  # set to {} to collect CUDA-event pairs per phase (bench.py)
         self._copy_streams = None
         self._upload_group = None
@@ -321,16 +408,27 @@ class ShardedSearcher:
         ftop = be.filter(queries, k, **kw)
         self._mark("filter_done")
         kth = None
+        peer = self._gather if self.world > 1 else None
         if exact and self.world > 1:
-            g_ftop = self._all_gather(ftop).view(self.world, b, k)  # rank-major == a [world, B, k] stack
-            self._mark("gather1_done")
-            kth = be.kth(g_ftop, k)
+            if peer is not None:
+                g_ftop = peer.gather(ftop)  # in place in this rank's peer buffer, rank-major == [world, B, k]
+                self._mark("gather1_done")
+                kth = be.kth(g_ftop, k, world=self.world, batch=b)
+            else:
+                g_ftop = self._all_gather(ftop).view(self.world, b, k)  # rank-major == a [world, B, k] stack
+                self._mark("gather1_done")
+                kth = be.kth(g_ftop, k)
         else:
             self._mark("gather1_done")
         self._mark("kth_done")
         block = be.finish(queries, k, kth, **kw)
         self._mark("finish_done")
-        blocks = self._all_gather(block) if self.world > 1 else block
+        if self.world == 1:
+            blocks = block
+        elif peer is not None:
+            blocks = peer.gather(block)
+        else:
+            blocks = self._all_gather(block)
         self._mark("gather2_done")
         out = be.merge(blocks, self.world, b, k)
         self._mark("merge_done")

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CMW_ABI_VERSION 5
+#define CMW_ABI_VERSION 6
 
 /* metric -- rag_engine/storage/vector_store.py:48-51 fixes the collection to cosine
  * ({"hnsw:space": "cosine"}); inner product is the north star's second metric. */
@@ -73,7 +73,7 @@ extern "C" {
 
 /* per-query flags written by cmw_search (out_flags) */
 #define CMW_FLAG_UNCERTIFIED 1 /* the exactness certificate could not be established, or a candidate pool overflowed */
-#define CMW_FLAG_PEER_TIMEOUT 2 /* cmw_exchange_merge: a peer never published its candidates (results invalid) */
+#define CMW_FLAG_PEER_TIMEOUT 2 /* cmw_exchange_merge / cmw_peer_gather: a peer never published its data (results invalid) */
 
 /* limits (checked, not silent): k <= CMW_MAX_K; cmw_multivector S*k <= CMW_MAX_MULTIVECTOR_ENTRIES;
  * cmw_merge_topk / cmw_shard_merge / cmw_exchange_merge G*k <= CMW_MAX_MERGE_ENTRIES.  k above ~330 cannot be
@@ -209,6 +209,11 @@ int cmw_search_finish(cmw_store* s, const float* queries_dev, int batch, int k, 
                       const float* global_kth_dev, void* block_dev, void* ws_dev, size_t ws_bytes, void* stream);
 int cmw_shard_merge(const void* blocks_dev, int G, int B, int k, int k_out, float* out_scores_dev,
                     int64_t* out_ids_dev, double* out_scores64_dev, int32_t* out_flags_dev, void* stream);
+/* the same with the status word of cmw_peer_gather: if *peer_status_dev != 0 when the kernel runs, every query
+ * comes back empty (ids -1) with that value as its flags (CMW_FLAG_PEER_TIMEOUT) */
+int cmw_shard_merge_ex(const void* blocks_dev, int G, int B, int k, int k_out, float* out_scores_dev,
+                       int64_t* out_ids_dev, double* out_scores64_dev, int32_t* out_flags_dev,
+                       const int32_t* peer_status_dev, void* stream);
 
 /* ---- fused exchange + merge over NVLink peer memory (alternative to all-gather + cmw_merge_topk).
  * Every rank allocates one peer buffer (cmw_peer_alloc: cudaMalloc + cudaIpc handle, zero-initialised,
@@ -235,6 +240,22 @@ int cmw_exchange_merge_ex(void* const* peer_bufs_host, int G, int rank, int max_
                           int k_out, uint32_t epoch, const double* scores64_local_dev, const int64_t* ids_local_dev,
                           const int32_t* flags_local_dev, float* out_scores_dev, int64_t* out_ids_dev,
                           double* out_scores64_dev, int32_t* out_flags_dev, int timeout_ms, void* stream);
+
+/* ---- the two exchanges of the two-phase row-sharded search over NVLink peer memory instead of NCCL.
+ * One peer buffer per rank of cmw_peer_gather_bytes(G, max_bytes_per_rank) bytes (cmw_peer_alloc / cmw_peer_open as
+ * above).  cmw_peer_gather launches, stream-ordered and without host synchronisation: a send kernel that stores
+ * `nbytes` of src_dev into this rank's slot of EVERY rank's buffer (st.global over NVLink 5 / NVSwitch), fences
+ * system-wide and raises this rank's epoch flag on every peer; then a one-block kernel that holds the stream until
+ * all G slots of this epoch have landed -- for at most timeout_ms (0 = 2 s), after which (or when a peer published a
+ * different nbytes) CMW_FLAG_PEER_TIMEOUT is OR-ed into *status_dev (sticky: the exchange is out of step, rebuild
+ * it).  *gathered_dev_out = the G slots, rank-major and contiguous (G * nbytes bytes) IN this rank's peer buffer:
+ * what all-gather into one tensor would have produced, read in place by cmw_shard_kth / cmw_shard_merge_ex.  It
+ * stays valid until the call after next (two regions alternate by epoch parity).  Every rank must call with the
+ * same nbytes and the same epoch sequence 1, 2, 3, ...  (epoch != 0). */
+size_t cmw_peer_gather_bytes(int G, size_t max_bytes_per_rank);
+int cmw_peer_gather(void* const* peer_bufs_host, int G, int rank, size_t max_bytes_per_rank, const void* src_dev,
+                    size_t nbytes, uint32_t epoch, int timeout_ms, int32_t* status_dev, void** gathered_dev_out,
+                    void* stream);
 
 /* ---- instrumentation ---- */
 /* number of kernels this library has launched since load (all stores, all streams) */

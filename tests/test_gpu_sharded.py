@@ -19,7 +19,7 @@ import synth
 from oracle.cport import exact_topk_c
 from cmw_rag_b200 import DenseStore
 from cmw_rag_b200 import _native as N
-from cmw_rag_b200.sharded import PeerExchange, ShardedSearcher, shard_bounds
+from cmw_rag_b200.sharded import PeerExchange, PeerGather, ShardedSearcher, shard_bounds
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 dev = torch.device(f"cuda:{{local}}"); torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
@@ -83,6 +83,38 @@ for it in range(5):
     assert torch.equal(a_i, b_i) and torch.equal(a_s, b_s), (rank, it)
     assert int(b_f.sum()) == 0
 assert (b_i.cpu().numpy() == np.roll(ref_ids, 4, axis=0)).all()
+# the two-phase search with BOTH exchanges over peer memory (cmw_peer_gather) instead of NCCL: same answer, call
+# after call (the two gather regions alternate by epoch parity), exact and approximate mode, host forms included
+pg = PeerGather(device=local, max_batch=64, max_k=64)
+via_peer = ShardedSearcher(st, gather=pg)
+for it in range(6):
+    qi = torch.from_numpy(np.roll(q, it, axis=0).copy()).to(dev)
+    mode = "f32" if it % 3 else "bf16"
+    a_s, a_i, a_f = s.search(qi, k, mode=mode)
+    b_s, b_i, b_f = via_peer.search(qi, k, mode=mode)
+    torch.cuda.synchronize()
+    assert torch.equal(a_i, b_i) and torch.equal(a_s, b_s) and torch.equal(a_f.to(torch.int32), b_f.to(torch.int32)), (rank, it)
+    if mode == "f32":
+        assert (b_i.cpu().numpy() == np.roll(ref_ids, it, axis=0)).all() and int(b_f.sum()) == 0
+tickets = [via_peer.search_host_submit(np.roll(q, it, axis=0).copy(), k) for it in range(3)]
+for it, t in enumerate(tickets):
+    o = via_peer.search_host_wait(t)
+    assert (o[1] == np.roll(ref_ids, it, axis=0)).all() and (o[2] == 0).all(), (rank, it)
+assert int(pg.status.item()) == 0
+if world > 1:
+    # a rank that skips an exchange: the others' wait is bounded, the status word is set and the merge kernel
+    # reports CMW_FLAG_PEER_TIMEOUT for every query instead of hanging the GPU or returning stale data
+    dist.barrier()
+    pg2 = PeerGather(device=local, max_batch=64, max_k=64, timeout_ms=100)
+    if rank == 0:
+        lone = ShardedSearcher(st, gather=pg2)
+        _, t_i, t_f = lone.search(qd, k, mode="bf16")
+        torch.cuda.synchronize()
+        assert (t_f.cpu().numpy() == N.FLAG_PEER_TIMEOUT).all() and (t_i.cpu().numpy() == -1).all()
+        assert int(pg2.status.item()) == N.FLAG_PEER_TIMEOUT
+    dist.barrier()
+    pg2.close()
+pg.close()
 if world > 1:
     # a peer that never shows up: the merge kernel's wait is bounded and reports CMW_FLAG_PEER_TIMEOUT
     dist.barrier()
