@@ -1,5 +1,5 @@
-"""torchrun worker: two ranks exchange top-k candidates through the fused NVLink peer-memory kernels (K5x) and check
-the merge against the oracle.  Used by __graft_entry__.smoke() on boxes with two or more GPUs."""
+"""torchrun worker: two ranks exchange top-k candidates through the fused NVLink peer-memory kernels (K5x), and run the
+two-phase search with both of its exchanges over peer memory (cmw_peer_gather), each checked against the oracle.  Used by __graft_entry__.smoke() on boxes with two or more GPUs."""
 import os
 import sys
 
@@ -13,7 +13,7 @@ import torch.distributed as dist  # noqa: E402
 
 import synth  # noqa: E402
 from cmw_rag_b200 import DenseStore  # noqa: E402
-from cmw_rag_b200.sharded import PeerExchange, ShardedSearcher, shard_bounds  # noqa: E402
+from cmw_rag_b200.sharded import PeerExchange, PeerGather, ShardedSearcher, shard_bounds  # noqa: E402
 from oracle.cport import exact_topk_c  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -32,6 +32,11 @@ torch.cuda.synchronize()
 ref_ids, _, _ = exact_topk_c(c, q, k)
 assert (mi.cpu().numpy() == ref_ids).all() and int(fl.sum()) == 0
 ex.close()
+pg = PeerGather(device=local, max_batch=16, max_k=16)
+ms2, mi2, fl2 = ShardedSearcher(st, gather=pg).search(torch.from_numpy(q).to(dev), k)
+torch.cuda.synchronize()
+assert (mi2.cpu().numpy() == ref_ids).all() and int(fl2.sum()) == 0 and torch.equal(ms2, ms)
+pg.close()
 dist.barrier()
 dist.destroy_process_group()
 print("peer exchange ok", rank)
