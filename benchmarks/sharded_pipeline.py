@@ -16,7 +16,7 @@ import torch.distributed as dist  # noqa: E402
 
 import bench  # noqa: E402
 from cmw_rag_b200.engine import pinned_empty  # noqa: E402
-from cmw_rag_b200.sharded import ShardedSearcher, shard_bounds  # noqa: E402
+from cmw_rag_b200.sharded import PeerGather, ShardedSearcher, shard_bounds  # noqa: E402
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -25,13 +25,14 @@ dev = torch.device(f"cuda:{local}")
 torch.cuda.set_device(dev)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-rows, dim, B, k, steps = 1_000_000, 1536, 4096, 100, 20
+rows, dim, B, k, steps = int(os.environ.get("ROWS", "1000000")), 1536, 4096, 100, int(os.environ.get("STEPS", "20"))
 lo, hi = shard_bounds(rows, world)[rank]
 st, first = bench.build_store(torch, dim, dev, lo, hi)
 q, _ = bench.make_queries(torch, dist, first, lo, B, dim, dev, 7, rank, world)
 q_host = pinned_empty((B, dim), np.float32)
 q_host[:] = q.cpu().numpy()
-s = ShardedSearcher(st)
+pg = PeerGather(device=local, max_batch=B, max_k=k) if world > 1 and os.environ.get("EXCHANGE", "gather") == "gather" else None
+s = ShardedSearcher(st, gather=pg)
 
 
 def barrier():
@@ -107,6 +108,8 @@ if world > 1:
 if rank == 0:
     res["world"] = world
     print(json.dumps(res), flush=True)
+if pg is not None:
+    pg.close()
 st.close()
 if world > 1:
     dist.barrier()

@@ -370,14 +370,13 @@ class ShardedSearcher:
         q = qbuf[:b]
         main.wait_event(e_in)
         ms, mi, fl = self.search(q, k, **kw)
-        fl = fl.to(torch.int32)
         e_done = torch.cuda.Event()
         e_done.record(main)
         with torch.cuda.stream(down):
             down.wait_event(e_done)
             torch.from_numpy(out[0]).copy_(ms, non_blocking=True)
             torch.from_numpy(out[1]).copy_(mi, non_blocking=True)
-            torch.from_numpy(out[2]).copy_(fl, non_blocking=True)
+            torch.from_numpy(out[2]).copy_(fl.to(torch.int32), non_blocking=True)
             e_out = torch.cuda.Event()
             e_out.record(down)
         # the ticket keeps every device tensor alive until the wait: nothing allocated on one stream is handed
