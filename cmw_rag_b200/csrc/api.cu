@@ -31,10 +31,15 @@ struct WsLayout {
     int bpad;
 };
 
+// Padded batch = n_groups query groups of `nt` columns each (gemm_group_width, gemm_common.cuh).  Up to 256 queries:
+// one group, padded to 16.  Beyond: as many groups as 256-wide ones would take, but only as wide as needed, in
+// steps of 64 -- 384 queries are two groups of 192, not two of 256 with a quarter of the tensor work on padding.
 static int pad_batch(int batch) {
     if (batch <= 16) return 16;
     if (batch <= 256) return (int)align_up((size_t)batch, 16);
-    return (int)align_up((size_t)batch, 256);
+    const int groups = (batch + 255) / 256;
+    const int nt = (int)align_up((size_t)((batch + groups - 1) / groups), 64);
+    return nt * groups;
 }
 
 static WsLayout ws_layout(int dim, int batch, int kprime, bool tf32 = true) {

@@ -273,7 +273,7 @@ void set_scan_order(GemmParams& p, const GemmArgs& a, int tile_rows) {
 // which K2 kernel a padded batch runs on: CTA pairs (cta_group::2) for the tensor-bound batches, single CTAs
 // for the HBM-bound ones
 static bool use_cta_pairs(const Options& o, int bpad) {
-    return o.gemm_2cta != 0 && bpad >= (int)o.gemm_2cta_min_batch && (bpad % 256 == 0 || (bpad < 256 && bpad % 64 == 0));
+    return o.gemm_2cta != 0 && bpad >= (int)o.gemm_2cta_min_batch && gemm_group_width(bpad) % 64 == 0;
 }
 
 // true when the slabs of a multi-slab search scan the store's tiles in the stride permutation (set_scan_order),
@@ -298,7 +298,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.tf32 = a.tf32;
     p.kb_elems = a.tf32 ? kBlockK / 2 : kBlockK;
     p.num_kb = (s->dim + p.kb_elems - 1) / p.kb_elems;
-    p.nt = a.bpad < kMaxNT ? a.bpad : kMaxNT;
+    p.nt = gemm_group_width(a.bpad);
     CMW_REQUIRE(p.nt % 16 == 0 && a.bpad % p.nt == 0, "launch_gemm: bad query padding %d", a.bpad);
     p.n_groups = a.bpad / p.nt;
     p.batch = a.batch;

@@ -340,7 +340,7 @@ int launch_gemm_2cta(const GemmArgs& a, cudaStream_t stream) {
     p.tf32 = 0;
     p.kb_elems = kBlockK;
     p.num_kb = (s->dim + kBlockK - 1) / kBlockK;
-    p.nt = a.bpad < kMaxNT ? a.bpad : kMaxNT;
+    p.nt = gemm_group_width(a.bpad);
     CMW_REQUIRE(p.nt % 64 == 0 && a.bpad % p.nt == 0, "launch_gemm_2cta: bad query padding %d", a.bpad);
     p.n_groups = a.bpad / p.nt;
     p.batch = a.batch;

@@ -50,6 +50,14 @@ struct GemmParams {
     const float* pool_thr;
 };
 
+// width of one query group of a padded batch (api.cu: pad_batch): the whole batch up to 256 queries, else the
+// batch split evenly over ceil(bpad / 256) groups
+__host__ __device__ inline int gemm_group_width(int bpad) {
+    if (bpad <= kMaxNT) return bpad;
+    const int groups = (bpad + kMaxNT - 1) / kMaxNT;
+    return bpad / groups;
+}
+
 // Which (row tile, query group) items worker `w` of `nw` (a CTA, or a CTA pair) processes; item = tile *
 // n_groups + group: round-robin, so that at any moment the workers are on the same few row tiles (one HBM
 // read per tile, L2 hits for its other query groups; working set ~5 tiles).  Measured alternative (ncu r01h):

@@ -823,6 +823,36 @@ def test_fuzz_search_against_oracle(torch_cuda, seed):
     st.close()
 
 
+@pytest.mark.parametrize("b", [257, 320, 384, 400, 513, 600, 777, 1000])
+def test_query_groups_only_as_wide_as_needed(torch_cuda, b):
+    """Batches above 256 are split into ceil(B / 256) query groups of equal width in steps of 64 (384 -> 2 x 192, not
+    2 x 256 with a quarter of the tensor work on padding): CTA-pair and 1-CTA kernels, fp16 tiles and the tf32
+    filter of a store without 16-bit tiles, all against the oracle."""
+    from cmw_rag_b200 import DenseStore
+    from cmw_rag_b200 import _native as N
+
+    n, d, k = 20000, 256, 30
+    c = synth.make_corpus(n, d, seed=31)
+    q, _ = synth.make_queries(c, b, seed=32)
+    ref_ids, ref_sc, _ = exact_topk_c(c, q, k)
+    st = DenseStore(d, n)
+    st.append(c)
+    st32 = DenseStore(d, n, f32=True, bf16=False)
+    st32.append(c)
+    try:
+        for pairs in (1, 0):
+            N.set_option("gemm_2cta", pairs)
+            sc, ids, fl = st.search_host(q, k, mode="f32", algo="gemm")
+            assert (fl == 0).all() and (ids == ref_ids).all(), (b, pairs, int((ids != ref_ids).sum()))
+            assert np.abs(sc - ref_sc).max() <= F32_TOL
+        sc, ids, fl = st32.search_host(q, k, mode="f32")
+        assert (fl == 0).all() and (ids == ref_ids).all(), (b, "tf32")
+    finally:
+        N.set_option("gemm_2cta", 1)
+        st.close()
+        st32.close()
+
+
 @pytest.mark.parametrize("seed", range(16))
 def test_fuzz_two_phase_row_shards_on_one_gpu(torch_cuda, seed):
     """The row-sharded search (filter | k-th over all shards | finish with the global cut | merge + cross-shard
