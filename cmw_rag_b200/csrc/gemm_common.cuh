@@ -16,6 +16,7 @@ constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;      // TMEM columns per accumulator stage
 constexpr int kStageCap = 512;       // staged survivors per epilogue warp (8 bytes each), 1-CTA kernel
 constexpr int kStageCap2 = 256;      // same, CTA-pair kernel (8 epilogue warps, 128 columns each)
+constexpr int kAggregateFrom = 64;   // staged survivors from which a flush reserves pool slots per run of one query
 
 struct GemmParams {
     int dim;
@@ -91,6 +92,40 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 __device__ __forceinline__ void flush_staged(const uint2* stg, int wcount, int lane, int64_t row_warp0,
                                              const GemmParams& p) {
     __syncwarp();
+    if (wcount >= kAggregateFrom) {
+        // Many survivors = a slab whose threshold is still loose (5 % of all scores pass right after the first
+        // slab): entries of one query sit next to each other in the staging buffer (they were staged column by
+        // column), so one atomic per RUN of equal queries within the 32 entries a warp takes at a time reserves
+        // the slots of the whole run.
+        const uint32_t lanemask_lt = (1u << lane) - 1u;
+        for (int e0 = 0; e0 < wcount; e0 += 64) {  // two chunks of 32 per round: as many atomics in flight as below
+            const int ea = e0 + lane, eb = e0 + 32 + lane;
+            const bool va = ea < wcount, vb = eb < wcount;
+            const uint2 na = va ? stg[ea] : make_uint2(0u, 0u);
+            const uint2 nb = vb ? stg[eb] : make_uint2(0u, 0u);
+            const int qa = va ? (int)(na.y >> 5) : (0x40000000 | lane);
+            const int qb = vb ? (int)(nb.y >> 5) : (0x40000000 | lane);
+            const uint32_t sa = __match_any_sync(0xffffffffu, qa);
+            const uint32_t sb = __match_any_sync(0xffffffffu, qb);
+            const int la = __ffs(sa) - 1, lb = __ffs(sb) - 1;
+            int ba = 0, bb = 0;
+            if (va && lane == la) ba = atomicAdd(p.pool_cnt + qa, __popc(sa));
+            if (vb && lane == lb) bb = atomicAdd(p.pool_cnt + qb, __popc(sb));
+            ba = __shfl_sync(0xffffffffu, ba, la);
+            bb = __shfl_sync(0xffffffffu, bb, lb);
+            const int pa = ba + __popc(sa & lanemask_lt), pb = bb + __popc(sb & lanemask_lt);
+            if (va && pa < kPoolCap) {
+                p.pool_scores[(size_t)qa * kPoolCap + pa] = __uint_as_float(na.x);
+                p.pool_ids[(size_t)qa * kPoolCap + pa] = (int32_t)(row_warp0 + (int)(na.y & 31u));
+            }
+            if (vb && pb < kPoolCap) {
+                p.pool_scores[(size_t)qb * kPoolCap + pb] = __uint_as_float(nb.x);
+                p.pool_ids[(size_t)qb * kPoolCap + pb] = (int32_t)(row_warp0 + (int)(nb.y & 31u));
+            }
+        }
+        __syncwarp();
+        return;
+    }
     for (int e = lane; e < wcount; e += 64) {
         const bool two = (e + 32 < wcount);
         const uint2 en0 = stg[e];
