@@ -6,6 +6,7 @@
 // "ties broken by lower id"); results are best-first like collection.query() of
 // rag_engine/storage/vector_store.py:59-66.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace cmw {
 
@@ -306,14 +307,36 @@ __device__ __forceinline__ void select_and_compact(uint32_t (&key)[kCompactPer],
 }
 
 __global__ void __launch_bounds__(kCompactThreads, 5) pool_compact_kernel(Pool pool, int kprime, int final) {
-    extern __shared__ __align__(16) uint8_t cmp_smem[];
+    extern __shared__ __align__(16) uint8_t cmp_smem[];  // 32 KB: the staged entries, later the sort keys
     __shared__ SelectShared sm;
+    __shared__ __align__(8) uint64_t stage_bar;
     const int b = blockIdx.x;
     const int t = threadIdx.x;
     const int n_in = pool.cnt[b];
     const int n = n_in < kPoolCap ? n_in : kPoolCap;
     const float* sc = pool.scores + (size_t)b * kPoolCap;
     const int32_t* id = pool.ids + (size_t)b * kPoolCap;
+    // The n entries come in through TWO bulk async copies (scores, ids: cp.async.bulk + mbarrier transaction count,
+    // SASS UBLKCP) instead of 32 predicated loads per thread: with 48 registers per thread the compiler cannot keep
+    // more than a few of those loads in flight, and the load phase was 60 % of the kernel's stall samples (ncu
+    // source page, prof_r02_tail) -- a chain of L2 / HBM latencies per CTA.
+    float* s_sc = reinterpret_cast<float*>(cmp_smem);
+    int32_t* s_id = reinterpret_cast<int32_t*>(cmp_smem + (size_t)kPoolCap * sizeof(float));
+    if (t == 0) {
+        ptx::mbar_init(&stage_bar, 1);
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+    if (n > 0) {
+        if (t == 0) {
+            const uint32_t bytes = ((uint32_t)n * 4u + 15u) & ~15u;  // rounds up inside the pool's own 16 KB row
+            const uint64_t pol = ptx::l2_policy_evict_first();
+            ptx::mbar_arrive_expect_tx(&stage_bar, 2u * bytes);
+            ptx::bulk_g2s(s_sc, sc, bytes, &stage_bar, pol);
+            ptx::bulk_g2s(s_id, id, bytes, &stage_bar, pol);
+        }
+        ptx::mbar_wait(&stage_bar, 0);
+    }
     uint32_t key[kCompactPer];
     int32_t rid[kCompactPer];
 #pragma unroll
@@ -321,14 +344,15 @@ __global__ void __launch_bounds__(kCompactThreads, 5) pool_compact_kernel(Pool p
         const int i = t + j * kCompactThreads;
         key[j] = 0xffffffffu;
         rid[j] = -1;
-        if (i < n) load_entry(sc[i], id[i], key[j], rid[j]);
+        if (i < n) load_entry(s_sc[i], s_id[i], key[j], rid[j]);
     }
-    // (the barriers of the first block scan inside separate these loads from the in-place write-back)
+    // (the barriers of the first block scan inside separate these reads from the in-place write-back and from the
+    // sort keys that later take the staging buffer's place)
     select_and_compact(key, rid, kprime, final, n_in > kPoolCap, pool, b, reinterpret_cast<uint64_t*>(cmp_smem), sm);
 }
 
 int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_t stream) {
-    const size_t smem = final ? (size_t)kPoolCap * sizeof(uint64_t) : 0;
+    const size_t smem = (size_t)kPoolCap * sizeof(uint64_t);  // staging (scores | ids) = the sort keys of the final call
     pool_compact_kernel<<<batch, kCompactThreads, smem, stream>>>(pool, kprime, final);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
