@@ -116,8 +116,9 @@ def traffic(path: str, key: str, substr: str, *kv: str) -> None:
              "traffic_bytes_per_step": sum(rd_b) + sum(wr_b),
              "source": f"{os.path.basename(path)} (`ncu --set full`), written by benchmarks/ncu_summarise.py traffic"}
     if "algorithmic_hbm_bytes_per_step" not in entry and {"rows", "dim"} <= set(meta):
-        # one pass over the 16-bit tiles + the row multipliers + the query tile
-        entry["algorithmic_hbm_bytes_per_step"] = meta["rows"] * (meta["dim"] * 2 + 4) + meta.get("batch", 0) * meta["dim"] * 2
+        # one pass over the tiles + the row multipliers + the query tile
+        elt = int(meta.get("elt_bytes", 2))  # bytes per element of the tiles the filter streams (4 for fp32 rows)
+        entry["algorithmic_hbm_bytes_per_step"] = meta["rows"] * (meta["dim"] * elt + 4) + meta.get("batch", 0) * meta["dim"] * elt
     for label, col in extra.items():
         entry[label] = [num(r[col]) for r in sel]
     out_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
