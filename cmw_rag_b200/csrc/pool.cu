@@ -369,42 +369,93 @@ int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_
 // 1 for the same reason.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCompactThreads, 5) wide_merge_kernel(Pool seg, Pool pool, int kprime, int final) {
-    extern __shared__ __align__(16) uint8_t wm_smem[];
+    extern __shared__ __align__(16) uint8_t wm_smem[];  // 32 KB: the staged survivors, later the sort keys
     __shared__ SelectShared sm;
-    __shared__ int seg_off[kWideSegments + 1];
+    __shared__ int seg_off[kWideSegments + 1];   // prefix sums of the segments' survivor counts
+    __shared__ int seg_poff[kWideSegments + 1];  // the same with every count rounded up to 4 entries (16 bytes)
     __shared__ int seg_flag;
+    __shared__ __align__(8) uint64_t stage_bar;
     const int b = blockIdx.x;
     const int t = threadIdx.x;
     if (t < 32) {
         const int c = (t < kWideSegments) ? seg.cnt[b * kWideSegments + t] : 0;
         const int of = (t < kWideSegments) ? seg.ovf[b * kWideSegments + t] : 0;
-        int v = c;
+        int v = c, vp = (c + 3) & ~3;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int u = __shfl_up_sync(0xffffffffu, v, o);
-            if (t >= o) v += u;
+            const int u = __shfl_up_sync(0xffffffffu, v, o);
+            const int up = __shfl_up_sync(0xffffffffu, vp, o);
+            if (t >= o) {
+                v += u;
+                vp += up;
+            }
         }
-        if (t < kWideSegments) seg_off[t + 1] = v;
-        if (t == 0) seg_off[0] = 0;
+        if (t < kWideSegments) {
+            seg_off[t + 1] = v;
+            seg_poff[t + 1] = vp;
+        }
+        if (t == 0) {
+            seg_off[0] = 0;
+            seg_poff[0] = 0;
+            ptx::mbar_init(&stage_bar, 1);
+            ptx::fence_barrier_init();
+        }
         const unsigned any = __ballot_sync(0xffffffffu, of != 0);
         if (t == 0) seg_flag = any != 0u;
     }
     __syncthreads();
     const int n_in = seg_off[kWideSegments];
-    const int n = n_in < kPoolCap ? n_in : kPoolCap;
+    const int n_pad = seg_poff[kWideSegments];
     uint32_t key[kCompactPer];
     int32_t rid[kCompactPer];
+    if (n_in <= kPoolCap && n_pad <= kPoolCap) {
+        // The survivors of the 16 segments come in through bulk async copies (one pair per segment, 16-byte
+        // granules: each segment's piece is padded to 4 entries in the staging buffer and the padding ignored)
+        // instead of predicated loads with a 16-way segment search per entry -- the same latency chain the
+        // compaction kernel had.
+        float* s_sc = reinterpret_cast<float*>(wm_smem);
+        int32_t* s_id = reinterpret_cast<int32_t*>(wm_smem + (size_t)kPoolCap * sizeof(float));
+        if (n_pad > 0) {
+            if (t == 0) {
+                const uint64_t pol = ptx::l2_policy_evict_first();
+                ptx::mbar_arrive_expect_tx(&stage_bar, 2u * (uint32_t)n_pad * 4u);
+                for (int sgm = 0; sgm < kWideSegments; ++sgm) {
+                    const uint32_t bytes = (uint32_t)(seg_poff[sgm + 1] - seg_poff[sgm]) * 4u;
+                    if (bytes == 0) continue;
+                    const size_t src = ((size_t)b * kWideSegments + sgm) * kPoolCap;
+                    ptx::bulk_g2s(s_sc + seg_poff[sgm], seg.scores + src, bytes, &stage_bar, pol);
+                    ptx::bulk_g2s(s_id + seg_poff[sgm], seg.ids + src, bytes, &stage_bar, pol);
+                }
+            }
+            ptx::mbar_wait(&stage_bar, 0);
+        }
 #pragma unroll
-    for (int j = 0; j < kCompactPer; ++j) {
-        const int i = t + j * kCompactThreads;
-        key[j] = 0xffffffffu;
-        rid[j] = -1;
-        if (i < n) {
-            int sgm = 0;
+        for (int j = 0; j < kCompactPer; ++j) {
+            const int i = t + j * kCompactThreads;
+            key[j] = 0xffffffffu;
+            rid[j] = -1;
+            if (i < n_pad) {
+                int sgm = 0;
 #pragma unroll
-            for (int q = 1; q < kWideSegments; ++q) sgm += (i >= seg_off[q]) ? 1 : 0;
-            const size_t src = ((size_t)b * kWideSegments + sgm) * kPoolCap + (size_t)(i - seg_off[sgm]);
-            load_entry(seg.scores[src], seg.ids[src], key[j], rid[j]);
+                for (int q = 1; q < kWideSegments; ++q) sgm += (i >= seg_poff[q]) ? 1 : 0;
+                if (i - seg_poff[sgm] < seg_off[sgm + 1] - seg_off[sgm]) load_entry(s_sc[i], s_id[i], key[j], rid[j]);
+            }
+        }
+    } else {
+        // more survivors than one pool holds (ties, overflowed segments): the first kPoolCap, flagged below
+        const int n = n_in < kPoolCap ? n_in : kPoolCap;
+#pragma unroll
+        for (int j = 0; j < kCompactPer; ++j) {
+            const int i = t + j * kCompactThreads;
+            key[j] = 0xffffffffu;
+            rid[j] = -1;
+            if (i < n) {
+                int sgm = 0;
+#pragma unroll
+                for (int q = 1; q < kWideSegments; ++q) sgm += (i >= seg_off[q]) ? 1 : 0;
+                const size_t src = ((size_t)b * kWideSegments + sgm) * kPoolCap + (size_t)(i - seg_off[sgm]);
+                load_entry(seg.scores[src], seg.ids[src], key[j], rid[j]);
+            }
         }
     }
     select_and_compact(key, rid, kprime, final, n_in > kPoolCap || seg_flag != 0, pool, b,
@@ -414,7 +465,7 @@ __global__ void __launch_bounds__(kCompactThreads, 5) wide_merge_kernel(Pool seg
 int launch_wide_select(Pool seg, Pool pool, int batch, int kprime, int final, cudaStream_t stream) {
     int rc = launch_pool_compact(seg, batch * kWideSegments, kprime, 0, stream);
     if (rc) return rc;
-    const size_t smem = final ? (size_t)kPoolCap * sizeof(uint64_t) : 0;
+    const size_t smem = (size_t)kPoolCap * sizeof(uint64_t);  // staging (scores | ids) = the sort keys of a final call
     wide_merge_kernel<<<batch, kCompactThreads, smem, stream>>>(seg, pool, kprime, final);
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
