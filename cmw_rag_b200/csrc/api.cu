@@ -8,7 +8,7 @@
 //   for each slab of rows (first slab dense, later slabs growing geometrically):
 //       filter kernel (K1 scan or K2 tcgen05 GEMM) admits rows with score >= thr into the pools
 //       compaction keeps the best K' per query and raises thr
-//   (batches <= 32: a 65536-row first slab through a scratch matrix + two-level selection, then the rest of
+//   (batches <= 32: a first slab of up to 131072 rows through a scratch matrix + two-level selection, then the rest of
 //    the corpus in one launch when its expected admissions fit the pool)
 //   cmw_search_host / _submit / _wait: the same behind H2D / D2H copies, blocking or pipelined
 //   F32_EXACT: fp64 rescoring of the K' survivors from the fp32 tiles + final selection + certificate
@@ -63,7 +63,7 @@ static WsLayout ws_layout(int dim, int batch, int kprime, bool tf32 = true) {
     w.pool_thr = take((size_t)w.bpad * sizeof(float));
     w.pool_ovf = take((size_t)w.bpad * sizeof(int32_t));
     w.exact = take((size_t)batch * kprime * sizeof(double));
-    // scratch of the wide first slab, small batches only: scores + ids in 16 pool-sized segments per query, and
+    // scratch of the wide first slab, small batches only: scores + ids in kWideSegments pool-sized segments per query, and
     // the segments' cnt / thr / ovf
     w.wide = take(batch <= kWideDenseMaxBatch
                       ? (size_t)batch * kWideDenseRows * 8 + (size_t)batch * kWideSegments * 12 + 1024
@@ -455,8 +455,8 @@ static int run_filter_half(const SearchPlan& pl, const float* queries_dev, cudaS
     int rc;
     const int64_t rows = s->rows;
     // First slab: every row's score is kept (no threshold exists yet).  Large batches write it straight into
-    // the pools (4096 rows = the pool capacity).  Small batches take a WIDE first slab of up to 65536 rows
-    // whose scores go to a scratch matrix of 16 pool-sized segments per query, from which a two-level
+    // the pools (4096 rows = the pool capacity).  Small batches take a WIDE first slab of up to 131072 rows
+    // whose scores go to a scratch matrix of up to 32 pool-sized segments per query, from which a two-level
     // selection fills the pools.  (The segments' survivors, kprime and ties each, must fit one pool: fewer
     // segments for a large kprime.)
     int wide_segs = (kPoolCap - 256) / kprime;
@@ -585,7 +585,7 @@ static int run_filter_half(const SearchPlan& pl, const float* queries_dev, cudaS
         seen = slab0;
         while (seen < rows) {
             int64_t m, end;
-            // After a wide first slab the threshold is the kprime-th best of 65536 rows: the rest of the corpus
+            // After a wide first slab the threshold is the kprime-th best of its 65536+ rows: the rest of the corpus
             // goes through ONE launch when its expected admissions, (live rows left) * kprime / (live rows seen),
             // plus the kprime survivors fill at most 85 % of the pool (up to ~1.05M rows at kprime = 224).  K2
             // scans the tiles in a stride permutation, so the slab was a representative sample and the estimate

@@ -56,9 +56,11 @@ constexpr int kPoolCap = 4096;      // entries per query
 constexpr int kDenseSlabRows = 4096;  // first slab: every row is written (no threshold yet); = kPoolCap
 constexpr int kMaxKPrime = 1024;
 // Small batches take a WIDE first slab: its scores and ids go to a scratch matrix in the workspace, laid out as
-// 16 pool-sized segments per query, instead of the pools (fewer slabs -- filter launches and compactions, 7-12 us
-// each however little they do -- per search)
-constexpr int kWideDenseRows = 65536;
+// up to 32 pool-sized segments per query, instead of the pools (fewer slabs -- filter launches and compactions,
+// 7-12 us each however little they do -- per search).  How many segments a search uses depends on K' (their
+// survivors must fit one pool): 17 at k = 100, all 32 at k <= 50 -- a 100k-row collection searched for its top-20
+// (the reference's production shape) is ONE slab: 6 kernels per search.
+constexpr int kWideDenseRows = 131072;
 constexpr int kWideSegments = kWideDenseRows / kPoolCap;
 constexpr int kWideDenseMaxBatch = 32;
 constexpr int kScanMaxQueries = 4;  // queries K1 scores per pass over the corpus

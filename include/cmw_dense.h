@@ -276,7 +276,7 @@ int cmw_profile_read(double* ms, int64_t* counts, int n);
  *                             0 = statistical bound, bf16_sigmas x sigma with u = 2^-8 (K' = max(k + 64, 2k))
  *   "bf16_eps" (0 = from the bound above), "bf16_sigmas" (8), "f32_eps" (0 = (D/32 + 12) 2^-24)   certificate bounds
  *   "repair" (2)              cmw_search_host repair chain for flagged queries: 0 off, 1 stage 1, 2 both stages
- *   "wide_dense" (1)          batches up to 32: 65536-row first slab through a scratch matrix, then the rest of
+ *   "wide_dense" (1)          batches up to 32: first slab of up to 131072 rows through a scratch matrix, then the rest of
  *                             the corpus in one launch when the expected admissions fit the pool
  *   "scan_permute" (1)        K2 scans the row tiles in a stride permutation: every slab is a representative sample
  *                             of the corpus, the admission thresholds hold whatever order the corpus is stored in
