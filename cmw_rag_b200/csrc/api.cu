@@ -466,6 +466,11 @@ static int run_filter_half(const SearchPlan& pl, const float* queries_dev, cudaS
     const int64_t wide_rows = (int64_t)wide_segs * kPoolCap;
     const int64_t slab0 = wide ? (rows < wide_rows ? rows : wide_rows)
                                : (rows < kDenseSlabRows ? rows : (int64_t)kDenseSlabRows);
+    // Programmatic dependent launch of this search's kernels (ptx.cuh: pdl_wait) where the chain of small kernels IS
+    // the search: a small batch over a collection that is one wide slab (6 kernels; 100k rows, k = 20: -2 % at batch
+    // 1, -7 % at batch 16-32).  With a second, long filter launch behind the first slab it measured neutral at
+    // batch 1 and 1-2 % slower at batch 4-32 (benchmarks/pdl_ab.py), so those searches launch plainly.
+    t_pdl_search = (wide && slab0 == rows) ? 1 : 0;
     // What the schedule below reasons about is the number of LIVE rows the slabs so far have seen: the admission
     // threshold is the kprime-th best of those.  K2 scans a stride permutation of the tiles, so its slabs see the
     // store-wide live fraction; K1 (and small stores) scan in storage order, where the tombstones may sit in one

@@ -25,6 +25,8 @@ namespace cmw {
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_kernel_launches;
+extern std::atomic<int> g_pdl;
+extern thread_local int t_pdl_search;
 
 #define CMW_CUDA_OK(expr)                                                                        \
     do {                                                                                         \
@@ -45,6 +47,25 @@ extern std::atomic<long long> g_kernel_launches;
     } while (0)
 
 #define CMW_LAUNCHED() (::cmw::g_kernel_launches.fetch_add(1, std::memory_order_relaxed))
+
+#ifdef __CUDACC__
+// kernel<<<grid, block, smem, stream>>>(args...), optionally as a programmatic dependent launch (ptx.cuh: pdl_wait)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && ::cmw::t_pdl_search != 0 && ::cmw::g_pdl.load(std::memory_order_relaxed) != 0) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // candidate pool: the state shared by the filter kernels (K1 scan, K2 GEMM), the compaction

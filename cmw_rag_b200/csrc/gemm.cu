@@ -78,6 +78,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    // programmatic dependent launch (small batches): everything above -- descriptor prefetch, barrier init, TMEM
+    // allocation -- may run while the previous kernel of the search is still finishing; the query tile, the
+    // admission thresholds and the pools are its outputs
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -342,7 +347,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     const int grid = n_items < s->sm_count ? n_items : s->sm_count;
     // 8 epilogue warps for the widest query groups (192 or 256 columns): there the 4-warp epilogue of a tile takes as long as streaming its rows from HBM; narrower groups measured no gain
     const int threads = (p.nt >= 192 && p.nt % 64 == 0) ? kGemmThreadsWide : kGemmThreads;
-    gemm_topk_kernel<<<grid, threads, smem, stream>>>(a.tf32 ? s->tmap_f32 : s->tmap_bf16, tmap_b, p);
+    CMW_CUDA_OK(launch_kernel(gemm_topk_kernel, dim3(grid), dim3(threads), smem, stream, a.batch <= kWideDenseMaxBatch,
+                              a.tf32 ? s->tmap_f32 : s->tmap_bf16, tmap_b, p));
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;

@@ -20,6 +20,9 @@ prep_queries_kernel(const float* __restrict__ q, int batch, int bpad, int dim, i
                     float* __restrict__ q_tf32, Pool pool, int dense_count, Pool seg, int wide_rows) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // (this kernel overwrites the workspace the previous search's last kernels may still be reading)
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     if (b >= bpad) return;
     // wide first slab: the 16 scratch segments of this query start out holding their share of its rows
     if (seg.cnt != nullptr && b < batch && lane < kWideSegments) {
@@ -117,9 +120,9 @@ int launch_prep_queries(const float* q, int batch, int bpad, int dim, int metric
                         double* qres, float* q_f32, __nv_bfloat16* q_bf16, int half_tiles, float* q_tf32, Pool pool,
                         int dense_count, Pool seg, int wide_rows, cudaStream_t stream) {
     const int wpb = 8;
-    prep_queries_kernel<<<(bpad + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, batch, bpad, dim, metric, qn64, q4, qres,
-                                                                        q_f32, q_bf16, half_tiles, q_tf32, pool,
-                                                                        dense_count, seg, wide_rows);
+    CMW_CUDA_OK(launch_kernel(prep_queries_kernel, dim3((bpad + wpb - 1) / wpb), dim3(wpb * 32), 0, stream,
+                              batch <= kWideDenseMaxBatch, q, batch, bpad, dim, metric, qn64, q4, qres, q_f32, q_bf16,
+                              half_tiles, q_tf32, pool, dense_count, seg, wide_rows));
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
@@ -312,6 +315,8 @@ __global__ void __launch_bounds__(kCompactThreads, 5) pool_compact_kernel(Pool p
     __shared__ __align__(8) uint64_t stage_bar;
     const int b = blockIdx.x;
     const int t = threadIdx.x;
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     const int n_in = pool.cnt[b];
     const int n = n_in < kPoolCap ? n_in : kPoolCap;
     const float* sc = pool.scores + (size_t)b * kPoolCap;
@@ -353,7 +358,8 @@ __global__ void __launch_bounds__(kCompactThreads, 5) pool_compact_kernel(Pool p
 
 int launch_pool_compact(Pool pool, int batch, int kprime, int final, cudaStream_t stream) {
     const size_t smem = (size_t)kPoolCap * sizeof(uint64_t);  // staging (scores | ids) = the sort keys of the final call
-    pool_compact_kernel<<<batch, kCompactThreads, smem, stream>>>(pool, kprime, final);
+    CMW_CUDA_OK(launch_kernel(pool_compact_kernel, dim3(batch), dim3(kCompactThreads), smem, stream,
+                              batch <= kWideDenseMaxBatch * kWideSegments, pool, kprime, final));
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
@@ -377,6 +383,8 @@ __global__ void __launch_bounds__(kCompactThreads, 5) wide_merge_kernel(Pool seg
     __shared__ __align__(8) uint64_t stage_bar;
     const int b = blockIdx.x;
     const int t = threadIdx.x;
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     if (t < 32) {
         const int c = (t < kWideSegments) ? seg.cnt[b * kWideSegments + t] : 0;
         const int of = (t < kWideSegments) ? seg.ovf[b * kWideSegments + t] : 0;
@@ -466,7 +474,8 @@ int launch_wide_select(Pool seg, Pool pool, int batch, int kprime, int final, cu
     int rc = launch_pool_compact(seg, batch * kWideSegments, kprime, 0, stream);
     if (rc) return rc;
     const size_t smem = (size_t)kPoolCap * sizeof(uint64_t);  // staging (scores | ids) = the sort keys of a final call
-    wide_merge_kernel<<<batch, kCompactThreads, smem, stream>>>(seg, pool, kprime, final);
+    CMW_CUDA_OK(launch_kernel(wide_merge_kernel, dim3(batch), dim3(kCompactThreads), smem, stream, true, seg, pool,
+                              kprime, final));
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;
@@ -485,6 +494,8 @@ rescore_kernel(const float* __restrict__ f32, const double* __restrict__ norm64,
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     const int n = pool.cnt[b] < kprime ? pool.cnt[b] : kprime;
     // The pool is sorted by filter score.  With a_k its k-th filter score, every row whose filter score
     // is below a_k - 2*eps has an exact score below a_k - eps <= (k-th exact score): it cannot be in the
@@ -556,6 +567,8 @@ select_kernel(Pool pool, int k, int kprime, const double* __restrict__ exact, co
               double* __restrict__ out_scores64, int32_t* __restrict__ out_flags, double* __restrict__ out_aux) {
     extern __shared__ __align__(16) uint8_t sel_smem[];
     const int b = blockIdx.x;
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     const int n = pool.cnt[b] < kprime ? pool.cnt[b] : kprime;
     const int m = next_pow2(n < 2 ? 2 : n);
     uint64_t* hi = reinterpret_cast<uint64_t*>(sel_smem);
@@ -622,13 +635,14 @@ int launch_rescore_select(const Store* s, Pool pool, int batch, int k, int kprim
     if (per_query > max_per_query) per_query = max_per_query;
     if (per_query < 1) per_query = 1;
     dim3 grid(per_query, batch);
-    rescore_kernel<<<grid, wpb * 32, 0, stream>>>(s->f32, s->norm64, s->live, s->dim, pool, kprime,
-                                                 metric, q_raw, cert, k, exact_ws);
+    const bool pdl = batch <= kWideDenseMaxBatch;
+    CMW_CUDA_OK(launch_kernel(rescore_kernel, grid, dim3(wpb * 32), 0, stream, pdl, s->f32, s->norm64, s->live, s->dim,
+                              pool, kprime, metric, q_raw, cert, k, exact_ws));
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     const size_t smem = (size_t)next_pow2_host(kprime) * 16;
-    select_kernel<<<batch, 256, smem, stream>>>(pool, k, kprime, exact_ws, cert, s->id_offset, out_scores,
-                                               out_ids, out_scores64, out_flags, out_aux);
+    CMW_CUDA_OK(launch_kernel(select_kernel, dim3(batch), dim3(256), smem, stream, pdl, pool, k, kprime, exact_ws, cert,
+                              s->id_offset, out_scores, out_ids, out_scores64, out_flags, out_aux));
     CMW_LAUNCHED();
     CMW_CUDA_OK(cudaGetLastError());
     return 0;

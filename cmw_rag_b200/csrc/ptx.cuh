@@ -25,6 +25,15 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---- programmatic dependent launch -----------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its
+// predecessor in the stream is still running; pdl_wait() holds it until that predecessor has completed and its
+// writes are visible (a no-op for a plain launch), pdl_launch_dependents() lets the NEXT kernel in the stream do
+// the same with respect to this one.  Used for the chain of small dependent kernels of a small-batch search:
+// launch latency and prologues (barrier init, TMEM allocation, descriptor prefetch) overlap the predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- mbarrier ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

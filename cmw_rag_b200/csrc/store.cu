@@ -23,6 +23,8 @@ namespace cmw {
 
 static thread_local std::string t_last_error;
 std::atomic<long long> g_kernel_launches{0};
+std::atomic<int> g_pdl{1};  // programmatic dependent launch of the small-batch kernel chain (option "pdl")
+thread_local int t_pdl_search = 0;  // set per search by run_filter_half: this search's kernels are launched that way
 Options g_opt;
 
 void set_error(const char* fmt, ...) {
@@ -242,6 +244,7 @@ int cmw_set_option(const char* name, double value) {
     else if (!strcmp(name, "repair")) g_opt.repair = value;
     else if (!strcmp(name, "host_overlap")) g_opt.host_overlap = value;
     else if (!strcmp(name, "wide_dense")) g_opt.wide_dense = value;
+    else if (!strcmp(name, "pdl")) g_pdl.store(value != 0 ? 1 : 0);
     else if (!strcmp(name, "scan_permute")) g_opt.scan_permute = value;
     else if (!strcmp(name, "gemm_2cta")) g_opt.gemm_2cta = value;
     else if (!strcmp(name, "gemm_clc")) g_opt.gemm_clc = value;
@@ -267,6 +270,7 @@ double cmw_get_option(const char* name) {
     if (!strcmp(name, "repair")) return g_opt.repair;
     if (!strcmp(name, "host_overlap")) return g_opt.host_overlap;
     if (!strcmp(name, "wide_dense")) return g_opt.wide_dense;
+    if (!strcmp(name, "pdl")) return (double)g_pdl.load();
     if (!strcmp(name, "scan_permute")) return g_opt.scan_permute;
     if (!strcmp(name, "gemm_2cta")) return g_opt.gemm_2cta;
     if (!strcmp(name, "gemm_clc")) return g_opt.gemm_clc;

@@ -278,6 +278,10 @@ int cmw_profile_read(double* ms, int64_t* counts, int n);
  *   "repair" (2)              cmw_search_host repair chain for flagged queries: 0 off, 1 stage 1, 2 both stages
  *   "wide_dense" (1)          batches up to 32: first slab of up to 131072 rows through a scratch matrix, then the rest of
  *                             the corpus in one launch when the expected admissions fit the pool
+ *   "pdl" (1)                 batches up to 32 over a collection that fits one wide first slab: the chain of small
+ *                             dependent kernels that IS such a search is launched with programmatic stream
+ *                             serialization (each kernel's launch and prologue overlap its predecessor's tail;
+ *                             griddepcontrol.wait before the first dependent access)
  *   "scan_permute" (1)        K2 scans the row tiles in a stride permutation: every slab is a representative sample
  *                             of the corpus, the admission thresholds hold whatever order the corpus is stored in
  *   "host_overlap" (0)        pipelined host API: 1 = a ticket's finalisation runs next to the following ticket's filter (measured: no gain)
