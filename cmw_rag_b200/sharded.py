@@ -152,21 +152,44 @@ class PeerGather:
         nbytes = int(lib.cmw_peer_gather_bytes(self.world, self.max_bytes))
         own = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
-        N.check(lib.cmw_peer_alloc(self.device, nbytes, ctypes.byref(own), handle), "cmw_peer_alloc")
+        failure = None
+        try:
+            N.check(lib.cmw_peer_alloc(self.device, nbytes, ctypes.byref(own), handle), "cmw_peer_alloc")
+        except Exception as exc:  # noqa: BLE001 -- decided together below: a rank must not leave the others waiting
+            failure = exc
         handles: list = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle.raw), group=group)
-        self._own = own
+        dist.all_gather_object(handles, bytes(handle.raw) if failure is None else None, group=group)
+        self._own = own if failure is None else None
         self._opened = []
         ptrs = []
+        if failure is None and any(h is None for h in handles):
+            failure = RuntimeError("a peer could not allocate its buffer")
         for g in range(self.world):
+            if failure is not None:
+                break
             if g == self.rank:
                 ptrs.append(own.value)
                 continue
             p = ctypes.c_void_p()
-            N.check(lib.cmw_peer_open(self.device, ctypes.create_string_buffer(handles[g], 64), ctypes.byref(p)),
-                    "cmw_peer_open")
+            try:
+                N.check(lib.cmw_peer_open(self.device, ctypes.create_string_buffer(handles[g], 64), ctypes.byref(p)),
+                        "cmw_peer_open")
+            except Exception as exc:  # noqa: BLE001
+                failure = exc
+                break
             self._opened.append(p)
             ptrs.append(p.value)
+        # one verdict for all ranks (a rank that cannot map a peer -- no P2P path, IPC disabled -- must not leave the
+        # others in a collective): every rank raises, or none
+        ok = torch.tensor([0 if failure is not None else 1], dtype=torch.int32, device=f"cuda:{self.device}")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            for p in self._opened:
+                lib.cmw_peer_close(p)
+            if self._own is not None:
+                lib.cmw_peer_free(own)
+            self._own, self._opened = None, []
+            raise RuntimeError(f"PeerGather: peer memory unavailable on at least one rank ({failure!r} on rank {self.rank})")
         self._ptrs = (ctypes.c_void_p * self.world)(*ptrs)
         self.status = torch.zeros((1,), dtype=torch.int32, device=f"cuda:{self.device}")
         self.epoch = 0
