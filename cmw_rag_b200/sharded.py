@@ -33,6 +33,16 @@ def shard_bounds(n_rows: int, world: int) -> list[tuple[int, int]]:
     return out
 
 
+def upload_slice(batch: int, world: int, rank: int) -> tuple[int, int, int]:
+    """The rows of a replicated host batch that rank ``rank`` uploads itself (the others arrive through the NVLink
+    all-gather): ``(lo, hi, per)`` with ``per = ceil(batch / world)`` rows per rank in the padded gather buffer and
+    ``[lo, hi)`` the real rows of this rank's piece (empty for the last ranks of a short batch)."""
+    per = (batch + world - 1) // world if world > 0 else batch
+    lo = min(batch, rank * per)
+    hi = min(batch, lo + per)
+    return lo, hi, per
+
+
 class PeerExchange:
     """The NVLink peer-memory alternative to all-gather + merge (cmw_exchange_merge, exchange.cu).
 
@@ -369,7 +379,7 @@ class ShardedSearcher:
         if out is None:
             out = (np.empty((b, k), np.float32), np.empty((b, k), np.int64), np.zeros((b,), np.int32))
         sliced = upload == "sliced" and self.world > 1 and b >= self.world
-        per = (b + self.world - 1) // self.world if sliced else b
+        lo, hi, per = upload_slice(b, self.world, self.rank) if sliced else (0, b, b)
         rows_buf = per * self.world if sliced else b
         # query buffers are the searcher's own and go round (an allocation in flight -- cudaMalloc behind the
         # caching allocator -- stalls the host for tens of milliseconds while the GPU is busy)
@@ -379,8 +389,6 @@ class ShardedSearcher:
             if sliced:
                 if self._upload_group is None:  # its own communicator: independent of the search's exchanges
                     self._upload_group = self.dist.new_group(backend="nccl") if self.group is None else self.group
-                lo = min(b, self.rank * per)
-                hi = min(b, lo + per)
                 mine = qbuf[self.rank * per:(self.rank + 1) * per]
                 if hi > lo:
                     mine[: hi - lo].copy_(src[lo:hi], non_blocking=True)
@@ -404,8 +412,7 @@ class ShardedSearcher:
             e_out.record(down)
         # the ticket keeps every device tensor alive until the wait: nothing allocated on one stream is handed
         # back to the caching allocator while another stream may still be reading it
-        return {"event": e_out, "out": out, "keep": (src, ms, mi, fl), "q": qbuf,
-                "h2d_bytes": (min(b, self.rank * per + per) - min(b, self.rank * per) if sliced else b) * dim * 4}
+        return {"event": e_out, "out": out, "keep": (src, ms, mi, fl), "q": qbuf, "h2d_bytes": (hi - lo) * dim * 4}
 
     def search_host_wait(self, ticket):
         ticket["event"].synchronize()

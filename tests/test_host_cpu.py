@@ -646,3 +646,23 @@ def test_collection_registry_names_cache_and_persistence(monkeypatch, tmp_path):
     assert again.count() == 10 and again.similarity_search(e5[3], k=1)[0].page_content == "five3"
     assert reg2.get_store("v6").count() == 0  # never saved: starts empty
     reg2.close()
+
+
+def test_upload_slices_partition_the_batch():
+    """Row-sharded host form: every rank uploads its own piece of the replicated batch and the NVLink all-gather
+    completes it -- the pieces must partition [0, batch) for any batch / world, short and empty pieces included,
+    and sit at rank * per in the padded gather buffer."""
+    from cmw_rag_b200.sharded import upload_slice
+
+    for world in (1, 2, 3, 4, 7, 8):
+        for batch in (1, 2, 7, 8, 9, 37, 64, 1000, 4096, 4097):
+            covered = []
+            per0 = None
+            for rank in range(world):
+                lo, hi, per = upload_slice(batch, world, rank)
+                per0 = per if per0 is None else per0
+                assert per == per0 and per * world >= batch and (per - 1) * world < batch
+                assert 0 <= lo <= hi <= batch and hi - lo <= per
+                assert lo == min(batch, rank * per)  # the piece starts at its slot of the padded buffer
+                covered.extend(range(lo, hi))
+            assert covered == list(range(batch)), (world, batch)
